@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — block-level bloom probes/s on B200 (BASELINE.json metric), with roofline
+and CPU baseline.
+
+A "step" is one pass of the hot path over one batch: a 1 000-key batch (500 keys sampled
+from the corpus, 500 absent, kinds as sampled / 1:1:1) probed against every block of a
+10 M-row synthetic log corpus resident in HBM (BASELINE config 2).  Two layouts of the same
+rows exist: 2b = 1 000 blocks x 10 000 rows (merged files, ~70 KB of bitsets
+per block, HBM-bound) and 2a = 10 000 blocks x 1 000 rows (flush-shaped, ~7 KB per block,
+on the ALU/latency ridge).  `--workload` picks the headline one; the other is reported under
+"also".  Per-GPU work is fixed as N grows (every rank owns its own 10 M-row shard): weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 2b|2a] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_blocks, rows_per_block, blocks_per_file)
+    "2b": (1000, 10000, 100),
+    "2a": (10000, 1000, 100),
+}
+FPR = 0.001
+N_KEYS = 1000
+L2_BYTES = 126 * 1024 * 1024
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------- inputs ---
+def gen_corpus(workload: str, rank: int, scale: float = 1.0):
+    from oracle.corpus import SynthCorpus
+    n_blocks, rows, bpf = WORKLOADS[workload]
+    n_blocks = max(bpf, int(n_blocks * scale) // bpf * bpf)
+    t = time.time()
+    c = SynthCorpus(42, rank * n_blocks, n_blocks, rows, bpf)
+    log(f"corpus {workload}: {n_blocks} blocks x {rows} rows, {c.n_keys} distinct keys, "
+        f"{int(c.key_off[-1]) / 1e6:.0f} MB of key bytes ({time.time() - t:.1f}s)")
+    return c
+
+
+def size_filters(c, bs):
+    """(m,k) per (block,kind) from exact distinct counts (ingest.go:139-140)."""
+    from bloomsearch_b200 import _native as N
+    counts = np.diff(c.group_begin).astype(np.int64)
+    cache = {}
+    desc = np.zeros(len(counts), dtype=N.DESC_DTYPE)
+    wo = 0
+    for g, n in enumerate(counts):
+        n = int(max(n, 1))
+        mk = cache.get(n)
+        if mk is None:
+            mk = cache[n] = bs.estimate_parameters(n, FPR)
+        desc[g] = (mk[0], mk[1], wo)
+        wo += (mk[0] + 63) // 64
+    return desc, wo
+
+
+def make_batch(c, seed: int):
+    """500 present keys sampled from the corpus (kind = the set they came from) + 500 absent."""
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(c.n_keys, N_KEYS // 2, replace=False))
+    group_of = np.searchsorted(c.group_begin, idx, side="right") - 1
+    keys = [c.key(int(i)) for i in idx]
+    kinds = [int(g % 3) for g in group_of]
+    for i in range(N_KEYS - len(keys)):
+        keys.append(b"absent%d" % i)
+        kinds.append(i % 3)
+    perm = rng.permutation(len(keys))
+    return [keys[i] for i in perm], np.array([kinds[i] for i in perm], dtype=np.uint8)
+
+
+# ------------------------------------------------------------ clock sampler ---
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples = []
+        self._stop = threading.Event()
+        self.gpu = gpu_index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------- CPU baseline ---
+def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=8.0):
+    """Oracle port of the Go path on the host cores: per block parseFilterSection (CRC32C + BE
+    decode) then TestString for every key — a bounded sample of the same workload."""
+    from oracle import cref
+    threads = os.cpu_count() or 1
+    blob, off = cref.pack_keys(keys)
+    probe_units = min(n_units_total, max(threads, 8))
+    sec, sec_off = cref.encode_sections(desc[:probe_units * 3], words, probe_units)
+    t = time.perf_counter()
+    cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+    dt = max(time.perf_counter() - t, 1e-6)
+    n_sample = int(min(n_units_total, max(probe_units, probe_units * target_s / dt)))
+    sec, sec_off = cref.encode_sections(desc[:n_sample * 3], words, n_sample)
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    probes = n_sample * len(keys)
+    return {"value": probes / best, "unit": "probes/s", "cores": threads, "kind": "port",
+            "sample": f"{n_sample} of {n_units_total} blocks x {len(keys)} keys, section decode + probe per block, "
+                      f"{threads} threads, best of 2 ({best:.2f}s)"}, sec.nbytes
+
+
+# --------------------------------------------------------------------- main ---
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of the Go
+    engine's per-block loop: parseFilterSection + TestString) on the host cores.  The GPU is used
+    only to BUILD the corpus' filters (input preparation, untimed)."""
+    if rank != 0:
+        return
+    import bloomsearch_b200 as bs
+    from oracle import cref
+    wl = args.workload
+    c = gen_corpus(wl, 0, scale=0.1)  # bounded sample: 1/10 of the blocks per step
+    desc, n_words = size_filters(c, bs)
+    words = cref.build_filters(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc,
+                               n_words, n_threads=os.cpu_count() or 1)
+    keys, kinds = make_batch(c, 7)
+    blob, off = cref.pack_keys(keys)
+    threads = os.cpu_count() or 1
+    n_units = c.n_blocks
+    sec, sec_off = cref.encode_sections(desc, words, n_units)
+    for _ in range(args.warmup):
+        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_units * len(keys) / dt
+    sample = (f"{n_units} blocks ({wl} layout, 1/10 of the corpus) x {len(keys)} keys per step; per block: section "
+              f"CRC32C + BE decode, then TestString per key; {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "bloom probes/sec (block-level)", "value": value, "unit": "probes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"config2-{wl}: 10M-row log corpus, fpr 0.001, 1k-key batch (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "probes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="2b", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=8, help="distinct HBM copies cycled so every step misses L2")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary layout")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import bloomsearch_b200 as bs
+    from bloomsearch_b200 import _native as N
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = bs.Context(local_rank)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    results = {}
+    cpu = None
+    for wl in [args.workload] + ([] if args.no_also else [w for w in WORKLOADS if w != args.workload]):
+        headline = wl == args.workload
+        c = gen_corpus(wl, rank)
+        desc, n_words = size_filters(c, bs)
+        t = time.time()
+        words = ctx.build(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc, n_words)
+        log(f"GPU-built {len(desc)} filters, {n_words * 8 / 1e6:.1f} MB of bitsets ({time.time() - t:.1f}s incl. PCIe)")
+        keys, kinds = make_batch(c, 7 + rank)
+        n_units = c.n_blocks
+        # spot parity against the oracle before timing anything
+        from oracle import cref
+        chk = min(n_units, 24)
+        chk_words_end = int(desc[chk * 3 - 1]["word_off"]) + (int(desc[chk * 3 - 1]["m"]) + 63) // 64
+        want = cref.build_filters(c.blob, c.key_off, c.group_begin[:chk * 3 + 1], np.arange(chk * 3, dtype=np.uint32),
+                                  None, desc[:chk * 3], chk_words_end)
+        assert np.array_equal(words[:chk_words_end], want), "GPU-built filters differ from the oracle"
+        blob, off = N.pack_keys(keys)
+        want_m = cref.probe_matrix(desc[:chk * 3], words, chk, blob, off, kinds, n_threads=4)
+
+        n_rep = max(1, args.replicas)
+        corpora = [bs.Corpus(ctx, desc, words) for _ in range(n_rep)]
+        bitset_bytes = corpora[0].bitset_bytes(7)
+        queries = [bs.Query(cp, keys, kinds, None) for cp in corpora]
+        queries[0].run(N.PROBE_AUTO)
+        got_m, got_mask = queries[0].fetch()
+        assert np.array_equal(got_m[:chk], want_m), "GPU probe matrix differs from the oracle"
+        assert bs.unpack_mask(got_mask, n_units).all()
+        launches_per_step = queries[0].launches()
+
+        # ---- device-timed steps, inputs resident in HBM; replicas cycled so no step hits L2 ----
+        for i in range(args.warmup):
+            queries[i % n_rep].run(N.PROBE_AUTO)
+        barrier()
+        with ClockSampler(local_rank) as clk:
+            ctx.timer_begin()
+            for i in range(args.steps):
+                queries[i % n_rep].run(N.PROBE_AUTO)
+            ms = ctx.timer_end()
+            barrier()
+            # keep the sampler alive for at least ~1.5 s of load so it sees clocks under load
+            t_end = time.time() + max(0.0, 1.5 - ms / 1e3)
+            i = 0
+            while time.time() < t_end:
+                queries[i % n_rep].run(N.PROBE_AUTO)
+                i += 1
+                if i % 64 == 0:
+                    ctx.synchronize()
+            ctx.synchronize()
+        ms = max_over_ranks(ms)
+        probes_per_step = n_units * len(keys)
+        total_probes = sum_over_ranks(float(probes_per_step))
+        value = total_probes * args.steps / (ms / 1e3)
+
+        # ---- dominant kernel alone (probe, no mask kernel): roofline ----
+        for i in range(args.warmup):
+            queries[i % n_rep].run(N.PROBE_AUTO | N.RUN_MATRIX_ONLY)
+        ctx.synchronize()
+        ctx.timer_begin()
+        for i in range(args.steps):
+            queries[i % n_rep].run(N.PROBE_AUTO | N.RUN_MATRIX_ONLY)
+        k_ms = ctx.timer_end() / args.steps
+        algo_bytes = bitset_bytes + 32 * len(keys) + (len(keys) * n_units + 7) // 8
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = algo_bytes / (k_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "probe_staged_kernel", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": algo_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+
+        # ---- end to end through the C ABI call a host makes: host keys in, host masks out ----
+        e2e_steps = max(10, min(args.steps, 100))
+        m_bytes = n_units * ((len(keys) + 63) // 64) * 8
+        for i in range(3):
+            corpora[i % n_rep].probe(keys, kinds, None)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            corpora[i % n_rep].probe(keys, kinds, None)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": total_probes * e2e_steps / e2e_s, "unit": "probes/s",
+               "h2d_bytes_per_step": int(blob.nbytes + off.nbytes + kinds.nbytes),
+               "d2h_bytes_per_step": int(m_bytes + ((n_units + 63) // 64) * 8), "ms_per_step": e2e_s / e2e_steps * 1e3,
+               "what": "bsg_probe(): host key bytes -> H2D, hash, probe, D2H of the (block x key) matrix + mask"}
+
+        if headline and rank == 0 and not args.no_cpu:
+            cpu, _ = cpu_probe_rate(desc, words, n_units, keys, kinds)
+
+        results[wl] = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e,
+                       "clocks": clk.summary(), "launches_per_step": launches_per_step,
+                       "bitset_mb": bitset_bytes / 1e6, "n_units_per_gpu": n_units, "replicas": n_rep}
+        for q in queries:
+            q.close()
+        for cp in corpora:
+            cp.close()
+        del words, c
+
+    if rank == 0:
+        r = results[args.workload]
+        n_blocks, rows, _ = WORKLOADS[args.workload]
+        out = {
+            "metric": "bloom probes/sec (block-level)", "value": r["value"], "unit": "probes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"config2-{args.workload}: 10M-row synthetic log corpus per GPU as {n_blocks} blocks x "
+                                   f"{rows} rows, fpr 0.001, batched 1k-key block probe (500 present / 500 absent)",
+                       "keys_per_batch": N_KEYS, "blocks_per_gpu": r["n_units_per_gpu"],
+                       "bitset_mb_per_gpu": r["bitset_mb"],
+                       "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per step "
+                             f"({r['replicas'] * r['bitset_mb']:.0f} MB > 126 MB L2): inputs larger than L2",
+                       "sharding": "by file, one shard per GPU, no data-path collective"},
+            "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "clocks": r["clocks"],
+            "gpu_launches": r["launches_per_step"] * args.steps,
+            "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],
+                         "e2e": v["e2e"]} for w, v in results.items() if w != args.workload},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

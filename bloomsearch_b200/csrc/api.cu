@@ -1,0 +1,763 @@
+// C ABI of libbloomgpu.so (include/bloomgpu.h): context, corpus residency,
+// query objects, build and probe entry points.  Host-side logic only — all the
+// arithmetic lives in the kernels_*.cu files.  There is deliberately no CPU
+// path: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bsg_internal.h"
+
+using namespace bsg;
+
+// ------------------------------------------------------------------ errors ---
+static thread_local std::string t_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? BSG_ERR_NOMEM : BSG_ERR_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(_e));                                                    \
+    } while (0)
+
+extern "C" int bsg_abi_version(void) { return BSG_ABI_VERSION; }
+
+extern "C" const char* bsg_strerror(int code) {
+    switch (code) {
+    case BSG_OK: return "ok";
+    case BSG_ERR_INVALID: return "invalid argument";
+    case BSG_ERR_CUDA: return "CUDA error (no device, or runtime failure)";
+    case BSG_ERR_NOMEM: return "out of memory";
+    case BSG_ERR_FORMAT: return "malformed filter section";
+    case BSG_ERR_UNSUPPORTED: return "unsupported";
+    case BSG_ERR_COMM: return "NCCL error";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char* bsg_last_error(void) { return t_last_error.c_str(); }
+
+// ----------------------------------------------------------------- context ---
+struct bsg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t cur_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    std::vector<cudaStream_t> stream_pool;
+    void* comm = nullptr;  // bsg_comm.cpp
+    int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
+    int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
+};
+
+extern "C" void bsg_comm_destroy_internal(void* comm);
+
+static cudaStream_t pool_get(bsg_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->stream_pool.empty()) {
+        cudaStream_t s = ctx->stream_pool.back();
+        ctx->stream_pool.pop_back();
+        return s;
+    }
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return s;
+}
+static void pool_put(bsg_ctx* ctx, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stream_pool.push_back(s);
+}
+
+extern "C" int bsg_create(int device, bsg_ctx** out) {
+    if (!out) return fail(BSG_ERR_INVALID, "bsg_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(BSG_ERR_CUDA, "no CUDA device available (%s); libbloomgpu has no CPU fallback",
+                    e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(BSG_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    bsg_ctx* ctx = new (std::nothrow) bsg_ctx();
+    if (!ctx) return fail(BSG_ERR_NOMEM, "ctx alloc");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->total_mem = prop.totalGlobalMem;
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(BSG_ERR_UNSUPPORTED, "device compute capability %d.%d < 10.0: this library is sm_100a only",
+                    prop.major, prop.minor);
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->cur_stream = ctx->own_stream;
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(probe_staged_configure(ctx->max_smem_optin));
+    CUDA_TRY(build_configure(ctx->max_smem_optin));
+    if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
+    if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
+    *out = ctx;
+    return BSG_OK;
+}
+
+extern "C" void bsg_destroy(bsg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
+    for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" int bsg_set_stream(bsg_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    ctx->cur_stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return BSG_OK;
+}
+
+extern "C" int bsg_synchronize(bsg_ctx* ctx) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->cur_stream));
+    return BSG_OK;
+}
+
+extern "C" int bsg_device_info(bsg_ctx* ctx, int* sm_count, size_t* smem_optin, size_t* total_mem, int* cc_major,
+                               int* cc_minor) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (smem_optin) *smem_optin = static_cast<size_t>(ctx->max_smem_optin);
+    if (total_mem) *total_mem = ctx->total_mem;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return BSG_OK;
+}
+
+extern "C" int bsg_timer_begin(bsg_ctx* ctx) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->cur_stream));
+    return BSG_OK;
+}
+
+extern "C" int bsg_timer_end(bsg_ctx* ctx, float* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->cur_stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return BSG_OK;
+}
+
+// ------------------------------------------------------------------ sizing ---
+extern "C" void bsg_estimate(uint64_t n, double fpr, uint64_t* m, uint64_t* k) {
+    // bloom.EstimateParameters (float64) followed by New()'s clamp to >= 1.  A Go host
+    // calls the library itself and passes integers; this helper is for other hosts.
+    const double ln2 = std::log(2.0);
+    const double md = std::ceil(-1.0 * static_cast<double>(n) * std::log(fpr) / std::pow(ln2, 2.0));
+    const uint64_t mm = static_cast<uint64_t>(md);
+    const double kd = std::ceil(ln2 * static_cast<double>(mm) / static_cast<double>(n));
+    const uint64_t kk = static_cast<uint64_t>(kd);
+    if (m) *m = mm < 1 ? 1 : mm;
+    if (k) *k = kk < 1 ? 1 : kk;
+}
+
+// ----------------------------------------------------------- small helpers ---
+namespace {
+
+template <typename T>
+struct DevBuf {  // RAII device allocation
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T)); }
+    T* release() { T* r = p; p = nullptr; return r; }
+};
+
+constexpr uint64_t kMaxM = 1ull << 62;
+constexpr uint64_t kKeyPad = 16;  // WordReader may read up to the 8-byte boundary + one word past a key
+
+inline uint64_t words_for(uint64_t m) { return (m + 63) >> 6; }
+inline uint64_t even_up(uint64_t w) { return (w + 1) & ~1ull; }
+
+int validate_filter(const bsg_filter_desc& d, uint64_t n_words, const char* what, uint64_t idx) {
+    if (d.m == 0) return BSG_OK;
+    if (d.m > kMaxM) return fail(BSG_ERR_INVALID, "%s %llu: m=%llu exceeds 2^62", what, (unsigned long long)idx,
+                                 (unsigned long long)d.m);
+    if (d.k == 0 || d.k > 0x7fffffffull)
+        return fail(BSG_ERR_INVALID, "%s %llu: k=%llu out of range", what, (unsigned long long)idx,
+                    (unsigned long long)d.k);
+    const uint64_t nw = words_for(d.m);
+    if (nw > 0xffffffffull) return fail(BSG_ERR_INVALID, "%s %llu: filter too large", what, (unsigned long long)idx);
+    if (d.word_off > n_words || nw > n_words - d.word_off)
+        return fail(BSG_ERR_INVALID, "%s %llu: words [%llu,+%llu) outside the words array (%llu)", what,
+                    (unsigned long long)idx, (unsigned long long)d.word_off, (unsigned long long)nw,
+                    (unsigned long long)n_words);
+    return BSG_OK;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------- hash ---
+extern "C" int bsg_hash_keys(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
+                             uint64_t* out_hashes) {
+    if (!ctx || !key_off || !out_hashes) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (n_keys == 0) return BSG_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t nbytes = key_off[n_keys];
+    if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
+    for (uint64_t i = 0; i < n_keys; ++i)
+        if (key_off[i + 1] < key_off[i] || key_off[i + 1] - key_off[i] > 0xffffffffull)
+            return fail(BSG_ERR_INVALID, "key_off not monotone at %llu", (unsigned long long)i);
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    DevBuf<uint8_t> d_keys;
+    DevBuf<uint64_t> d_off, d_h;
+    int rc = BSG_OK;
+    do {
+        if (d_keys.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_keys + 1) != cudaSuccess ||
+            d_h.alloc(n_keys * 4) != cudaSuccess) { rc = fail(BSG_ERR_NOMEM, "device alloc"); break; }
+        cudaError_t e = cudaSuccess;
+        if (nbytes) e = cudaMemcpyAsync(d_keys.p, keys, nbytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, key_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = launch_hash_keys(d_keys.p, d_off.p, n_keys, d_h.p, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_hashes, d_h.p, n_keys * 32, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_hash_keys: %s", cudaGetErrorString(e));
+    } while (0);
+    pool_put(ctx, s);
+    return rc;
+}
+
+// ------------------------------------------------------------------- build ---
+extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
+                         const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_filter,
+                         const uint32_t* group_filter2, const bsg_filter_desc* desc, uint32_t n_filters,
+                         uint64_t* out_words, uint64_t n_words) {
+    if (!ctx || !key_off || !desc || !out_words || (n_groups && (!group_begin || !group_filter)))
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
+    if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
+    for (uint64_t i = 0; i < n_keys; ++i)
+        if (key_off[i + 1] < key_off[i] || key_off[i + 1] - key_off[i] > 0xffffffffull)
+            return fail(BSG_ERR_INVALID, "key_off not monotone at %llu", (unsigned long long)i);
+    std::vector<BuildFilter> bf(n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+        if (desc[f].m == 0) return fail(BSG_ERR_INVALID, "filter %u: m == 0", f);
+        int rc = validate_filter(desc[f], n_words, "filter", f);
+        if (rc) return rc;
+        bf[f].word_off = desc[f].word_off;
+        bf[f].m = desc[f].m;
+        bf[f].inv = reciprocal(desc[f].m);
+        bf[f].k = static_cast<uint32_t>(desc[f].k);
+        bf[f].nwords = static_cast<uint32_t>(words_for(desc[f].m));
+    }
+    // Split oversized groups so one CTA never owns more than kSplit keys (sub-groups
+    // share the filters; the staged bitset is merged with RED.OR).  group_begin is a
+    // CSR array, so sub-group boundaries stay contiguous.
+    constexpr uint64_t kSplit = 16384;
+    std::vector<uint64_t> gbe;
+    std::vector<uint32_t> gf, gf2;
+    gbe.reserve(static_cast<size_t>(n_groups) + 1);
+    gf.reserve(n_groups);
+    if (group_filter2) gf2.reserve(n_groups);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const uint64_t b = group_begin[g], e = group_begin[g + 1];
+        if (e < b || e > n_keys) return fail(BSG_ERR_INVALID, "group %u: key range [%llu,%llu) invalid", g,
+                                             (unsigned long long)b, (unsigned long long)e);
+        if (group_filter[g] >= n_filters) return fail(BSG_ERR_INVALID, "group %u: filter id out of range", g);
+        if (group_filter2 && group_filter2[g] != BSG_NO_FILTER && group_filter2[g] >= n_filters)
+            return fail(BSG_ERR_INVALID, "group %u: secondary filter id out of range", g);
+        for (uint64_t s0 = b; s0 < e; s0 += kSplit) {
+            gbe.push_back(s0);
+            gf.push_back(group_filter[g]);
+            if (group_filter2) gf2.push_back(group_filter2[g]);
+        }
+    }
+    gbe.push_back(n_groups ? group_begin[n_groups] : 0);
+    if (gf.size() > 0x7fffffffull) return fail(BSG_ERR_INVALID, "too many groups");
+    const uint32_t n_sub = static_cast<uint32_t>(gf.size());
+
+    // shared-memory staging capacity: largest primary filter that still lets 2 CTAs share an SM
+    const uint32_t cap_limit = static_cast<uint32_t>(std::min<int>(ctx->max_smem_optin, 100 * 1024));
+    uint32_t smem_cap = 0;
+    for (uint32_t g = 0; g < n_sub; ++g) {
+        const uint64_t bytes = static_cast<uint64_t>(bf[gf[g]].nwords) * 8;
+        if (bytes <= cap_limit) smem_cap = std::max<uint32_t>(smem_cap, static_cast<uint32_t>((bytes + 15) & ~15ull));
+    }
+
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    DevBuf<uint8_t> d_keys;
+    DevBuf<uint64_t> d_off, d_gb, d_out;
+    DevBuf<uint32_t> d_gf, d_gf2;
+    DevBuf<BuildFilter> d_bf;
+    int rc = BSG_OK;
+    do {
+        if (d_keys.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_keys + 1) != cudaSuccess ||
+            d_gb.alloc(gbe.size()) != cudaSuccess || d_out.alloc(n_words) != cudaSuccess ||
+            d_gf.alloc(n_sub) != cudaSuccess || d_bf.alloc(n_filters) != cudaSuccess ||
+            (group_filter2 && d_gf2.alloc(n_sub) != cudaSuccess)) { rc = fail(BSG_ERR_NOMEM, "device alloc"); break; }
+        cudaError_t e = cudaSuccess;
+        if (nbytes) e = cudaMemcpyAsync(d_keys.p, keys, nbytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, key_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gb.p, gbe.data(), gbe.size() * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gf.p, gf.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_sub && group_filter2)
+            e = cudaMemcpyAsync(d_gf2.p, gf2.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_filters)
+            e = cudaMemcpyAsync(d_bf.p, bf.data(), n_filters * sizeof(BuildFilter), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_out.p, 0, std::max<uint64_t>(n_words, 1) * 8, s);
+        if (e == cudaSuccess)
+            e = launch_build(d_keys.p, d_off.p, d_gb.p, n_sub, d_gf.p, group_filter2 ? d_gf2.p : nullptr, d_bf.p,
+                             d_out.p, smem_cap, s);
+        if (e == cudaSuccess && n_words) e = cudaMemcpyAsync(out_words, d_out.p, n_words * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_build: %s", cudaGetErrorString(e));
+    } while (0);
+    pool_put(ctx, s);
+    return rc;
+}
+
+// ------------------------------------------------------------------ corpus ---
+struct bsg_corpus {
+    int device = 0;
+    uint64_t n_units = 0;
+    DevFilter* d_udesc = nullptr;
+    UnitTab* d_utab = nullptr;
+    uint64_t* d_words = nullptr;
+    uint64_t total_words = 0;
+    uint32_t* d_staged_list = nullptr;  // nullptr when every unit is staged (identity list)
+    uint32_t n_staged = 0;
+    uint32_t* d_gather_list = nullptr;
+    uint32_t n_gather = 0;
+    uint32_t stage_cap_bytes = 0;  // largest staged unit (all kinds), 16-byte multiple
+    uint64_t kind_bytes[3] = {0, 0, 0};         // Σ 8*ceil(m/64) per kind
+    uint64_t staged_kind_bytes[3] = {0, 0, 0};  // same, staged units only (padded words)
+    std::vector<bsg_filter_desc> h_desc;        // caller's (m,k) with word_off in the device layout
+};
+
+extern "C" void bsg_corpus_free(bsg_corpus* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_udesc);
+    cudaFree(c->d_utab);
+    cudaFree(c->d_words);
+    cudaFree(c->d_staged_list);
+    cudaFree(c->d_gather_list);
+    delete c;
+}
+
+extern "C" uint64_t bsg_corpus_units(const bsg_corpus* c) { return c ? c->n_units : 0; }
+
+extern "C" uint64_t bsg_corpus_bitset_bytes(const bsg_corpus* c, uint32_t kind_mask) {
+    if (!c) return 0;
+    uint64_t t = 0;
+    for (int k = 0; k < 3; ++k)
+        if (kind_mask & (1u << k)) t += c->kind_bytes[k];
+    return t;
+}
+
+extern "C" int bsg_corpus_unit_desc(const bsg_corpus* c, uint64_t unit, bsg_filter_desc out_desc[3]) {
+    if (!c || !out_desc || unit >= c->n_units) return fail(BSG_ERR_INVALID, "bad unit");
+    for (int k = 0; k < 3; ++k) out_desc[k] = c->h_desc[unit * 3 + k];
+    return BSG_OK;
+}
+
+namespace {
+
+// Shared tail of the two corpus loaders: given per-slot (m,k) [m==0 absent], lays
+// the corpus out, uploads descriptor tables and decides staged vs gather units.
+struct Layout {
+    std::vector<DevFilter> udesc;
+    std::vector<UnitTab> utab;
+    uint64_t total_words = 0;
+};
+
+int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
+    L.udesc.resize(n_units * 3);
+    L.utab.resize(n_units);
+    uint64_t cur = 0;
+    for (uint64_t u = 0; u < n_units; ++u) {
+        UnitTab& t = L.utab[u];
+        t.word_base = cur;
+        t.total = 0;
+        t.reserved = 0;
+        uint64_t unit_words = 0;
+        for (int k = 0; k < 3; ++k) {
+            const bsg_filter_desc& d = desc[u * 3 + k];
+            DevFilter& f = L.udesc[u * 3 + k];
+            if (d.m == 0) { f = DevFilter{cur + unit_words, 0, 0, 0, 0}; t.nw[k] = 0; continue; }
+            const uint64_t nw = words_for(d.m);
+            f.word_off = cur + unit_words;
+            f.m = d.m;
+            f.inv = reciprocal(d.m);
+            f.k = static_cast<uint32_t>(d.k);
+            f.nwords = static_cast<uint32_t>(nw);
+            const uint64_t padded = even_up(nw);
+            if (unit_words + padded > 0xffffffffull) return fail(BSG_ERR_INVALID, "unit %llu too large", (unsigned long long)u);
+            t.nw[k] = static_cast<uint32_t>(padded);
+            unit_words += padded;
+        }
+        t.total = static_cast<uint32_t>(unit_words);
+        cur += unit_words;
+    }
+    L.total_words = cur;
+    return BSG_OK;
+}
+
+int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter_desc* desc, cudaStream_t s) {
+    const uint64_t n_units = c->n_units;
+    // staged vs gather: a unit is staged when at least 3 stages of its size fit
+    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - 2 * kProbeMaxStages * sizeof(uint64_t);
+    const uint64_t unit_limit = budget / 3 - kProbeStageHeaderBytes;
+    std::vector<uint32_t> staged, gather;
+    uint32_t cap = 0;
+    c->h_desc.resize(n_units * 3);
+    for (uint64_t u = 0; u < n_units; ++u) {
+        const uint64_t bytes = static_cast<uint64_t>(L.utab[u].total) * 8;
+        const bool st = bytes <= unit_limit;
+        if (st) { staged.push_back(static_cast<uint32_t>(u)); cap = std::max<uint32_t>(cap, static_cast<uint32_t>(bytes)); }
+        else gather.push_back(static_cast<uint32_t>(u));
+        for (int k = 0; k < 3; ++k) {
+            const bsg_filter_desc& d = desc[u * 3 + k];
+            c->h_desc[u * 3 + k] = bsg_filter_desc{d.m, d.m ? d.k : 0, L.udesc[u * 3 + k].word_off};
+            if (d.m) {
+                c->kind_bytes[k] += words_for(d.m) * 8;
+                if (st) c->staged_kind_bytes[k] += static_cast<uint64_t>(L.utab[u].nw[k]) * 8;
+            }
+        }
+    }
+    c->stage_cap_bytes = (cap + 15u) & ~15u;
+    c->n_staged = static_cast<uint32_t>(staged.size());
+    c->n_gather = static_cast<uint32_t>(gather.size());
+    if (!gather.empty()) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_gather_list), gather.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(c->d_gather_list, gather.data(), gather.size() * 4, cudaMemcpyHostToDevice, s));
+        if (!staged.empty()) {
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_staged_list), staged.size() * 4));
+            CUDA_TRY(cudaMemcpyAsync(c->d_staged_list, staged.data(), staged.size() * 4, cudaMemcpyHostToDevice, s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));  // vectors die with this scope
+    }
+    return BSG_OK;
+}
+
+}  // namespace
+
+extern "C" int bsg_corpus_load(bsg_ctx* ctx, const bsg_filter_desc* desc, uint64_t n_units, const uint64_t* words,
+                               uint64_t n_words, int big_endian, bsg_corpus** out) {
+    if (!ctx || !out || (n_units && !desc) || (n_words && !words)) return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (n_units > 0xfffffff0ull / 3) return fail(BSG_ERR_INVALID, "too many units");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (uint64_t f = 0; f < n_units * 3; ++f) {
+        int rc = validate_filter(desc[f], n_words, "filter slot", f);
+        if (rc) return rc;
+    }
+    Layout L;
+    int rc = make_layout(desc, n_units, L);
+    if (rc) return rc;
+    std::vector<uint64_t> src_off(n_units * 3);
+    for (uint64_t f = 0; f < n_units * 3; ++f) src_off[f] = desc[f].word_off;
+
+    bsg_corpus* c = new (std::nothrow) bsg_corpus();
+    if (!c) return fail(BSG_ERR_NOMEM, "corpus alloc");
+    c->device = ctx->device;
+    c->n_units = n_units;
+    c->total_words = L.total_words;
+    cudaStream_t s = pool_get(ctx);
+    if (!s) { delete c; return fail(BSG_ERR_CUDA, "stream create failed"); }
+    DevBuf<uint64_t> d_src, d_src_off;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_udesc), std::max<uint64_t>(n_units * 3, 1) * sizeof(DevFilter)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_utab), std::max<uint64_t>(n_units, 1) * sizeof(UnitTab)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_words), (L.total_words + 2) * 8));
+        CUDA_TRY(d_src.alloc(n_words));
+        CUDA_TRY(d_src_off.alloc(n_units * 3));
+        CUDA_TRY(cudaMemsetAsync(c->d_words, 0, (L.total_words + 2) * 8, s));
+        if (n_units) {
+            CUDA_TRY(cudaMemcpyAsync(c->d_udesc, L.udesc.data(), n_units * 3 * sizeof(DevFilter), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_utab, L.utab.data(), n_units * sizeof(UnitTab), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_src_off.p, src_off.data(), n_units * 3 * 8, cudaMemcpyHostToDevice, s));
+        }
+        if (n_words) CUDA_TRY(cudaMemcpyAsync(d_src.p, words, n_words * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_repack(d_src.p, d_src_off.p, c->d_udesc, n_units * 3, c->d_words, big_endian, s));
+        int r = finish_corpus(ctx, c, L, desc, s);
+        if (r) return r;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return BSG_OK;
+    };
+    rc = body();
+    pool_put(ctx, s);
+    if (rc) { bsg_corpus_free(c); return rc; }
+    *out = c;
+    return BSG_OK;
+}
+
+// ------------------------------------------------------------------- query ---
+struct bsg_query {
+    int device = 0;
+    uint32_t n_keys = 0;
+    uint32_t prog_len = 0;
+    uint32_t kind_mask = 0;
+    uint32_t row_words32 = 0;
+    uint64_t n_units = 0;
+    uint8_t* d_keys = nullptr;
+    uint64_t* d_key_off = nullptr;
+    uint8_t* d_kinds = nullptr;
+    uint64_t* d_hashes = nullptr;
+    bsg_expr_op* d_prog = nullptr;
+    uint32_t* d_matrix32 = nullptr;
+    uint32_t* d_mask32 = nullptr;
+    int last_launches = 0;
+};
+
+extern "C" void bsg_query_free(bsg_query* q) {
+    if (!q) return;
+    cudaSetDevice(q->device);
+    cudaFree(q->d_keys);
+    cudaFree(q->d_key_off);
+    cudaFree(q->d_kinds);
+    cudaFree(q->d_hashes);
+    cudaFree(q->d_prog);
+    cudaFree(q->d_matrix32);
+    cudaFree(q->d_mask32);
+    delete q;
+}
+
+extern "C" int bsg_query_last_launches(const bsg_query* q) { return q ? q->last_launches : 0; }
+
+static int validate_program(const bsg_expr_op* prog, uint32_t prog_len, uint32_t n_keys) {
+    uint32_t sp = 0;
+    for (uint32_t pc = 0; pc < prog_len; ++pc) {
+        const uint32_t op = prog[pc].op, arg = prog[pc].arg;
+        switch (op) {
+        case BSG_OP_LEAF:
+            if (arg >= n_keys) return fail(BSG_ERR_INVALID, "program[%u]: leaf %u >= n_keys %u", pc, arg, n_keys);
+            ++sp;
+            break;
+        case BSG_OP_TRUE: case BSG_OP_FALSE: ++sp; break;
+        case BSG_OP_AND: case BSG_OP_OR:
+            if (arg > sp) return fail(BSG_ERR_INVALID, "program[%u]: pops %u of %u", pc, arg, sp);
+            sp = sp - arg + 1;
+            break;
+        default: return fail(BSG_ERR_INVALID, "program[%u]: unknown op %u", pc, op);
+        }
+        if (sp > BSG_MAX_STACK) return fail(BSG_ERR_INVALID, "program[%u]: stack deeper than %d", pc, BSG_MAX_STACK);
+    }
+    if (sp != 1) return fail(BSG_ERR_INVALID, "program leaves %u values on the stack (want 1)", sp);
+    return BSG_OK;
+}
+
+static int query_create_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                           uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                           cudaStream_t s, bsg_query** out) {
+    if (!ctx || !corpus || !out || (n_keys && (!key_off || !key_kind)) || (prog_len && !prog))
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
+    if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
+    uint32_t kind_mask = 0;
+    for (uint32_t i = 0; i < n_keys; ++i) {
+        if (key_off[i + 1] < key_off[i] || key_off[i + 1] - key_off[i] > 0xffffffffull)
+            return fail(BSG_ERR_INVALID, "key_off not monotone at %u", i);
+        if (key_kind[i] > 2) return fail(BSG_ERR_INVALID, "key %u: kind %u unknown", i, key_kind[i]);
+        kind_mask |= 1u << key_kind[i];
+    }
+    if (prog_len) {
+        int rc = validate_program(prog, prog_len, n_keys);
+        if (rc) return rc;
+    }
+    bsg_query* q = new (std::nothrow) bsg_query();
+    if (!q) return fail(BSG_ERR_NOMEM, "query alloc");
+    q->device = ctx->device;
+    q->n_keys = n_keys;
+    q->prog_len = prog_len;
+    q->kind_mask = kind_mask;
+    q->n_units = corpus->n_units;
+    q->row_words32 = 2 * ((n_keys + 63) / 64);
+    auto body = [&]() -> int {
+        const uint64_t matrix_words32 = std::max<uint64_t>(q->n_units * q->row_words32, 1);
+        const uint64_t mask_words32 = std::max<uint64_t>(2 * ((q->n_units + 63) / 64), 1);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_keys), nbytes + kKeyPad));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_key_off), (static_cast<uint64_t>(n_keys) + 1) * 8));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_kinds), std::max<uint32_t>(n_keys, 1)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_hashes), std::max<uint64_t>(n_keys, 1) * 32));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_prog), std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_matrix32), matrix_words32 * 4));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_mask32), mask_words32 * 4));
+        CUDA_TRY(cudaMemsetAsync(q->d_matrix32, 0, matrix_words32 * 4, s));
+        CUDA_TRY(cudaMemsetAsync(q->d_mask32, 0, mask_words32 * 4, s));
+        CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
+        if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
+        if (n_keys) {
+            CUDA_TRY(cudaMemcpyAsync(q->d_key_off, key_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(launch_hash_keys(q->d_keys, q->d_key_off, n_keys, q->d_hashes, s));
+        }
+        if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+        return BSG_OK;
+    };
+    int rc = body();
+    if (rc) { bsg_query_free(q); return rc; }
+    *out = q;
+    return BSG_OK;
+}
+
+extern "C" int bsg_query_create(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                                uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                                bsg_query** out) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = query_create_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, ctx->cur_stream, out);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(ctx->cur_stream);  // host buffers may be reused by the caller
+    if (e != cudaSuccess) { bsg_query_free(*out); *out = nullptr; return fail(BSG_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+    return BSG_OK;
+}
+
+static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int path, int want_matrix, cudaStream_t s) {
+    (void)want_matrix;  // the matrix is always materialised (it is the tree kernel's input)
+    if (!ctx || !c || !q) return fail(BSG_ERR_INVALID, "NULL argument");
+    const bool matrix_only = (path & BSG_RUN_MATRIX_ONLY) != 0;
+    path &= 0xff;
+    if (q->n_units != c->n_units) return fail(BSG_ERR_INVALID, "query was created for a corpus of %llu units",
+                                              (unsigned long long)q->n_units);
+    if (path != BSG_PROBE_AUTO && path != BSG_PROBE_STAGED && path != BSG_PROBE_GATHER)
+        return fail(BSG_ERR_INVALID, "unknown path %d", path);
+    int launches = 0;
+    if (q->n_keys && c->n_units) {
+        // --- choose the data path for the stageable units ---
+        bool use_staged = c->n_staged > 0;
+        if (path == BSG_PROBE_GATHER) use_staged = false;
+        if (path == BSG_PROBE_AUTO && use_staged) {
+            // staged traffic = every byte of the touched kinds; gather traffic ~ one 32 B sector per
+            // tested location (~3 on average for an absent key, k for a present one) + the descriptor.
+            uint64_t staged_bytes = 0;
+            for (int k = 0; k < 3; ++k)
+                if (q->kind_mask & (1u << k)) staged_bytes += c->staged_kind_bytes[k];
+            const uint64_t gather_bytes = static_cast<uint64_t>(c->n_staged) * q->n_keys * (4 * 32 + 32);
+            use_staged = staged_bytes <= gather_bytes;
+        }
+        const int cw = (ctx->probe_warps > 0 && ctx->probe_warps <= kProbeConsumerWarps) ? ctx->probe_warps
+                                                                                        : kProbeConsumerWarps;
+        if (use_staged) {
+            ProbeStagedPlan plan;
+            const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - 2 * kProbeMaxStages * sizeof(uint64_t);
+            plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);
+            const uint64_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
+            int max_stages = kProbeMaxStages;
+            if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
+            plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, budget / stage_bytes));
+            if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: stage does not fit shared memory");
+            plan.smem_bytes = 2 * kProbeMaxStages * sizeof(uint64_t) + plan.n_stages * stage_bytes;
+            plan.grid = static_cast<int>(std::min<uint64_t>(c->n_staged, ctx->sm_count));
+            plan.consumer_warps = cw;
+            const uint32_t pass_keys = cw * 32 * kProbeMaxKeysPerThread;
+            for (uint32_t kb = 0; kb < q->n_keys; kb += pass_keys) {
+                const uint32_t nk = std::min<uint32_t>(pass_keys, q->n_keys - kb);
+                CUDA_TRY(launch_probe_staged(plan, c->d_udesc, c->d_utab, c->d_words, c->d_staged_list, c->n_staged,
+                                             q->d_hashes, q->d_kinds, kb, nk, q->kind_mask, q->d_matrix32,
+                                             q->row_words32, s));
+                ++launches;
+            }
+        } else if (c->n_staged) {
+            CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_staged_list, c->n_staged, q->d_hashes,
+                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s));
+            ++launches;
+        }
+        if (c->n_gather) {
+            CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_gather_list, c->n_gather, q->d_hashes,
+                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s));
+            ++launches;
+        }
+    }
+    if (c->n_units && !matrix_only) {
+        if (q->prog_len) {
+            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->d_prog, q->prog_len, q->d_mask32, s));
+        } else {
+            CUDA_TRY(launch_fill_mask(q->d_mask32, c->n_units, s));
+        }
+        ++launches;
+    }
+    q->last_launches = launches;
+    return BSG_OK;
+}
+
+extern "C" int bsg_query_run(bsg_ctx* ctx, const bsg_corpus* corpus, bsg_query* q, int path, int want_matrix) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return query_run_on(ctx, corpus, q, path, want_matrix, ctx->cur_stream);
+}
+
+static int query_fetch_on(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s) {
+    if (n_units != q->n_units) return fail(BSG_ERR_INVALID, "n_units mismatch");
+    if (out_matrix && q->n_keys && n_units)
+        CUDA_TRY(cudaMemcpyAsync(out_matrix, q->d_matrix32, n_units * q->row_words32 * 4, cudaMemcpyDeviceToHost, s));
+    if (out_mask && n_units)
+        CUDA_TRY(cudaMemcpyAsync(out_mask, q->d_mask32, ((n_units + 63) / 64) * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BSG_OK;
+}
+
+extern "C" int bsg_query_fetch(bsg_ctx* ctx, bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask) {
+    if (!ctx || !q) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return query_fetch_on(q, n_units, out_matrix, out_mask, ctx->cur_stream);
+}
+
+extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                         uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                         uint64_t* out_matrix, uint64_t* out_mask) {
+    if (!ctx || !corpus) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    bsg_query* q = nullptr;
+    int rc = query_create_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, &q);
+    if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, BSG_PROBE_AUTO, out_matrix != nullptr, s);
+    if (rc == BSG_OK) rc = query_fetch_on(q, corpus->n_units, out_matrix, out_mask, s);
+    else cudaStreamSynchronize(s);
+    bsg_query_free(q);
+    pool_put(ctx, s);
+    return rc;
+}
+
+// ---- hooks for bsg_comm.cpp (keeps bsg_ctx's layout private to this file) ----
+extern "C" int bsg_ctx_device_internal(bsg_ctx* ctx) { return ctx->device; }
+extern "C" void** bsg_ctx_comm_slot_internal(bsg_ctx* ctx) { return &ctx->comm; }
+extern "C" int bsg_set_last_error_internal(int code, const char* msg) { return fail(code, "%s", msg); }
+
+// ---- section loader: see sections.cu ----

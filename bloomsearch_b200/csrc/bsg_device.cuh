@@ -1,0 +1,177 @@
+// Device-side arithmetic shared by every kernel: bloom/v3 base hashes
+// (MurmurHash3_x64_128 of key and key||0x01, seed 0), location(h,i), exact
+// reduction mod m by a precomputed reciprocal, and the mbarrier / bulk-copy
+// (TMA 1-D) PTX wrappers used by the staged probe kernel.
+//
+// Reference arithmetic: bits-and-blooms/bloom/v3 v3.7.0 bloom.go (baseHashes,
+// location) + murmur.go (sum256), reached from ingest.go:142 (AddString) and
+// query_exec.go:141-154 (TestString).  sm_100a only.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsg {
+
+// ---------------------------------------------------------------- murmur3 ---
+constexpr uint64_t kC1 = 0x87c37b91114253d5ULL;
+constexpr uint64_t kC2 = 0x4cf5ad432745937fULL;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+__device__ __forceinline__ void bmix(uint64_t& h1, uint64_t& h2, uint64_t k1, uint64_t k2) {
+    k1 *= kC1; k1 = rotl64(k1, 31); k1 *= kC2; h1 ^= k1;
+    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+    k2 *= kC2; k2 = rotl64(k2, 33); k2 *= kC1; h2 ^= k2;
+    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+}
+
+// Tail (k1,k2 already zero-padded little-endian words; a zero word mixes to a
+// no-op so no branch on the tail length is needed) + finalisation.
+__device__ __forceinline__ void finalize(uint64_t h1, uint64_t h2, uint64_t k1, uint64_t k2,
+                                         uint64_t total_len, uint64_t& o1, uint64_t& o2) {
+    k2 *= kC2; k2 = rotl64(k2, 33); k2 *= kC1; h2 ^= k2;
+    k1 *= kC1; k1 = rotl64(k1, 31); k1 *= kC2; h1 ^= k1;
+    h1 ^= total_len; h2 ^= total_len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    o1 = h1; o2 = h2;
+}
+
+__device__ __forceinline__ uint64_t low_bytes_mask(uint32_t nbytes) {  // nbytes in [0,8]
+    return nbytes >= 8 ? ~0ULL : ((1ULL << (8 * nbytes)) - 1ULL);
+}
+
+// Streams little-endian 64-bit words out of an arbitrarily aligned byte range
+// using only aligned 8-byte loads (the buffer must be readable up to the next
+// 8-byte boundary past its end; device key buffers are padded by 16 bytes).
+struct WordReader {
+    const uint64_t* p;
+    uint64_t cur;
+    uint32_t sh;  // bit shift 0..56
+    __device__ __forceinline__ explicit WordReader(const uint8_t* addr) {
+        uintptr_t a = reinterpret_cast<uintptr_t>(addr);
+        p = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+        sh = static_cast<uint32_t>(a & 7) * 8;
+        cur = __ldg(p);
+    }
+    __device__ __forceinline__ uint64_t next() {
+        uint64_t w;
+        ++p;
+        if (sh == 0) {
+            w = cur;
+            cur = __ldg(p);
+        } else {
+            uint64_t nx = __ldg(p);
+            w = (cur >> sh) | (nx << (64 - sh));
+            cur = nx;
+        }
+        return w;
+    }
+};
+
+// Two-part reader: bytes of `a` (len la) followed by bytes of `b` (len lb),
+// presented as one little-endian word stream.  Used for field + "::" + token
+// hashing without materialising the joined key (tokenizer.go:508-511).
+// (Declared here; used by the fused field-token build path.)
+
+// baseHashes(key): h[0..1] = murmur(key), h[2..3] = murmur(key || 0x01).
+__device__ __forceinline__ void base_hashes(const uint8_t* key, uint32_t len, uint64_t h[4]) {
+    uint64_t h1 = 0, h2 = 0;
+    const uint32_t nblocks = len >> 4;
+    const uint32_t t = len & 15;
+    uint64_t k1 = 0, k2 = 0;
+    if (len != 0) {
+        WordReader rd(key);
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            uint64_t a = rd.next();
+            uint64_t c = rd.next();
+            bmix(h1, h2, a, c);
+        }
+        if (t > 0) k1 = rd.next() & low_bytes_mask(t);
+        if (t > 8) k2 = rd.next() & low_bytes_mask(t - 8);
+    }
+    finalize(h1, h2, k1, k2, len, h[0], h[1]);
+    // virtual extra byte 0x01 at position len
+    if (t < 8) k1 |= 1ULL << (8 * t); else k2 |= 1ULL << (8 * (t - 8));
+    if (t == 15) {  // the extra byte completes a 16-byte block; empty tail
+        bmix(h1, h2, k1, k2);
+        k1 = 0; k2 = 0;
+    }
+    finalize(h1, h2, k1, k2, static_cast<uint64_t>(len) + 1, h[2], h[3]);
+}
+
+// ------------------------------------------------------ location + modulo ---
+// location(h,i) = h[i%2] + i*h[2+(((i+(i%2))%4)/2)]  (uint64 wraparound)
+//   i%4: 0 -> h0+i*h2, 1 -> h1+i*h3, 2 -> h0+i*h3, 3 -> h1+i*h2
+__device__ __forceinline__ uint64_t location(const uint64_t h[4], uint32_t i) {
+    const uint64_t a = (i & 1) ? h[1] : h[0];
+    const uint64_t b = (((i + (i & 1)) & 3) >> 1) ? h[3] : h[2];
+    return a + static_cast<uint64_t>(i) * b;
+}
+
+// x mod m, exact, with inv = floor(2^64/m) for m >= 2 and inv = 2^64-1 for m == 1
+// (host: bsg::reciprocal).  q = hi64(x*inv) is floor(x/m) or one less, so a single
+// conditional subtraction finishes it.  Requires m < 2^63.
+__device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) {
+    const uint64_t q = __umul64hi(x, inv);
+    uint64_t r = x - q * m;
+    if (r >= m) r -= m;
+    return r;
+}
+
+// -------------------------------------------------- mbarrier / bulk copy ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); size and both
+// addresses must be multiples of 16 bytes.  Completion is signalled on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace bsg

@@ -1,0 +1,100 @@
+// Internal (non-ABI) declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/bloomgpu.h"
+
+namespace bsg {
+
+// Device-side filter descriptor (32 B, 16-byte aligned so it loads as 2x LDG.128
+// and can be bulk-copied into a stage header).  m == 0: filter absent.
+struct __align__(16) DevFilter {
+    uint64_t word_off;  // offset of the filter's first uint64 word in the corpus words array (even)
+    uint64_t m;         // bits
+    uint64_t inv;       // floor(2^64/m) (2^64-1 for m == 1), see mod_m
+    uint32_t k;         // hash functions
+    uint32_t nwords;    // ceil(m/64)
+};
+static_assert(sizeof(DevFilter) == 32, "DevFilter must be 32 bytes");
+
+// Per-unit staging record read by the probe producer warp (32 B).  A unit's three
+// filters are stored back to back (field, token, fieldtoken), each padded to an
+// even number of words so every filter starts 16-byte aligned (bulk-copy rule).
+struct __align__(16) UnitTab {
+    uint64_t word_base;  // first word of the unit's words (even)
+    uint32_t nw[3];      // padded word count per kind (0 when absent)
+    uint32_t total;      // nw[0] + nw[1] + nw[2]
+    uint64_t reserved;
+};
+static_assert(sizeof(UnitTab) == 32, "UnitTab must be 32 bytes");
+
+// Build-side filter descriptor (over the caller's out_words layout).
+struct __align__(16) BuildFilter {
+    uint64_t word_off;
+    uint64_t m;
+    uint64_t inv;
+    uint32_t k;
+    uint32_t nwords;
+};
+
+inline uint64_t reciprocal(uint64_t m) {
+    if (m <= 1) return ~0ULL;
+    return static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / m);
+}
+
+constexpr int kProbeConsumerWarps = 16;
+constexpr int kProbeThreads = (kProbeConsumerWarps + 1) * 32;  // + 1 producer warp
+constexpr int kProbeMaxStages = 16;
+constexpr int kProbeStageHeaderBytes = 128;  // 3 x DevFilter (96 B) + pad
+constexpr int kProbeMaxKeysPerThread = 4;    // staged path handles <= 16*32*4 = 2048 keys per pass
+
+// ---- launch wrappers (defined in the kernels_*.cu files) -------------------
+cudaError_t launch_hash_keys(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,
+                             uint64_t* d_hashes, cudaStream_t s);
+
+struct ProbeStagedPlan {
+    int n_stages;
+    uint32_t stage_data_bytes;  // per-stage capacity for filter words
+    size_t smem_bytes;
+    int grid;
+    int consumer_warps;  // 0 = default (kProbeConsumerWarps)
+};
+cudaError_t probe_staged_configure(int max_smem_optin);
+cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const DevFilter* d_udesc, const UnitTab* d_utab,
+                                const uint64_t* d_words, const uint32_t* d_unit_list,
+                                uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t key_base,
+                                uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32, uint32_t row_words32,
+                                cudaStream_t s);
+cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
+                                uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
+                                uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s);
+cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
+                             const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s);
+cudaError_t launch_fill_mask(uint32_t* d_mask32, uint64_t n_units, cudaStream_t s);
+
+cudaError_t build_configure(int max_smem_optin);
+cudaError_t launch_build(const uint8_t* d_keys, const uint64_t* d_key_off, const uint64_t* d_group_begin,
+                         uint32_t n_groups, const uint32_t* d_group_filter, const uint32_t* d_group_filter2,
+                         const BuildFilter* d_filters, uint64_t* d_out_words, uint32_t smem_cap_bytes,
+                         cudaStream_t s);
+
+cudaError_t launch_repack(const uint64_t* d_src, const uint64_t* d_src_off, const DevFilter* d_udesc,
+                          uint64_t n_filters, uint64_t* d_dst, int big_endian, cudaStream_t s);
+
+// Section parsing on the device (file_format.go:392-448): per unit, verify
+// CRC32C, parse flags / length prefixes / (m,k,bitlen) headers.
+struct SectionInfo {          // written by the parse kernel, one per unit
+    int32_t status;           // 0 ok, else negative detail code
+    uint32_t present;         // flags byte
+    uint64_t m[3], k[3];      // per present filter
+    uint64_t words_byte_off[3];  // offset of the first BE word inside `sections`
+};
+cudaError_t launch_parse_sections(const uint8_t* d_sections, const uint64_t* d_sec_off, uint64_t n_units,
+                                  int verify_crc, SectionInfo* d_info, cudaStream_t s);
+cudaError_t launch_repack_sections(const uint8_t* d_sections, const SectionInfo* d_info, const DevFilter* d_udesc,
+                                   uint64_t n_units, uint64_t* d_dst, cudaStream_t s);
+
+cudaError_t launch_or_words(uint64_t* d_dst, const uint64_t* d_src, uint64_t n_words, cudaStream_t s);
+
+}  // namespace bsg

@@ -1,0 +1,348 @@
+"""Host-side mirror of the reference's filter build / probe call sites over the C ABI.
+
+  BloomEntrySets.build_filters  <- ingest.go:24-145 (bloomEntrySets, buildFilters,
+                                   buildSizedBloomFilter), called per block and per file
+                                   from flush.go:204,253 / merge.go:516,771
+  Corpus.evaluate_bloom_filters <- query_exec.go:75-159, batched over every unit of a
+                                   resident corpus instead of one filter triple at a time
+  BloomFilter / BloomFilters    <- the value types of file_format.go:328-332 (m, k, words)
+
+All arithmetic happens in libbloomgpu.so on the GPU; nothing here hashes or tests
+bits on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .query import BloomQuery, CompiledQuery, compile_bloom_query
+
+
+class Context:
+    """Owns a bsg_ctx (device, streams)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().bsg_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def device_info(self) -> dict:
+        sm, cmaj, cmin = C.c_int(), C.c_int(), C.c_int()
+        smem, total = C.c_size_t(), C.c_size_t()
+        N.check(N.lib().bsg_device_info(self._h, C.byref(sm), C.byref(smem), C.byref(total), C.byref(cmaj), C.byref(cmin)))
+        return {"sm_count": sm.value, "smem_optin": smem.value, "total_mem": total.value,
+                "cc": (cmaj.value, cmin.value)}
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        N.check(N.lib().bsg_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        N.check(N.lib().bsg_synchronize(self._h))
+
+    def timer_begin(self):
+        N.check(N.lib().bsg_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        N.check(N.lib().bsg_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- K1 ----
+    def hash_keys(self, keys: Sequence[bytes]) -> np.ndarray:
+        blob, off = N.pack_keys(list(keys))
+        out = np.zeros((len(keys), 4), dtype=np.uint64)
+        N.check(N.lib().bsg_hash_keys(self._h, N.ptr(blob), N.ptr(off), len(keys), N.ptr(out)))
+        return out
+
+    # ---- K2/K3 ----
+    def build(self, blob: np.ndarray, key_off: np.ndarray, group_begin: np.ndarray, group_filter: np.ndarray,
+              group_filter2: Optional[np.ndarray], desc: np.ndarray, n_words: int) -> np.ndarray:
+        """Raw bsg_build over packed keys; returns the native-endian words array."""
+        desc = np.ascontiguousarray(desc, dtype=N.DESC_DTYPE)
+        group_begin = np.ascontiguousarray(group_begin, dtype=np.uint64)
+        group_filter = np.ascontiguousarray(group_filter, dtype=np.uint32)
+        gf2 = None if group_filter2 is None else np.ascontiguousarray(group_filter2, dtype=np.uint32)
+        key_off = np.ascontiguousarray(key_off, dtype=np.uint64)
+        out = np.zeros(max(int(n_words), 1), dtype=np.uint64)
+        N.check(N.lib().bsg_build(self._h, N.ptr(blob), N.ptr(key_off), len(key_off) - 1, N.ptr(group_begin),
+                                  len(group_filter), N.ptr(group_filter), N.ptr(gf2), N.ptr(desc), len(desc),
+                                  N.ptr(out), int(n_words)))
+        return out[:int(n_words)]
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        N.check(N.lib().bsg_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        N.check(N.lib().bsg_comm_init(self._h, rank, world, buf))
+
+    def or_reduce(self, words: np.ndarray) -> np.ndarray:
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        N.check(N.lib().bsg_or_reduce(self._h, N.ptr(words), len(words)))
+        return words
+
+    def allgather_masks(self, local: np.ndarray, world: int) -> np.ndarray:
+        local = np.ascontiguousarray(local, dtype=np.uint64)
+        out = np.zeros((world, len(local)), dtype=np.uint64)
+        N.check(N.lib().bsg_allgather_masks(self._h, N.ptr(local), len(local), N.ptr(out)))
+        return out
+
+
+def estimate_parameters(n: int, fpr: float) -> tuple[int, int]:
+    """bloom.EstimateParameters + New's clamp (bsg_estimate)."""
+    m, k = C.c_uint64(), C.c_uint64()
+    N.lib().bsg_estimate(n, fpr, C.byref(m), C.byref(k))
+    return m.value, k.value
+
+
+@dataclass
+class BloomFilter:
+    """Value mirror of *bloom.BloomFilter: m bits, k hashes, native-endian uint64 words."""
+    m: int
+    k: int
+    words: np.ndarray
+
+    def write_to(self) -> bytes:
+        """BloomFilter.WriteTo framing (big-endian), file_format.go:368."""
+        hdr = np.array([self.m, self.k, self.m], dtype=">u8").tobytes()
+        return hdr + self.words.astype(">u8").tobytes()
+
+    @classmethod
+    def read_from(cls, raw: bytes) -> "BloomFilter":
+        m, k, bitlen = (int(x) for x in np.frombuffer(raw[:24], dtype=">u8"))
+        nw = (bitlen + 63) // 64
+        return cls(m, k, np.frombuffer(raw[24:24 + 8 * nw], dtype=">u8").astype(np.uint64))
+
+
+@dataclass
+class BloomFilters:
+    """file_format.go:328-332; any member may be None (absent => cannot disqualify)."""
+    FieldBloomFilter: Optional[BloomFilter] = None
+    TokenBloomFilter: Optional[BloomFilter] = None
+    FieldTokenBloomFilter: Optional[BloomFilter] = None
+
+    def as_tuple(self):
+        return (self.FieldBloomFilter, self.TokenBloomFilter, self.FieldTokenBloomFilter)
+
+
+class BloomEntrySets:
+    """ingest.go:24-123: distinct field / token / field::token entries of a set of rows.
+    Dedup stays on the host (Python sets here, Go maps in the reference); hashing and
+    bit-setting run on the GPU at build_filters time."""
+
+    def __init__(self):
+        self.fields: set = set()
+        self.tokens: set = set()
+        self.fieldTokens: set = set()
+
+    def add_field(self, path: bytes):
+        self.fields.add(path)
+
+    def add_token(self, token: bytes):
+        self.tokens.add(token)
+
+    def add_field_token(self, path: bytes, token: bytes):  # ingest.go:95-102
+        self.fieldTokens.add(path + b"::" + token)
+
+    def union_into(self, dst: "BloomEntrySets"):  # ingest.go:105-115
+        dst.fields |= self.fields
+        dst.tokens |= self.tokens
+        dst.fieldTokens |= self.fieldTokens
+
+    def counts(self):  # ingest.go:117-123
+        return {"Fields": len(self.fields), "Tokens": len(self.tokens), "FieldTokens": len(self.fieldTokens)}
+
+    def build_filters(self, ctx: Context, false_positive_rate: float) -> BloomFilters:  # ingest.go:127-133
+        return build_filters_many(ctx, [self], false_positive_rate)[0]
+
+
+def build_filters_many(ctx: Context, sets: Sequence[BloomEntrySets], fpr: float,
+                       file_sets: Optional[Sequence[BloomEntrySets]] = None,
+                       file_of: Optional[Sequence[int]] = None):
+    """One bsg_build call for many entry sets (all partition buffers of a flush,
+    flush.go:138-282).  If file_sets/file_of are given, set i also feeds the union filter
+    of file file_of[i], sized from file_sets[...]'s exact distinct counts (flush.go:221,253);
+    returns (block_filters, file_filters) then, else block_filters."""
+    keys: List[bytes] = []
+    group_begin = [0]
+    group_filter: List[int] = []
+    group_filter2: List[int] = []
+    desc = []
+    word_off = 0
+
+    def new_filter(n_entries: int) -> int:
+        nonlocal word_off
+        m, k = estimate_parameters(max(n_entries, 1), fpr)  # ingest.go:139-140
+        desc.append((m, k, word_off))
+        word_off += (m + 63) // 64
+        return len(desc) - 1
+
+    file_ids = None
+    if file_sets is not None:
+        file_ids = [[new_filter(len(s)) for s in (fs.fields, fs.tokens, fs.fieldTokens)] for fs in file_sets]
+    block_ids = []
+    for i, es in enumerate(sets):
+        ids = []
+        for kind, entries in enumerate((es.fields, es.tokens, es.fieldTokens)):
+            fid = new_filter(len(entries))
+            ids.append(fid)
+            keys.extend(entries)
+            group_begin.append(len(keys))
+            group_filter.append(fid)
+            group_filter2.append(file_ids[file_of[i]][kind] if file_ids is not None else N.NO_FILTER)
+        block_ids.append(ids)
+    blob, off = N.pack_keys(keys)
+    d = np.array(desc, dtype=N.DESC_DTYPE) if desc else np.zeros(0, N.DESC_DTYPE)
+    words = ctx.build(blob, off, np.array(group_begin, np.uint64), np.array(group_filter, np.uint32),
+                      np.array(group_filter2, np.uint32) if file_ids is not None else None, d, word_off)
+
+    def mk(fid):
+        m, k, wo = desc[fid]
+        return BloomFilter(m, k, words[wo:wo + (m + 63) // 64].copy())
+
+    blocks = [BloomFilters(*(mk(f) for f in ids)) for ids in block_ids]
+    if file_ids is None:
+        return blocks
+    return blocks, [BloomFilters(*(mk(f) for f in ids)) for ids in file_ids]
+
+
+class Corpus:
+    """A set of units (data blocks or files) whose filters are resident in HBM."""
+
+    def __init__(self, ctx: Context, desc: np.ndarray, words: np.ndarray, big_endian: bool = False):
+        desc = np.ascontiguousarray(desc, dtype=N.DESC_DTYPE).reshape(-1)
+        assert len(desc) % 3 == 0
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.ctx = ctx
+        self.n_units = len(desc) // 3
+        self._h = C.c_void_p()
+        N.check(N.lib().bsg_corpus_load(ctx.handle, N.ptr(desc), self.n_units, N.ptr(words) if len(words) else None,
+                                        len(words), 1 if big_endian else 0, C.byref(self._h)))
+
+    @classmethod
+    def from_filters(cls, ctx: Context, units: Sequence[BloomFilters]) -> "Corpus":
+        desc = np.zeros(len(units) * 3, dtype=N.DESC_DTYPE)
+        chunks = []
+        off = 0
+        for u, bf in enumerate(units):
+            for kind, f in enumerate(bf.as_tuple()):
+                if f is None:
+                    continue
+                desc[u * 3 + kind] = (f.m, f.k, off)
+                chunks.append(np.asarray(f.words, dtype=np.uint64))
+                off += len(f.words)
+        words = np.concatenate(chunks) if chunks else np.zeros(0, np.uint64)
+        return cls(ctx, desc, words)
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_corpus_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def bitset_bytes(self, kind_mask: int = 7) -> int:
+        return N.lib().bsg_corpus_bitset_bytes(self._h, kind_mask)
+
+    # ---- probe: host buffers in, host buffers out (the call the Go shim makes) ----
+    def probe(self, keys: Sequence[bytes], kinds, prog: Optional[np.ndarray] = None, want_matrix: bool = True,
+              want_mask: bool = True):
+        blob, off = N.pack_keys(list(keys))
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        q = len(keys)
+        matrix = np.zeros((self.n_units, (q + 63) // 64), dtype=np.uint64) if want_matrix else None
+        mask = np.zeros((self.n_units + 63) // 64, dtype=np.uint64) if want_mask else None
+        pp, pl = (None, 0) if prog is None else (N.ptr(np.ascontiguousarray(prog, N.OP_DTYPE)), len(prog))
+        N.check(N.lib().bsg_probe(self.ctx.handle, self._h, N.ptr(blob), N.ptr(off), q, N.ptr(kinds), pp, pl,
+                                  N.ptr(matrix), N.ptr(mask)))
+        return matrix, mask
+
+    def evaluate_bloom_filters(self, query: Optional[BloomQuery]) -> np.ndarray:
+        """evaluateBloomFilters (query_exec.go:75-87) for every unit at once -> bool[n_units]."""
+        cq = compile_bloom_query(query)
+        _, mask = self.probe(cq.keys, cq.kinds, cq.prog, want_matrix=False)
+        return unpack_mask(mask, self.n_units)
+
+
+class Query:
+    """Device-resident query (keys hashed once) for repeated / timed probes."""
+
+    def __init__(self, corpus: Corpus, keys: Sequence[bytes], kinds, prog: Optional[np.ndarray] = None):
+        self.corpus = corpus
+        self.n_keys = len(keys)
+        blob, off = N.pack_keys(list(keys))
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        pp, pl = (None, 0) if prog is None else (N.ptr(np.ascontiguousarray(prog, N.OP_DTYPE)), len(prog))
+        self._h = C.c_void_p()
+        N.check(N.lib().bsg_query_create(corpus.ctx.handle, corpus.handle, N.ptr(blob), N.ptr(off), self.n_keys,
+                                         N.ptr(kinds), pp, pl, C.byref(self._h)))
+
+    def run(self, path: int = N.PROBE_AUTO, corpus: Optional[Corpus] = None):
+        c = corpus or self.corpus
+        N.check(N.lib().bsg_query_run(c.ctx.handle, c.handle, self._h, path, 1))
+
+    def launches(self) -> int:
+        return N.lib().bsg_query_last_launches(self._h)
+
+    def fetch(self, want_matrix: bool = True, want_mask: bool = True):
+        n = self.corpus.n_units
+        matrix = np.zeros((n, (self.n_keys + 63) // 64), dtype=np.uint64) if want_matrix else None
+        mask = np.zeros((n + 63) // 64, dtype=np.uint64) if want_mask else None
+        N.check(N.lib().bsg_query_fetch(self.corpus.ctx.handle, self._h, n, N.ptr(matrix), N.ptr(mask)))
+        return matrix, mask
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_query_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def unpack_mask(mask: np.ndarray, n_units: int) -> np.ndarray:
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")
+    return bits[:n_units].astype(bool)
+
+
+def unpack_matrix(matrix: np.ndarray, n_keys: int) -> np.ndarray:
+    """uint64[n_units, ceil(Q/64)] -> bool[n_units, Q]."""
+    n_units = matrix.shape[0]
+    if n_units == 0 or n_keys == 0:
+        return np.zeros((n_units, n_keys), dtype=bool)
+    bits = np.unpackbits(np.ascontiguousarray(matrix).view(np.uint8).reshape(n_units, -1), axis=1, bitorder="little")
+    return bits[:, :n_keys].astype(bool)

@@ -1,0 +1,199 @@
+/*
+ * bloomgpu.h — C ABI of libbloomgpu.so: the B200 (sm_100a) implementation of
+ * bloomsearch's bloom-filter build / probe hot path.
+ *
+ * This is the drop-in boundary a cgo shim binds (see INTEGRATION.md and
+ * go/bloomgpu/).  The reference (danthegoodman1/bloomsearch @ 10735cf9, pure Go)
+ * has no FFI seam of its own; the seam is the *bloom.BloomFilter value used at
+ * exactly these call sites, each of which one entry point below replaces:
+ *
+ *   build   ingest.go:127-145  buildFilters / buildSizedBloomFilter
+ *           (called from flush.go:204,253 and merge.go:516,771)   -> bsg_build
+ *   probe   query_exec.go:75-159 evaluateBloom{Filters,Expression,Condition}
+ *           (called from query_exec.go:399-404 file level,
+ *            query_exec.go:592-597 block level)                    -> bsg_probe
+ *   decode  file_format.go:392-448 parseFilterSection + bloom ReadFrom
+ *           (per block per query in the reference)                 -> bsg_corpus_load[_sections]
+ *   sizing  bloom.NewWithEstimates via ingest.go:140               -> bsg_estimate (helper)
+ *
+ * Conventions: every function returns 0 on success or a negative bsg_status;
+ * bsg_strerror(code) gives a static string, bsg_last_error(ctx) the detail of
+ * the last failure on the calling thread.  All pointers are plain host memory
+ * owned by the caller and are not retained after the call returns (cgo rule).
+ * No CPU fallback exists: without a CUDA device every entry point fails with
+ * BSG_ERR_CUDA.  Entry points are thread-safe; concurrent probes on one ctx
+ * run on separate streams.
+ *
+ * Bit-exact contract (what "same filter" means): bit b of a filter lives in
+ * native-endian uint64 word b>>6 at mask 1<<(b&63) (bitset.BitSet), locations
+ * are location(h,i) % m with h = the four MurmurHash3_x64_128 base hashes of
+ * bloom/v3 (see oracle/bloomref.h for the restated algorithm).
+ */
+#ifndef BLOOMGPU_H
+#define BLOOMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSG_ABI_VERSION 1
+
+typedef enum bsg_status {
+    BSG_OK = 0,
+    BSG_ERR_INVALID = -1,    /* bad argument (NULL, m too large, malformed program, ...) */
+    BSG_ERR_CUDA = -2,       /* CUDA runtime / driver failure or no device */
+    BSG_ERR_NOMEM = -3,      /* host or device allocation failed */
+    BSG_ERR_FORMAT = -4,     /* filter section framing / CRC error (per-unit detail in status array) */
+    BSG_ERR_UNSUPPORTED = -5,/* feature not available (e.g. NCCL not loadable) */
+    BSG_ERR_COMM = -6        /* NCCL failure */
+} bsg_status;
+
+typedef struct bsg_ctx bsg_ctx;
+typedef struct bsg_corpus bsg_corpus;
+typedef struct bsg_query bsg_query;
+
+/* One bloom filter: m bits, k hash functions, words start at word_off (in uint64
+ * units) inside the accompanying words array.  m == 0 means "filter absent"
+ * (Go nil): an absent filter cannot disqualify (query_exec.go:137-151). */
+typedef struct bsg_filter_desc {
+    uint64_t m;
+    uint64_t k;
+    uint64_t word_off;
+} bsg_filter_desc;
+
+/* Condition kinds, query.go:478-484.  Kind selects which of a unit's three
+ * filters a key is tested against. */
+enum { BSG_KIND_FIELD = 0, BSG_KIND_TOKEN = 1, BSG_KIND_FIELDTOKEN = 2 };
+
+/* Postfix form of a BloomExpression tree (query.go:499-503).  Leaf i is query
+ * key i.  AND/OR pop `arg` values; AND 0 = true, OR 0 = false
+ * (query_exec.go:105-123).  TRUE encodes a nil Condition / nil child, FALSE an
+ * unknown expression or condition type (query_exec.go:121-123,155-156). */
+enum { BSG_OP_LEAF = 0, BSG_OP_AND = 1, BSG_OP_OR = 2, BSG_OP_TRUE = 3, BSG_OP_FALSE = 4 };
+typedef struct bsg_expr_op {
+    uint32_t op;
+    uint32_t arg;
+} bsg_expr_op;
+#define BSG_MAX_STACK 64 /* maximum evaluation-stack depth of a program */
+
+/* ---- context ------------------------------------------------------------ */
+int bsg_abi_version(void);
+const char *bsg_strerror(int code);
+const char *bsg_last_error(void); /* thread-local detail string */
+int bsg_create(int device, bsg_ctx **out);
+void bsg_destroy(bsg_ctx *ctx);
+/* Run all work of this ctx's *resident* entry points on an existing CUDA stream
+ * (cudaStream_t passed as void*); NULL restores the ctx's own stream. */
+int bsg_set_stream(bsg_ctx *ctx, void *cuda_stream);
+int bsg_synchronize(bsg_ctx *ctx);
+/* Device properties the host needs for planning / reporting. */
+int bsg_device_info(bsg_ctx *ctx, int *sm_count, size_t *smem_per_block_optin,
+                    size_t *total_mem, int *cc_major, int *cc_minor);
+
+/* ---- sizing helper (bloom.EstimateParameters + New's clamp) -------------- */
+void bsg_estimate(uint64_t n, double fpr, uint64_t *m, uint64_t *k);
+
+/* ---- K1: base hashes ----------------------------------------------------- *
+ * keys packed back to back; key i = keys[key_off[i] .. key_off[i+1]).
+ * out_hashes[4*i .. 4*i+3] = bloom/v3 baseHashes(key i).  Replaces the hashing
+ * inside every AddString/TestString (ingest.go:142, query_exec.go:141-154). */
+int bsg_hash_keys(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64_t n_keys,
+                  uint64_t *out_hashes);
+
+/* ---- K2/K3: build --------------------------------------------------------- *
+ * Builds n_filters filters in one call.  Keys are grouped: group g owns keys
+ * [group_begin[g], group_begin[g+1]) and inserts each into filter
+ * group_filter[g] (its block-level filter, ingest.go:139-145) and — when
+ * group_filter2 != NULL and group_filter2[g] != BSG_NO_FILTER — also into filter
+ * group_filter2[g] (the file-level union filter, flush.go:221,253; duplicates
+ * across groups are harmless because insertion is an idempotent OR, only the
+ * (m,k) sizing needs the exact union count, which the host's entry sets give).
+ * Each key is hashed once for both.  Several groups may share a filter.
+ * desc[f].word_off locates filter f inside out_words (n_words uint64, native
+ * endian), which the callee zero-initialises. */
+#define BSG_NO_FILTER 0xFFFFFFFFu
+int bsg_build(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64_t n_keys,
+              const uint64_t *group_begin, uint32_t n_groups, const uint32_t *group_filter,
+              const uint32_t *group_filter2, const bsg_filter_desc *desc, uint32_t n_filters,
+              uint64_t *out_words, uint64_t n_words);
+
+/* ---- corpus residency ------------------------------------------------------ *
+ * A corpus is n_units "units" (data blocks, or files for the file-level stage),
+ * each with up to three filters: desc[3*u + kind].  The words are copied to HBM
+ * and re-laid-out (16-byte aligned, unit-contiguous) for the probe kernels.
+ * big_endian != 0: `words` holds the on-disk big-endian uint64 words of
+ * bitset.WriteTo and is byte-swapped on the device. */
+int bsg_corpus_load(bsg_ctx *ctx, const bsg_filter_desc *desc, uint64_t n_units,
+                    const uint64_t *words, uint64_t n_words, int big_endian, bsg_corpus **out);
+/* Load straight from raw filter sections (file_format.go:343-385 framing):
+ * unit u = sections[sec_off[u] .. sec_off[u+1]).  Framing is parsed and the
+ * CRC32C verified (verify_crc != 0) — on the device; big-endian words are
+ * swapped on the device.  unit_status (nullable, n_units ints) receives 0 or
+ * the per-unit BSG_ERR_FORMAT detail code; a unit that fails to parse is kept
+ * as "all filters absent" so it cannot be disqualified, mirroring the
+ * reference's per-block error isolation (query_exec.go:580-590).  Returns
+ * BSG_OK even if some units failed; *n_bad (nullable) counts them. */
+int bsg_corpus_load_sections(bsg_ctx *ctx, const uint8_t *sections, const uint64_t *sec_off,
+                             uint64_t n_units, int verify_crc, int32_t *unit_status,
+                             uint64_t *n_bad, bsg_corpus **out);
+void bsg_corpus_free(bsg_corpus *corpus);
+uint64_t bsg_corpus_units(const bsg_corpus *corpus);
+/* Bytes of filter bitsets resident in HBM (Σ_b S_b of SURVEY.md §8d), optionally
+ * only for the kinds in kind_mask (bit kind). */
+uint64_t bsg_corpus_bitset_bytes(const bsg_corpus *corpus, uint32_t kind_mask);
+/* Copy unit u's descriptors (3) and words back out (tests / round trips). */
+int bsg_corpus_unit_desc(const bsg_corpus *corpus, uint64_t unit, bsg_filter_desc out_desc[3]);
+
+/* ---- K4/K5: probe ----------------------------------------------------------- *
+ * Tests n_keys keys against every unit of the corpus.
+ *   key_kind[q]   BSG_KIND_* : which filter of the unit key q is tested on
+ *   out_matrix    nullable; n_units rows of ceil(n_keys/64) uint64 words,
+ *                 bit q of row u = TestString(key q) on unit u (absent filter => 1)
+ *   prog/prog_len nullable postfix BloomExpression; NULL/0 => every unit survives
+ *                 (query_exec.go:81-83)
+ *   out_mask      nullable; ceil(n_units/64) uint64 words, bit u = unit u survives
+ * FieldToken keys are passed already joined as field + "::" + token
+ * (tokenizer.go:508-511); bytes are used verbatim (no normalisation). */
+int bsg_probe(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys, const uint64_t *key_off,
+              uint32_t n_keys, const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
+              uint64_t *out_matrix, uint64_t *out_mask);
+
+/* Resident form of the same call, for callers that keep a query on the device
+ * and for measurement: create uploads + hashes the keys once; run launches the
+ * probe (asynchronously, on the ctx stream); fetch copies results to the host. */
+enum { BSG_PROBE_AUTO = 0, BSG_PROBE_STAGED = 1, BSG_PROBE_GATHER = 2 };
+/* OR into `path`: run only the probe kernel(s) (bit matrix), skip the mask kernel. */
+#define BSG_RUN_MATRIX_ONLY 0x100
+int bsg_query_create(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys,
+                     const uint64_t *key_off, uint32_t n_keys, const uint8_t *key_kind,
+                     const bsg_expr_op *prog, uint32_t prog_len, bsg_query **out);
+int bsg_query_run(bsg_ctx *ctx, const bsg_corpus *corpus, bsg_query *q, int path, int want_matrix);
+int bsg_query_fetch(bsg_ctx *ctx, bsg_query *q, uint64_t n_units, uint64_t *out_matrix,
+                    uint64_t *out_mask);
+void bsg_query_free(bsg_query *q);
+/* Number of kernels the last bsg_query_run launched (for launch accounting). */
+int bsg_query_last_launches(const bsg_query *q);
+
+/* ---- device-event timing on the ctx stream (measurement only) ------------- */
+int bsg_timer_begin(bsg_ctx *ctx);
+int bsg_timer_end(bsg_ctx *ctx, float *elapsed_ms); /* records, synchronises, returns ms */
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------- *
+ * nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 (bsg_comm_unique_id)
+ * and distributed by the host (the Go side would ship it over its own RPC). */
+int bsg_comm_unique_id(uint8_t out_id[128]);
+int bsg_comm_init(bsg_ctx *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+/* In-place bitwise OR across ranks of equal-shape partial bitsets (file-level
+ * filters built from disjoint shards of a file's entries).
+ * words is HOST memory; result is identical on every rank. */
+int bsg_or_reduce(bsg_ctx *ctx, uint64_t *words, uint64_t n_words);
+/* Gather every rank's candidate mask (n_words each, host) into all (world*n_words). */
+int bsg_allgather_masks(bsg_ctx *ctx, const uint64_t *local, uint64_t n_words, uint64_t *all);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOOMGPU_H */

@@ -540,3 +540,60 @@ int64_t bref_probe_sections(const uint8_t *sections, const uint64_t *sec_off, ui
     parallel_ranges(n_units, n_threads, sections_range, &c);
     return c.errors;
 }
+
+typedef struct {
+    const uint8_t *sections; const uint64_t *sec_off;
+    const uint8_t *bytes; const uint64_t *key_off; const uint8_t *kinds; uint32_t n_keys;
+    uint64_t *out; uint64_t row_words; int64_t errors;
+} secm_ctx;
+
+static void sections_matrix_range(void *p, uint64_t lo, uint64_t hi) {
+    secm_ctx *c = (secm_ctx *)p;
+    int64_t errs = 0;
+    for (uint64_t u = lo; u < hi; u++) {
+        bref_filter *f[3];
+        int rc = bref_section_parse(c->sections + c->sec_off[u], (size_t)(c->sec_off[u + 1] - c->sec_off[u]), f);
+        if (rc != 0) { errs++; f[0] = f[1] = f[2] = NULL; }
+        uint64_t *row = c->out + u * c->row_words;
+        for (uint32_t q = 0; q < c->n_keys; q++) {
+            const bref_filter *flt = f[c->kinds[q]];
+            int r = flt ? bref_filter_test(flt, c->bytes + c->key_off[q], (size_t)(c->key_off[q + 1] - c->key_off[q])) : 1;
+            if (r) row[q >> 6] |= 1ULL << (q & 63);
+        }
+        for (int i = 0; i < 3; i++) bref_filter_free(f[i]);
+    }
+    __atomic_fetch_add(&c->errors, errs, __ATOMIC_RELAXED);
+}
+
+int64_t bref_probe_sections_matrix(const uint8_t *sections, const uint64_t *sec_off, uint64_t n_units,
+                                   const uint8_t *bytes, const uint64_t *key_off, const uint8_t *kinds,
+                                   uint32_t n_keys, uint64_t *out_matrix, int n_threads) {
+    uint64_t row_words = ((uint64_t)n_keys + 63) / 64;
+    memset(out_matrix, 0, (size_t)(n_units * row_words * 8));
+    secm_ctx c = { sections, sec_off, bytes, key_off, kinds, n_keys, out_matrix, row_words, 0 };
+    parallel_ranges(n_units, n_threads, sections_matrix_range, &c);
+    return c.errors;
+}
+
+/* Encode every unit's (up to three) filters, given as descriptors over a words array,
+ * into back-to-back filter sections (file_format.go:343-385).  Two-pass: call with
+ * out == NULL to obtain sec_off (n_units+1) and the total size. */
+uint64_t bref_encode_sections(const bref_desc *desc, const uint64_t *words, uint64_t n_units,
+                              uint64_t *sec_off, uint8_t *out) {
+    uint64_t pos = 0;
+    for (uint64_t u = 0; u < n_units; u++) {
+        bref_filter tmp[3];
+        const bref_filter *fl[3] = {NULL, NULL, NULL};
+        for (int k = 0; k < 3; k++) {
+            const bref_desc *d = &desc[u * 3 + k];
+            if (d->m == 0) continue;
+            tmp[k].m = d->m; tmp[k].k = d->k; tmp[k].nwords = (d->m + 63) >> 6;
+            tmp[k].words = (uint64_t *)(words + d->word_off);
+            fl[k] = &tmp[k];
+        }
+        sec_off[u] = pos;
+        pos += bref_section_encode(fl, out ? out + pos : NULL);
+    }
+    sec_off[n_units] = pos;
+    return pos;
+}

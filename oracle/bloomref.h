@@ -147,6 +147,19 @@ int bref_probe_mask(const bref_desc *desc, const uint64_t *words, uint64_t n_uni
 int64_t bref_probe_sections(const uint8_t *sections, const uint64_t *sec_off, uint64_t n_units,
                             const bref_expr *expr, uint64_t *out_mask, int n_threads);
 
+/* Same loop, but for a batch of independent single-condition queries evaluated in
+ * one pass over the corpus: per unit, parseFilterSection ONCE, then TestString for
+ * every key (hashing the key again for every unit, as TestString does), writing
+ * the (unit x key) bit matrix.  This is the conservative CPU statement of the
+ * batched probe: the real engine would re-decode every section once per query. */
+int64_t bref_probe_sections_matrix(const uint8_t *sections, const uint64_t *sec_off, uint64_t n_units,
+                                   const uint8_t *bytes, const uint64_t *key_off, const uint8_t *kinds,
+                                   uint32_t n_keys, uint64_t *out_matrix, int n_threads);
+
+/* Encode units (descriptors over a words array) into back-to-back filter sections. */
+uint64_t bref_encode_sections(const bref_desc *desc, const uint64_t *words, uint64_t n_units,
+                              uint64_t *sec_off, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

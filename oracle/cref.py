@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libbloomref.so")
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("bloomref.c", "bloomref.h")]
+    src = [os.path.join(_HERE, f) for f in ("bloomref.c", "bloomref.h", "corpusgen.c")]
     stale = (not os.path.exists(_SO)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:
@@ -101,6 +101,10 @@ def lib():
     L.bref_probe_mask.restype = C.c_int
     L.bref_probe_sections.argtypes = [vp, vp, C.c_uint64, C.POINTER(Expr), vp, C.c_int]
     L.bref_probe_sections.restype = C.c_int64
+    L.bref_probe_sections_matrix.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp, C.c_int]
+    L.bref_probe_sections_matrix.restype = C.c_int64
+    L.bref_encode_sections.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    L.bref_encode_sections.restype = C.c_uint64
     _lib = L
     return L
 
@@ -313,3 +317,24 @@ def probe_sections(sections: np.ndarray, sec_off: np.ndarray, expr, n_threads=1)
     e = None if expr is None else C.byref(make_expr(expr, keep))
     errs = lib().bref_probe_sections(_p(sections), _p(sec_off), n_units, e, _p(out), n_threads)
     return out, errs
+
+
+def probe_sections_matrix(sections: np.ndarray, sec_off: np.ndarray, blob, key_off, kinds, n_threads=1):
+    n_units = len(sec_off) - 1
+    q = len(key_off) - 1
+    out = np.zeros((n_units, (q + 63) // 64), dtype=np.uint64)
+    kinds = np.ascontiguousarray(kinds, np.uint8)
+    errs = lib().bref_probe_sections_matrix(_p(sections), _p(sec_off), n_units, _p(blob), _p(key_off), _p(kinds), q,
+                                            _p(out), n_threads)
+    return out, errs
+
+
+def encode_sections(desc, words, n_units):
+    """-> (uint8 sections, uint64 sec_off[n_units+1]) in the on-disk framing."""
+    desc = np.ascontiguousarray(desc, DESC_DTYPE)
+    words = np.ascontiguousarray(words, np.uint64)
+    sec_off = np.zeros(n_units + 1, dtype=np.uint64)
+    total = lib().bref_encode_sections(_p(desc), _p(words), n_units, _p(sec_off), None)
+    out = np.zeros(max(int(total), 1), dtype=np.uint8)
+    lib().bref_encode_sections(_p(desc), _p(words), n_units, _p(sec_off), _p(out))
+    return out[:int(total)], sec_off

@@ -1,0 +1,353 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle,
+bit for bit, on the same seeded inputs.  Integer / byte work: the bar is exact equality."""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import pytest
+
+import bloomsearch_b200 as bs
+from bloomsearch_b200 import _native as N
+from oracle import bloomref as pyref
+from oracle import cref
+from oracle.corpus import SynthCorpus
+from tests.helpers import oracle_units, rand_keys
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------- K1 hash ---
+def test_hash_keys_matches_oracle_all_lengths(ctx):
+    rng = random.Random(1234)
+    keys = [b""] + [bytes(rng.randrange(256) for _ in range(L)) for L in range(0, 100) for _ in range(8)]
+    keys += [b"hello", b"hello, world", b"The quick brown fox jumps over the lazy dog.", b"service::auth"]
+    got = ctx.hash_keys(keys)
+    want = np.array([cref.base_hashes(k) for k in keys], dtype=np.uint64)
+    assert np.array_equal(got, want)
+    # public MurmurHash3_x64_128 vectors (h0,h1 are murmur(key, seed 0))
+    assert tuple(int(x) for x in got[keys.index(b"hello")][:2]) == (0xCBD8A7B341BD9B02, 0x5B1E906A48AE1D19)
+
+
+def test_hash_keys_long_and_empty(ctx):
+    rng = random.Random(5)
+    keys = [bytes(rng.randrange(256) for _ in range(L)) for L in (0, 1, 15, 16, 17, 31, 32, 33, 255, 256, 4097, 70001)]
+    got = ctx.hash_keys(keys)
+    want = np.array([cref.base_hashes(k) for k in keys], dtype=np.uint64)
+    assert np.array_equal(got, want)
+    assert ctx.hash_keys([]).shape == (0, 4)
+
+
+# ------------------------------------------------------------- K2/K3 build ---
+def _build_case(ctx, groups, fpr, file_of=None, n_files=0, file_counts=None):
+    """groups: list of key lists.  Returns (gpu_words, oracle_words)."""
+    keys = [k for g in groups for k in g]
+    blob, off = N.pack_keys(keys)
+    group_begin = np.cumsum([0] + [len(g) for g in groups]).astype(np.uint64)
+    desc, word_off = [], 0
+    for g in groups:
+        m, k = bs.estimate_parameters(max(len(g), 1), fpr)
+        desc.append((m, k, word_off))
+        word_off += (m + 63) // 64
+    gf = np.arange(len(groups), dtype=np.uint32)
+    gf2 = None
+    if file_of is not None:
+        fids = []
+        for f in range(n_files):
+            m, k = bs.estimate_parameters(max(file_counts[f], 1), fpr)
+            fids.append(len(desc))
+            desc.append((m, k, word_off))
+            word_off += (m + 63) // 64
+        gf2 = np.array([fids[f] if f >= 0 else N.NO_FILTER for f in file_of], dtype=np.uint32)
+    d = np.array(desc, dtype=N.DESC_DTYPE)
+    got = ctx.build(blob, off, group_begin, gf, gf2, d, word_off)
+    want = cref.build_filters(blob, off, group_begin, gf, gf2, d, word_off)
+    return got, want, d
+
+
+def test_build_matches_oracle_small(ctx):
+    rng = random.Random(7)
+    groups = [rand_keys(rng, n, 1, 30) for n in (0, 1, 2, 9, 100, 101, 1000, 2030)]
+    got, want, _ = _build_case(ctx, groups, 0.001)
+    assert np.array_equal(got, want)
+
+
+def test_build_sizing_matches_reference_pins(ctx):
+    # file_format_test.go:28-94: counts {2,101,101} sized like NewWithEstimates(count, fpr)
+    assert bs.estimate_parameters(2, 0.001) == cref.estimate_parameters(2, 0.001) == (29, 11)
+    assert bs.estimate_parameters(101, 0.001) == (1453, 10)
+    assert bs.estimate_parameters(2, 0.02) == (17, 6)  # lifecycle_durability_test.go:1195
+    assert bs.estimate_parameters(100, 0.01) == (959, 7)  # bloom_tree_engine_test.go:366
+    for n in (1, 3, 17, 1000, 10 ** 4, 10 ** 5, 10 ** 6, 12345678):
+        for p in (0.5, 0.1, 0.01, 0.001, 1e-6, 1e-9):
+            assert bs.estimate_parameters(n, p) == cref.estimate_parameters(n, p) == pyref.estimate_parameters(n, p)
+
+
+def test_build_with_file_level_union(ctx):
+    # flush.go:204-254: block filters + file filter sized for the union's distinct count
+    c = SynthCorpus(42, 0, 20, 500, 10)
+    groups, file_of = [], []
+    for b in range(c.n_blocks):
+        for kind in range(3):
+            groups.append(c.group_keys(b, kind))
+            file_of.append((b // c.blocks_per_file) * 3 + kind)
+    counts = [int(c.file_counts[f // 3][f % 3]) for f in range(c.n_files * 3)]
+    got, want, d = _build_case(ctx, groups, 0.001, file_of, c.n_files * 3, counts)
+    assert np.array_equal(got, want)
+    # and the file filter equals buildSizedBloomFilter(union) (duplicates are idempotent)
+    n_block_filters = len(groups)
+    for f in range(c.n_files * 3):
+        union = set()
+        for b in range((f // 3) * c.blocks_per_file, (f // 3 + 1) * c.blocks_per_file):
+            union.update(c.group_keys(b, f % 3))
+        assert len(union) == counts[f]
+        ref = cref.Filter.build_sized(sorted(union), 0.001)
+        m, k, wo = (int(x) for x in d[n_block_filters + f])
+        assert (ref.m, ref.k) == (m, k)
+        assert np.array_equal(got[wo:wo + ref.nwords], ref.words())
+
+
+def test_build_large_filter_global_atomics_and_split_groups(ctx):
+    # one filter of 300k keys: > shared-memory staging and > the 16k-key group split
+    keys = [b"key-%d" % i for i in range(300_000)]
+    got, want, d = _build_case(ctx, [keys], 0.001)
+    assert int(d[0]["m"]) > 227 * 1024 * 8
+    assert np.array_equal(got, want)
+
+
+def test_build_shared_filter_across_groups(ctx):
+    # shards of one entry set -> same filter: OR is idempotent and commutative
+    rng = random.Random(3)
+    keys = rand_keys(rng, 5000, 3, 20)
+    blob, off = N.pack_keys(keys)
+    m, k = bs.estimate_parameters(len(keys), 0.001)
+    d = np.array([(m, k, 0)], dtype=N.DESC_DTYPE)
+    gb = np.array([0, 1000, 1001, 3500, 5000], dtype=np.uint64)
+    gf = np.zeros(4, dtype=np.uint32)
+    got = ctx.build(blob, off, gb, gf, None, d, (m + 63) // 64)
+    ref = cref.Filter.build_sized(keys, 0.001)
+    assert np.array_equal(got, ref.words())
+
+
+def test_build_edge_m_values(ctx):
+    # Barrett reduction exactness on awkward moduli, incl. m == 1 and powers of two
+    rng = random.Random(11)
+    keys = rand_keys(rng, 64, 1, 12)
+    blob, off = N.pack_keys(keys)
+    ms = [1, 2, 3, 5, 63, 64, 65, 127, 128, 129, 4095, 4096, 4097, (1 << 20) - 1, 1 << 20, (1 << 20) + 1,
+          (1 << 27) - 1, 1 << 27, (1 << 32) + 7]
+    desc, wo = [], 0
+    for i, m in enumerate(ms):
+        desc.append((m, 1 + i % 13, wo))
+        wo += (m + 63) // 64
+    d = np.array(desc, dtype=N.DESC_DTYPE)
+    n = len(ms)
+    gb = (np.arange(0, n + 1) * 3).astype(np.uint64)  # 3 keys per filter, 57 <= 64 keys
+    gf = np.arange(n, dtype=np.uint32)
+    got = ctx.build(blob, off, gb, gf, None, d, wo)
+    want = cref.build_filters(blob, off, gb, gf, None, d, wo)
+    assert np.array_equal(got, want)
+
+
+# --------------------------------------------------------------- K4 probe ---
+def _probe_case(ctx, desc, words, keys, kinds, prog=None, paths=(N.PROBE_AUTO, N.PROBE_STAGED, N.PROBE_GATHER)):
+    n_units = len(desc) // 3
+    blob, off = N.pack_keys(keys)
+    kinds = np.asarray(kinds, dtype=np.uint8)
+    want_m = cref.probe_matrix(desc, words, n_units, blob, off, kinds)
+    want_mask = cref.probe_mask(desc, words, n_units, blob, off, kinds, prog)
+    corpus = bs.Corpus(ctx, desc, words)
+    try:
+        m, mask = corpus.probe(keys, kinds, prog)
+        assert np.array_equal(m, want_m)
+        assert np.array_equal(mask, want_mask)
+        for path in paths:
+            q = bs.Query(corpus, keys, kinds, prog)
+            q.run(path)
+            m2, mask2 = q.fetch()
+            q.close()
+            assert np.array_equal(m2, want_m), f"path {path}"
+            assert np.array_equal(mask2, want_mask), f"path {path}"
+    finally:
+        corpus.close()
+    return want_m, want_mask
+
+
+def _mixed_keys(rng, unit_keys, n_present, n_absent):
+    keys, kinds = [], []
+    flat = [(kind, k) for kinds_ in unit_keys for kind, ks in enumerate(kinds_) for k in ks]
+    for kind, k in rng.sample(flat, min(n_present, len(flat))):
+        keys.append(k)
+        kinds.append(kind)
+    for i in range(n_absent):
+        keys.append(b"absent%d" % i)
+        kinds.append(i % 3)
+    return keys, kinds
+
+
+def test_probe_matrix_and_mask_small_corpus(ctx):
+    rng = random.Random(21)
+    unit_keys = [(rand_keys(rng, 9, 3, 12), rand_keys(rng, 200 + 13 * u, 1, 16), rand_keys(rng, 210 + 7 * u, 4, 30))
+                 for u in range(37)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    keys, kinds = _mixed_keys(rng, unit_keys, 60, 40)
+    cq = bs.compile_bloom_query(bs.BloomQuery(bs.And(bs.Or(*[bs.Token(k) for k, kd in zip(keys, kinds) if kd == 1][:5]),
+                                                     bs.Field(unit_keys[0][0][0]))))
+    # use the raw key list with a hand-written program instead, exercising every op
+    prog = np.array([(N.OP_LEAF, 0), (N.OP_LEAF, 1), (N.OP_OR, 2), (N.OP_LEAF, 2), (N.OP_TRUE, 0), (N.OP_AND, 3),
+                     (N.OP_FALSE, 0), (N.OP_OR, 2)], dtype=N.OP_DTYPE)
+    want_m, want_mask = _probe_case(ctx, desc, words, keys, kinds, prog)
+    assert want_m.any() and not want_m.all()
+    assert cq.prog is not None
+
+
+@pytest.mark.parametrize("n_keys", [1, 2, 5, 8, 31, 32, 33, 64, 65, 511, 512, 513, 1000, 2049])
+def test_probe_key_count_boundaries(ctx, n_keys):
+    rng = random.Random(100 + n_keys)
+    unit_keys = [(rand_keys(rng, 5, 3, 8), rand_keys(rng, 150, 1, 10), rand_keys(rng, 160, 4, 20)) for _ in range(19)]
+    desc, words = oracle_units(unit_keys, 0.01)
+    keys, kinds = _mixed_keys(rng, unit_keys, n_keys // 2, n_keys - n_keys // 2)
+    _probe_case(ctx, desc, words, keys[:n_keys], kinds[:n_keys])
+
+
+def test_probe_absent_filters_fail_open_and_empty_cases(ctx):
+    rng = random.Random(9)
+    unit_keys = [(rand_keys(rng, 4, 3, 8), rand_keys(rng, 50, 1, 10), rand_keys(rng, 50, 4, 20)) for _ in range(6)]
+    absent = {(0, 0), (1, 1), (2, 2), (3, 0), (3, 1), (3, 2)}
+    desc, words = oracle_units(unit_keys, 0.001, absent)
+    keys, kinds = _mixed_keys(rng, unit_keys, 10, 11)
+    want_m, _ = _probe_case(ctx, desc, words, keys, kinds)
+    # unit 3 has no filters at all: every probe must say "maybe" (query_exec.go:137-151)
+    assert bs.unpack_matrix(want_m, len(keys))[3].all()
+    # no keys, no program: every unit survives (query_exec.go:81-83)
+    corpus = bs.Corpus(ctx, desc, words)
+    m, mask = corpus.probe([], [], None)
+    assert bs.unpack_mask(mask, corpus.n_units).all()
+    corpus.close()
+    # empty corpus
+    empty = bs.Corpus(ctx, np.zeros(0, N.DESC_DTYPE), np.zeros(0, np.uint64))
+    m, mask = empty.probe([b"x"], [1], None)
+    assert m.shape[0] == 0 and mask.shape[0] == 0
+    empty.close()
+
+
+def test_probe_large_filters_take_gather_path(ctx):
+    # file-level sized filters (> shared memory): only the gather path can serve them
+    big = [b"tok-%d" % i for i in range(400_000)]
+    f_big = cref.Filter.build_sized(big, 0.001)
+    small = [b"f%d" % i for i in range(9)]
+    f_small = cref.Filter.build_sized(small, 0.001)
+    desc = np.zeros(6, dtype=cref.DESC_DTYPE)
+    wb, ws = f_big.words(), f_small.words()
+    desc[0] = (f_small.m, f_small.k, 0)
+    desc[1] = (f_big.m, f_big.k, len(ws))
+    desc[3] = (f_small.m, f_small.k, 0)            # unit 1 shares the small field filter words
+    desc[4] = (f_small.m, f_small.k, 0)
+    words = np.concatenate([ws, wb])
+    keys = [b"tok-5", b"tok-399999", b"nope", b"f3", b"f9"] + [b"absent%d" % i for i in range(70)]
+    kinds = [1, 1, 1, 0, 0] + [1] * 70
+    want_m, _ = _probe_case(ctx, desc, words, keys, kinds)
+    bits = bs.unpack_matrix(want_m, len(keys))
+    assert bits[0, 0] and bits[0, 1] and bits[0, 3] and not bits[0, 4]
+
+
+def test_probe_big_endian_load_equals_native(ctx):
+    rng = random.Random(77)
+    unit_keys = [(rand_keys(rng, 5, 3, 8), rand_keys(rng, 300, 1, 10), rand_keys(rng, 300, 4, 20)) for _ in range(8)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    keys, kinds = _mixed_keys(rng, unit_keys, 30, 30)
+    blob, off = N.pack_keys(keys)
+    want = cref.probe_matrix(desc, words, 8, blob, off, np.asarray(kinds, np.uint8))
+    be = words.byteswap()  # what bitset.WriteTo puts on disk
+    corpus = bs.Corpus(ctx, desc, be, big_endian=True)
+    m, _ = corpus.probe(keys, kinds)
+    corpus.close()
+    assert np.array_equal(m, want)
+
+
+def test_synth_corpus_config2_shape_parity(ctx):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: GPU-built filters ==
+    oracle-built filters, GPU candidate matrix == oracle matrix, staged == gather."""
+    c = SynthCorpus(42, 0, 60, 1000, 10)
+    counts = c.group_counts()
+    desc = np.zeros(c.n_blocks * 3, dtype=N.DESC_DTYPE)
+    wo = 0
+    for g in range(c.n_blocks * 3):
+        m, k = bs.estimate_parameters(max(int(counts.reshape(-1)[g]), 1), 0.001)
+        desc[g] = (m, k, wo)
+        wo += (m + 63) // 64
+    gf = np.arange(c.n_blocks * 3, dtype=np.uint32)
+    words = ctx.build(c.blob, c.key_off, c.group_begin, gf, None, desc, wo)
+    want_words = cref.build_filters(c.blob, c.key_off, c.group_begin, gf, None, desc, wo, n_threads=4)
+    assert np.array_equal(words, want_words)
+    rng = random.Random(2)
+    present = [c.key(i) for i in rng.sample(range(c.n_keys), 500)]
+    kind_of = {}
+    for b in range(c.n_blocks):
+        for kind in range(3):
+            for i in range(int(c.group_begin[3 * b + kind]), int(c.group_begin[3 * b + kind + 1])):
+                kind_of.setdefault(i, kind)
+    idx = rng.sample(range(c.n_keys), 500)
+    keys = [c.key(i) for i in idx] + [b"absent%d" % i for i in range(500)]
+    kinds = [kind_of[i] for i in idx] + [i % 3 for i in range(500)]
+    _probe_case(ctx, desc, words, keys, kinds)
+    assert present
+
+
+# ------------------------------------------------- reference tests, mirrored ---
+def test_evaluate_bloom_filters_reference_cases(ctx):
+    """bloom_tree_engine_test.go:357-442 (TestEvaluateBloomFilters), same filters and queries,
+    evaluated on the GPU and by the oracle's recursive evaluator."""
+    def sized(entries):
+        f = cref.Filter.with_estimates(100, 0.01)
+        for e in entries:
+            f.add(e)
+        return f
+    ff = sized([b"user.name", b"user.age"])
+    tf = sized([b"alice", b"30"])
+    ftf = sized([bs.make_field_token_key(b"user.name", b"alice"), bs.make_field_token_key(b"user.age", b"30")])
+    assert (ff.m, ff.k) == (959, 7)
+    unit = bs.BloomFilters(*(bs.BloomFilter(f.m, f.k, f.words()) for f in (ff, tf, ftf)))
+    corpus = bs.Corpus.from_filters(ctx, [unit])
+    cases = [
+        ("nil query", None, True),
+        ("field exists", bs.NewQuery().Field("user.name").Build(), True),
+        ("field does not exist", bs.NewQuery().Field("nonexistent.field").Build(), False),
+        ("token exists", bs.NewQuery().Token("alice").Build(), True),
+        ("field-token exists", bs.NewQuery().FieldToken("user.name", "alice").Build(), True),
+        ("OR one match", bs.NewQuery().Match(bs.Or(bs.Field("nonexistent.field"), bs.Field("user.name"))).Build(), True),
+        ("AND one mismatch", bs.NewQuery().Match(bs.And(bs.Field("nonexistent.field"), bs.Field("user.name"))).Build(), False),
+        ("OR field / field-token", bs.NewQuery().Match(bs.Or(bs.Field("nonexistent.field"),
+                                                             bs.FieldToken("user.name", "alice"))).Build(), True),
+    ]
+    from bloomsearch_b200.query import to_oracle_tuple
+    for name, q, expected in cases:
+        got = bool(corpus.evaluate_bloom_filters(q)[0])
+        ref = cref.evaluate_bloom_filters(ff, tf, ftf, to_oracle_tuple(q.Expression) if q else None)
+        assert got == ref == expected, name
+    corpus.close()
+
+
+def test_example_config1_roundtrip(ctx):
+    """example_test.go:18-86 shape: 2 rows, 1 block; FieldToken("service","auth") keeps the block,
+    a token that is not there prunes it."""
+    es = bs.BloomEntrySets()
+    rows = [{"id": 1, "service": "auth", "message": "login timeout for user"},
+            {"id": 2, "service": "payment", "message": "charge succeeded"}]
+    for row in rows:
+        for path, value in row.items():
+            p = path.encode()
+            es.add_field(p)
+            for tok in str(value).lower().split():
+                es.add_token(tok.encode())
+                es.add_field_token(p, tok.encode())
+    filters = es.build_filters(ctx, 0.001)
+    for got, entries in zip(filters.as_tuple(), (es.fields, es.tokens, es.fieldTokens)):
+        ref = cref.Filter.build_sized(sorted(entries), 0.001)
+        assert (got.m, got.k) == (ref.m, ref.k)
+        assert np.array_equal(got.words, ref.words())
+    corpus = bs.Corpus.from_filters(ctx, [filters])
+    assert corpus.evaluate_bloom_filters(bs.NewQuery().FieldToken("service", "auth").Build())[0]
+    assert not corpus.evaluate_bloom_filters(bs.NewQuery().FieldToken("service", "billing").Build())[0]
+    assert not corpus.evaluate_bloom_filters(bs.NewQuery().Token("nonexistent-token").Build())[0]
+    corpus.close()
