@@ -249,17 +249,3 @@ def compile_bloom_query(query: Optional[BloomQuery]) -> CompiledQuery:
     out["op"] = arr[:, 0]
     out["arg"] = arr[:, 1]
     return CompiledQuery(keys, np.array(kinds, dtype=np.uint8), out)
-
-
-def to_oracle_tuple(e: Optional[BloomExpression]):
-    """Tree in the tuple form oracle/bloomref.py and oracle/cref.py evaluate (tests only)."""
-    if e is None:
-        return None
-    if e.ExpressionType == BloomExpressionCondition:
-        if e.Condition is None:
-            return ("COND", None)
-        c = e.Condition
-        return ("COND", (c.Type, _b(c.Field), _b(c.Token)))
-    if e.ExpressionType in (BloomExpressionAnd, BloomExpressionOr):
-        return (e.ExpressionType, [to_oracle_tuple(c) for c in e.Children])
-    return (e.ExpressionType, [])

@@ -36,3 +36,18 @@ def oracle_units(unit_keys, fpr, absent=()):
             off += len(w)
     words = np.concatenate(chunks) if chunks else np.zeros(0, np.uint64)
     return desc, words
+
+
+def to_oracle_tuple(e):
+    """bloomsearch_b200.query.BloomExpression -> the tuple form the oracle evaluators take."""
+    if e is None:
+        return None
+    b = lambda x: x if isinstance(x, (bytes, bytearray)) else str(x).encode()
+    if e.ExpressionType == "CONDITION":
+        if e.Condition is None:
+            return ("COND", None)
+        c = e.Condition
+        return ("COND", (c.Type, b(c.Field), b(c.Token)))
+    if e.ExpressionType in ("AND", "OR"):
+        return (e.ExpressionType, [to_oracle_tuple(c) for c in e.Children])
+    return (e.ExpressionType, [])

@@ -1,0 +1,82 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports exactly what
+include/bloomgpu.h declares, and fails loudly (never silently falls back) without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import bloomsearch_b200 as bs
+from bloomsearch_b200 import _native as N
+from oracle import cref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "bloomgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(bsg_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(N.ABI_SYMBOLS) == declared  # the Python binding tracks the header
+
+
+def test_abi_version_and_strerror():
+    lib = N.lib()
+    assert lib.bsg_abi_version() == 1
+    assert lib.bsg_strerror(0) == b"ok"
+    assert b"invalid" in lib.bsg_strerror(-1)
+    assert b"CUDA" in lib.bsg_strerror(-2)
+
+
+def test_header_cites_reference_call_sites():
+    hdr = open(os.path.join(ROOT, "include", "bloomgpu.h")).read()
+    for cite in ("ingest.go:127-145", "query_exec.go:75-159", "file_format.go:392-448", "flush.go:204,253"):
+        assert cite in hdr
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bs.BloomGpuError) as ei:
+        bs.Context(0)
+    assert ei.value.code == N.ERR_CUDA
+    assert "no CPU fallback" in ei.value.detail
+
+
+def test_null_arguments_are_rejected_not_crashing():
+    lib = N.lib()
+    assert lib.bsg_create(0, None) == N.ERR_INVALID
+    assert lib.bsg_synchronize(None) == N.ERR_INVALID
+    assert lib.bsg_probe(None, None, None, None, 0, None, None, 0, None, None) == N.ERR_INVALID
+    assert lib.bsg_build(None, None, None, 0, None, 0, None, None, None, 0, None, 0) == N.ERR_INVALID
+    assert lib.bsg_corpus_units(None) == 0
+    lib.bsg_corpus_free(None)
+    lib.bsg_query_free(None)
+    lib.bsg_destroy(None)
+
+
+def test_bsg_estimate_matches_oracle():
+    for n in (1, 2, 9, 100, 101, 220, 1000, 19557, 10 ** 6, 10 ** 8):
+        for p in (0.5, 0.02, 0.01, 0.001, 1e-9):
+            assert bs.estimate_parameters(n, p) == cref.estimate_parameters(n, p)
+
+
+def test_product_does_not_import_the_oracle():
+    """The product package must never route through oracle/ (tier rule)."""
+    pkg = os.path.join(ROOT, "bloomsearch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "bloomref" not in src and "from oracle" not in src and "import oracle" not in src, f

@@ -320,7 +320,7 @@ def test_evaluate_bloom_filters_reference_cases(ctx):
         ("OR field / field-token", bs.NewQuery().Match(bs.Or(bs.Field("nonexistent.field"),
                                                              bs.FieldToken("user.name", "alice"))).Build(), True),
     ]
-    from bloomsearch_b200.query import to_oracle_tuple
+    from tests.helpers import to_oracle_tuple
     for name, q, expected in cases:
         got = bool(corpus.evaluate_bloom_filters(q)[0])
         ref = cref.evaluate_bloom_filters(ff, tf, ftf, to_oracle_tuple(q.Expression) if q else None)
