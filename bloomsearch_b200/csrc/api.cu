@@ -355,7 +355,7 @@ struct bsg_corpus {
     int device = 0;
     uint64_t n_units = 0;
     DevFilter* d_udesc = nullptr;
-    UnitTab* d_utab = nullptr;
+    StageRow* d_stab = nullptr;  // one row per staged unit, staged order
     uint64_t* d_words = nullptr;
     uint64_t total_words = 0;
     uint32_t* d_staged_list = nullptr;  // nullptr when every unit is staged (identity list)
@@ -372,7 +372,7 @@ extern "C" void bsg_corpus_free(bsg_corpus* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_udesc);
-    cudaFree(c->d_utab);
+    cudaFree(c->d_stab);
     cudaFree(c->d_words);
     cudaFree(c->d_staged_list);
     cudaFree(c->d_gather_list);
@@ -440,16 +440,28 @@ int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
 int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter_desc* desc, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
     // staged vs gather: a unit is staged when at least 3 stages of its size fit
-    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - 2 * kProbeMaxStages * sizeof(uint64_t);
+    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - kProbeSmemPrefixBytes;
     const uint64_t unit_limit = budget / 3 - kProbeStageHeaderBytes;
     std::vector<uint32_t> staged, gather;
+    std::vector<StageRow> stab;
     uint32_t cap = 0;
     c->h_desc.resize(n_units * 3);
     for (uint64_t u = 0; u < n_units; ++u) {
         const uint64_t bytes = static_cast<uint64_t>(L.utab[u].total) * 8;
         const bool st = bytes <= unit_limit;
-        if (st) { staged.push_back(static_cast<uint32_t>(u)); cap = std::max<uint32_t>(cap, static_cast<uint32_t>(bytes)); }
-        else gather.push_back(static_cast<uint32_t>(u));
+        if (st) {
+            staged.push_back(static_cast<uint32_t>(u));
+            cap = std::max<uint32_t>(cap, static_cast<uint32_t>(bytes));
+            StageRow r;
+            r.unit = static_cast<uint32_t>(u);
+            r.total_words = L.utab[u].total;
+            r.word_base = L.utab[u].word_base;
+            for (int k = 0; k < 3; ++k) { r.nw[k] = L.utab[u].nw[k]; r.f[k] = L.udesc[u * 3 + k]; }
+            r.pad = 0;
+            stab.push_back(r);
+        } else {
+            gather.push_back(static_cast<uint32_t>(u));
+        }
         for (int k = 0; k < 3; ++k) {
             const bsg_filter_desc& d = desc[u * 3 + k];
             c->h_desc[u * 3 + k] = bsg_filter_desc{d.m, d.m ? d.k : 0, L.udesc[u * 3 + k].word_off};
@@ -462,6 +474,11 @@ int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter
     c->stage_cap_bytes = (cap + 15u) & ~15u;
     c->n_staged = static_cast<uint32_t>(staged.size());
     c->n_gather = static_cast<uint32_t>(gather.size());
+    if (!stab.empty()) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_stab), stab.size() * sizeof(StageRow)));
+        CUDA_TRY(cudaMemcpyAsync(c->d_stab, stab.data(), stab.size() * sizeof(StageRow), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));  // stab dies with this scope
+    }
     if (!gather.empty()) {
         CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_gather_list), gather.size() * 4));
         CUDA_TRY(cudaMemcpyAsync(c->d_gather_list, gather.data(), gather.size() * 4, cudaMemcpyHostToDevice, s));
@@ -502,14 +519,12 @@ extern "C" int bsg_corpus_load(bsg_ctx* ctx, const bsg_filter_desc* desc, uint64
     DevBuf<uint64_t> d_src, d_src_off;
     auto body = [&]() -> int {
         CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_udesc), std::max<uint64_t>(n_units * 3, 1) * sizeof(DevFilter)));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_utab), std::max<uint64_t>(n_units, 1) * sizeof(UnitTab)));
         CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_words), (L.total_words + 2) * 8));
         CUDA_TRY(d_src.alloc(n_words));
         CUDA_TRY(d_src_off.alloc(n_units * 3));
         CUDA_TRY(cudaMemsetAsync(c->d_words, 0, (L.total_words + 2) * 8, s));
         if (n_units) {
             CUDA_TRY(cudaMemcpyAsync(c->d_udesc, L.udesc.data(), n_units * 3 * sizeof(DevFilter), cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(c->d_utab, L.utab.data(), n_units * sizeof(UnitTab), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(d_src_off.p, src_off.data(), n_units * 3 * 8, cudaMemcpyHostToDevice, s));
         }
         if (n_words) CUDA_TRY(cudaMemcpyAsync(d_src.p, words, n_words * 8, cudaMemcpyHostToDevice, s));
@@ -671,26 +686,22 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             const uint64_t gather_bytes = static_cast<uint64_t>(c->n_staged) * q->n_keys * (4 * 32 + 32);
             use_staged = staged_bytes <= gather_bytes;
         }
-        const int cw = (ctx->probe_warps > 0 && ctx->probe_warps <= kProbeConsumerWarps) ? ctx->probe_warps
-                                                                                        : kProbeConsumerWarps;
         if (use_staged) {
             ProbeStagedPlan plan;
-            const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - 2 * kProbeMaxStages * sizeof(uint64_t);
+            const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - kProbeSmemPrefixBytes;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);
             const uint64_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
             if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
             plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, budget / stage_bytes));
             if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: stage does not fit shared memory");
-            plan.smem_bytes = 2 * kProbeMaxStages * sizeof(uint64_t) + plan.n_stages * stage_bytes;
+            plan.smem_bytes = kProbeSmemPrefixBytes + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(c->n_staged, ctx->sm_count));
-            plan.consumer_warps = cw;
-            const uint32_t pass_keys = cw * 32 * kProbeMaxKeysPerThread;
-            for (uint32_t kb = 0; kb < q->n_keys; kb += pass_keys) {
-                const uint32_t nk = std::min<uint32_t>(pass_keys, q->n_keys - kb);
-                CUDA_TRY(launch_probe_staged(plan, c->d_udesc, c->d_utab, c->d_words, c->d_staged_list, c->n_staged,
-                                             q->d_hashes, q->d_kinds, kb, nk, q->kind_mask, q->d_matrix32,
-                                             q->row_words32, s));
+            plan.warps = ctx->probe_warps;
+            for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
+                const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
+                CUDA_TRY(launch_probe_staged(plan, c->d_stab, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
+                                             q->kind_mask, q->d_matrix32, q->row_words32, s));
                 ++launches;
             }
         } else if (c->n_staged) {

@@ -129,6 +129,25 @@ __device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) 
     return r;
 }
 
+// Same reduction for m < 2^30, in 32-bit arithmetic only (12 instructions instead of
+// ~35 for the emulated 64x64 multiply-high): with I = inv = floor(2^64/m),
+//   step 1  t = hi32(x) mod m            (32-bit Barrett with hi32(I) = floor(2^32/m))
+//   step 2  y = t*2^32 + lo32(x) < m*2^32, so floor(y/m) < 2^32 and
+//           q = t*Ih + hi32(t*Il) + hi32(xl*Ih) is floor(y/m) - {0,1,2,3};
+//           y - q*m < 4m < 2^32 is exact in 32-bit wraparound arithmetic.
+// (proof in DESIGN.md; m == 1 works through inv = 2^64-1.)
+__device__ __forceinline__ uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih, uint32_t il) {
+    const uint32_t xh = static_cast<uint32_t>(x >> 32), xl = static_cast<uint32_t>(x);
+    uint32_t t = xh - __umulhi(xh, ih) * m;
+    if (t >= m) t -= m;
+    const uint32_t q = t * ih + __umulhi(t, il) + __umulhi(xl, ih);
+    uint32_t r = xl - q * m;
+    if (r >= 2u * m) r -= 2u * m;
+    if (r >= m) r -= m;
+    return r;
+}
+constexpr uint64_t kSmallModLimit = 1ull << 30;
+
 // -------------------------------------------------- mbarrier / bulk copy ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -166,6 +185,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); size and both
 // addresses must be multiples of 16 bytes.  Completion is signalled on `bar`.
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -29,6 +29,21 @@ struct __align__(16) UnitTab {
 };
 static_assert(sizeof(UnitTab) == 32, "UnitTab must be 32 bytes");
 
+// One row per staged unit, in staged order: the probe kernel bulk-copies the whole row
+// (descriptors + where the words live) into the stage header, and the 32-byte head of
+// the row of the unit that will occupy the same stage next.
+struct __align__(16) StageRow {
+    uint32_t unit;         // global unit id (matrix row)
+    uint32_t total_words;  // nw[0] + nw[1] + nw[2]
+    uint64_t word_base;    // first word of the unit's words (even)
+    uint32_t nw[3];        // padded word count per kind
+    uint32_t pad;
+    DevFilter f[3];
+};
+static_assert(sizeof(StageRow) == 128, "StageRow must be 128 bytes");
+constexpr uint32_t kStageRowBytes = 128;
+constexpr uint32_t kStageHeadBytes = 32;
+
 // Build-side filter descriptor (over the caller's out_words layout).
 struct __align__(16) BuildFilter {
     uint64_t word_off;
@@ -43,11 +58,10 @@ inline uint64_t reciprocal(uint64_t m) {
     return static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / m);
 }
 
-constexpr int kProbeConsumerWarps = 16;
-constexpr int kProbeThreads = (kProbeConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kProbeMaxStages = 16;
-constexpr int kProbeStageHeaderBytes = 128;  // 3 x DevFilter (96 B) + pad
-constexpr int kProbeMaxKeysPerThread = 4;    // staged path handles <= 16*32*4 = 2048 keys per pass
+constexpr int kProbeSmemPrefixBytes = 256;     // 16 mbarriers (128 B) + 16 done counters (64 B) + pad
+constexpr int kProbeStageHeaderBytes = 160;    // StageRow (128 B) + next unit's head (32 B)
+constexpr uint32_t kProbeMaxKeysPerPass = 1024;  // one key per thread, up to 32 warps
 
 // ---- launch wrappers (defined in the kernels_*.cu files) -------------------
 cudaError_t launch_hash_keys(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,
@@ -58,14 +72,13 @@ struct ProbeStagedPlan {
     uint32_t stage_data_bytes;  // per-stage capacity for filter words
     size_t smem_bytes;
     int grid;
-    int consumer_warps;  // 0 = default (kProbeConsumerWarps)
+    int warps;  // 0 = auto
 };
 cudaError_t probe_staged_configure(int max_smem_optin);
-cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const DevFilter* d_udesc, const UnitTab* d_utab,
-                                const uint64_t* d_words, const uint32_t* d_unit_list,
-                                uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t key_base,
-                                uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32, uint32_t row_words32,
-                                cudaStream_t s);
+cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
+                                const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
+                                uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
+                                uint32_t row_words32, cudaStream_t s);
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
                                 uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s);

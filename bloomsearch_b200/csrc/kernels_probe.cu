@@ -55,185 +55,206 @@ __device__ __forceinline__ bool test_hashes(const uint64_t h0, const uint64_t h1
 }
 
 // ------------------------------------------------------------ staged path ---
-// Shared-memory map: [full mbarriers x16][empty mbarriers x16] | stage 0 | stage 1 ...
-// stage = [128 B header: 3 x DevFilter, then {u32 unit, u32 pad, u64 word_base}] [unit words]
-struct StageHdrTail {
-    uint32_t unit;
-    uint32_t pad;
-    uint64_t word_base;
-};
+// Shared-memory map: [full mbarriers x16][done counters x16][pad] | stage 0 | stage 1 ...
+// stage = [StageRow of the unit, 128 B][head of the unit that will occupy this stage next, 32 B][unit words]
+// There is no producer warp: the warp whose release makes a stage free (last of n_warps to
+// bump done[s]) refills it at once, using the next unit's head that travelled in with the
+// current unit, so a refill never waits on a global load.
 
-template <int KPT>
-__global__ void __launch_bounds__(kProbeThreads, 1)
-probe_staged_kernel(const DevFilter* __restrict__ udesc, const UnitTab* __restrict__ utab,
-                    const uint64_t* __restrict__ words, const uint32_t* __restrict__ unit_list, uint32_t n_list,
+__device__ __forceinline__ void fill_stage(uint8_t* st, uint64_t* full_bar, const StageRow* __restrict__ stab,
+                                           uint32_t li, bool has_next, uint32_t li_next,
+                                           const uint64_t* __restrict__ words, uint64_t word_base, uint32_t nw0,
+                                           uint32_t nw1, uint32_t nw2, uint32_t kind_mask) {
+    const uint32_t b0 = (kind_mask & 1u) ? nw0 * 8u : 0u;
+    const uint32_t b1 = (kind_mask & 2u) ? nw1 * 8u : 0u;
+    const uint32_t b2 = (kind_mask & 4u) ? nw2 * 8u : 0u;
+    mbar_arrive_expect_tx(full_bar, kStageRowBytes + (has_next ? kStageHeadBytes : 0u) + b0 + b1 + b2);
+    bulk_g2s(st, &stab[li], kStageRowBytes, full_bar);
+    if (has_next) bulk_g2s(st + kStageRowBytes, &stab[li_next], kStageHeadBytes, full_bar);
+    uint8_t* data = st + kProbeStageHeaderBytes;
+    const uint64_t* src = words + word_base;
+    if (kind_mask == 7u) {
+        if (b0 + b1 + b2) bulk_g2s(data, src, b0 + b1 + b2, full_bar);
+    } else {
+        if (b0) bulk_g2s(data, src, b0, full_bar);
+        if (b1) bulk_g2s(data + nw0 * 8u, src + nw0, b1, full_bar);
+        if (b2) bulk_g2s(data + (nw0 + nw1) * 8u, src + nw0 + nw1, b2, full_bar);
+    }
+}
+
+// One membership test, m < 2^30, bitset in shared memory.
+__device__ __forceinline__ bool test_bit_s32(uint64_t loc, uint32_t m, uint32_t ih, uint32_t il,
+                                             const uint32_t* __restrict__ w32) {
+    const uint32_t bit = mod_m32(loc, m, ih, il);
+    return (w32[bit >> 5] >> (bit & 31u)) & 1u;
+}
+
+__device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
+                                                uint32_t ih, uint32_t il, uint32_t k,
+                                                const uint32_t* __restrict__ w32) {
+    uint64_t ih2 = 0, ih3 = 0;  // i*h2, i*h3 at i = multiple of 4
+    for (uint32_t i = 0; i < k; i += 4) {
+        if (!test_bit_s32(h0 + ih2, m, ih, il, w32)) return false;
+        if (i + 1 >= k) break;
+        if (!test_bit_s32(h1 + ih3 + h3, m, ih, il, w32)) return false;
+        if (i + 2 >= k) break;
+        if (!test_bit_s32(h0 + ih3 + 2 * h3, m, ih, il, w32)) return false;
+        if (i + 3 >= k) break;
+        if (!test_bit_s32(h1 + ih2 + 3 * h2, m, ih, il, w32)) return false;
+        ih2 += 4 * h2;
+        ih3 += 4 * h3;
+    }
+    return true;
+}
+
+// Same as test_hashes_s32 with the bitset read from global memory (gather path).
+__device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
+                                                uint32_t ih, uint32_t il, uint32_t k,
+                                                const uint32_t* __restrict__ w32) {
+    auto test = [&](uint64_t loc) {
+        const uint32_t bit = mod_m32(loc, m, ih, il);
+        return (__ldg(w32 + (bit >> 5)) >> (bit & 31u)) & 1u;
+    };
+    uint64_t ih2 = 0, ih3 = 0;
+    for (uint32_t i = 0; i < k; i += 4) {
+        if (!test(h0 + ih2)) return false;
+        if (i + 1 >= k) break;
+        if (!test(h1 + ih3 + h3)) return false;
+        if (i + 2 >= k) break;
+        if (!test(h0 + ih3 + 2 * h3)) return false;
+        if (i + 3 >= k) break;
+        if (!test(h1 + ih2 + 3 * h2)) return false;
+        ih2 += 4 * h2;
+        ih3 += 4 * h3;
+    }
+    return true;
+}
+
+template <int KPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
                     int n_stages, uint32_t stage_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + kProbeMaxStages;
-    uint8_t* stages = smem + 2 * kProbeMaxStages * sizeof(uint64_t);
+    uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
+    uint8_t* stages = smem + kProbeSmemPrefixBytes;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
     const uint32_t warp = tid >> 5;
-    const uint32_t n_cwarps = (blockDim.x >> 5) - 1;  // last warp is the producer
+    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t G = gridDim.x;
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], n_cwarps);
+            done[s] = 0;
         }
         fence_barrier_init();
     }
     __syncthreads();
 
-    const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
-    if (warp == n_cwarps) {
-        // ===== producer warp: lanes prefetch 32 UnitTabs at a time, lane 0 issues bulk copies =====
-        for (uint32_t it0 = 0; it0 < my_count; it0 += 32) {
-            const uint32_t it_l = it0 + lane;
-            uint32_t unit_l = 0;
-            UnitTab ut_l = {0, {0, 0, 0}, 0, 0};
-            if (it_l < my_count) {
-                const uint32_t li = blockIdx.x + it_l * gridDim.x;
-                unit_l = unit_list ? __ldg(&unit_list[li]) : li;
-                const uint4* p = reinterpret_cast<const uint4*>(&utab[unit_l]);
-                const uint4 a = __ldg(p);
-                const uint4 b = __ldg(p + 1);
-                ut_l.word_base = (static_cast<uint64_t>(a.y) << 32) | a.x;
-                ut_l.nw[0] = a.z; ut_l.nw[1] = a.w; ut_l.nw[2] = b.x; ut_l.total = b.y;
-            }
-            const uint32_t nb = min(32u, my_count - it0);
-            for (uint32_t j = 0; j < nb; ++j) {
-                const uint32_t unit = __shfl_sync(0xffffffffu, unit_l, j);
-                const uint32_t wb_lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(ut_l.word_base), j);
-                const uint32_t wb_hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(ut_l.word_base >> 32), j);
-                const uint32_t nw0 = __shfl_sync(0xffffffffu, ut_l.nw[0], j);
-                const uint32_t nw1 = __shfl_sync(0xffffffffu, ut_l.nw[1], j);
-                const uint32_t nw2 = __shfl_sync(0xffffffffu, ut_l.nw[2], j);
-                const uint32_t it = it0 + j;
-                const int s = it % n_stages;
-                const uint32_t ph = (it / n_stages) & 1u;
-                if (lane == 0) {
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
-                    const uint64_t word_base = (static_cast<uint64_t>(wb_hi) << 32) | wb_lo;
-                    StageHdrTail* tail = reinterpret_cast<StageHdrTail*>(st + 3 * sizeof(DevFilter));
-                    tail->unit = unit;
-                    tail->pad = 0;
-                    tail->word_base = word_base;
-                    const uint32_t b0 = (kind_mask & 1u) ? nw0 * 8u : 0u;
-                    const uint32_t b1 = (kind_mask & 2u) ? nw1 * 8u : 0u;
-                    const uint32_t b2 = (kind_mask & 4u) ? nw2 * 8u : 0u;
-                    mbar_arrive_expect_tx(&full[s], 3u * sizeof(DevFilter) + b0 + b1 + b2);
-                    bulk_g2s(st, &udesc[static_cast<size_t>(unit) * 3], 3u * sizeof(DevFilter), &full[s]);
-                    uint8_t* data = st + kProbeStageHeaderBytes;
-                    const uint64_t* src = words + word_base;
-                    if (kind_mask == 7u) {
-                        if (b0 + b1 + b2) bulk_g2s(data, src, b0 + b1 + b2, &full[s]);
-                    } else {
-                        if (b0) bulk_g2s(data, src, b0, &full[s]);
-                        if (b1) bulk_g2s(data + nw0 * 8u, src + nw0, b1, &full[s]);
-                        if (b2) bulk_g2s(data + (nw0 + nw1) * 8u, src + nw0 + nw1, b2, &full[s]);
-                    }
-                }
-                __syncwarp();
-            }
+    // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit ----
+    if (warp == 0 && lane < static_cast<uint32_t>(n_stages) && lane < my_count) {
+        const uint32_t li = blockIdx.x + lane * G;
+        const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
+        const uint4 a = __ldg(hp), b = __ldg(hp + 1);
+        const uint64_t word_base = (static_cast<uint64_t>(a.w) << 32) | a.z;
+        const bool has_next = lane + n_stages < my_count;
+        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, has_next,
+                   li + n_stages * G, words, word_base, b.x, b.y, b.z, kind_mask);
+    }
+
+    // ---- this thread's keys: key_base + j*blockDim + tid ----
+    uint64_t h[KPT][4];
+    uint32_t kd[KPT];
+    bool valid[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const uint32_t qrel = j * blockDim.x + tid;
+        valid[j] = qrel < n_keys;
+        kd[j] = 0;
+        h[j][0] = h[j][1] = h[j][2] = h[j][3] = 0;
+        if (valid[j]) {
+            const uint32_t q = key_base + qrel;
+            const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+            const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+            h[j][0] = a.x; h[j][1] = a.y; h[j][2] = b.x; h[j][3] = b.y;
+            kd[j] = __ldg(&kinds[q]);
         }
-    } else {
-        // ===== consumer warps: thread owns keys key_base + j*(n_cwarps*32) + tid =====
-        const uint32_t cthreads = n_cwarps * 32;
-        uint64_t h[KPT][4];
-        uint32_t kd[KPT];
-        bool valid[KPT];
+    }
+
+    for (uint32_t it = 0; it < my_count; ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1u;
+        mbar_wait(&full[s], ph);
+        uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
+        const StageRow* row = reinterpret_cast<const StageRow*>(st);
+        const uint32_t unit = row->unit;
+        const uint64_t word_base = row->word_base;
+        const uint32_t* data32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes);
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
-            const uint32_t qrel = j * cthreads + tid;
-            valid[j] = qrel < n_keys;
-            kd[j] = 0;
-            h[j][0] = h[j][1] = h[j][2] = h[j][3] = 0;
+            const uint32_t group_first = j * blockDim.x + warp * 32;  // warp-uniform
+            if (group_first >= n_keys) break;
+            bool res = false;
             if (valid[j]) {
-                const uint32_t q = key_base + qrel;
-                const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-                const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-                h[j][0] = a.x; h[j][1] = a.y; h[j][2] = b.x; h[j][3] = b.y;
-                kd[j] = __ldg(&kinds[q]);
-            }
-        }
-        for (uint32_t it = 0; it < my_count; ++it) {
-            const int s = it % n_stages;
-            const uint32_t ph = (it / n_stages) & 1u;
-            mbar_wait(&full[s], ph);
-            const uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
-            const DevFilter* hdr = reinterpret_cast<const DevFilter*>(st);
-            const StageHdrTail* tail = reinterpret_cast<const StageHdrTail*>(st + 3 * sizeof(DevFilter));
-            const uint32_t unit = tail->unit;
-            const uint64_t word_base = tail->word_base;
-            const uint32_t* data32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes);
-#pragma unroll
-            for (int j = 0; j < KPT; ++j) {
-                // warp-uniform: does this warp's 32-key group hold any key?
-                const uint32_t group_first = j * cthreads + warp * 32;
-                if (group_first >= n_keys) break;
-                bool res = false;
-                if (valid[j]) {
-                    const DevFilter f = hdr[kd[j]];
-                    if (f.m == 0) {
-                        res = true;  // absent filter cannot disqualify (query_exec.go:137-151)
-                    } else {
-                        const uint32_t* w32 = data32 + static_cast<uint32_t>(f.word_off - word_base) * 2u;
-                        res = test_hashes(h[j][0], h[j][1], h[j][2], h[j][3], f.m, f.inv, f.k,
-                                          [&](uint64_t idx) { return w32[static_cast<uint32_t>(idx)]; });
-                    }
+                const DevFilter f = row->f[kd[j]];
+                if (f.m == 0) {
+                    res = true;  // absent filter cannot disqualify (query_exec.go:137-151)
+                } else {
+                    const uint32_t* w32 = data32 + static_cast<uint32_t>(f.word_off - word_base) * 2u;
+                    res = test_hashes_s32(h[j][0], h[j][1], h[j][2], h[j][3], static_cast<uint32_t>(f.m),
+                                          static_cast<uint32_t>(f.inv >> 32), static_cast<uint32_t>(f.inv), f.k, w32);
                 }
-                const uint32_t bits = __ballot_sync(0xffffffffu, res);
-                if (lane == 0)
-                    matrix32[static_cast<size_t>(unit) * row_words32 + ((key_base + group_first) >> 5)] = bits;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            const uint32_t bits = __ballot_sync(0xffffffffu, res);
+            if (lane == 0) matrix32[static_cast<size_t>(unit) * row_words32 + ((key_base + group_first) >> 5)] = bits;
+        }
+        // ---- release: the last warp out refills this stage with unit it + n_stages ----
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
+            if (old == n_warps - 1) {
+                done[s] = 0;
+                const uint32_t nxt = it + n_stages;
+                if (nxt < my_count) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
+                    const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
+                    const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
+                    fence_proxy_async();
+                    fill_stage(st, &full[s], stab, blockIdx.x + nxt * G, nxt + n_stages < my_count,
+                               blockIdx.x + (nxt + n_stages) * G, words, nwb, b.x, b.y, b.z, kind_mask);
+                }
+            }
         }
     }
 }
 
-static int g_max_smem_optin = 0;  // recorded for diagnostics
-
 cudaError_t probe_staged_configure(int max_smem_optin) {
-    g_max_smem_optin = max_smem_optin;
-    (void)g_max_smem_optin;
-    cudaError_t e;
-    e = cudaFuncSetAttribute(probe_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(probe_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(probe_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    return e;
+    return cudaFuncSetAttribute(probe_staged_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                max_smem_optin);
 }
 
-cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const DevFilter* d_udesc, const UnitTab* d_utab,
-                                const uint64_t* d_words, const uint32_t* d_unit_list, uint32_t n_list,
-                                const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t key_base, uint32_t n_keys,
-                                uint32_t kind_mask, uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s) {
+cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
+                                const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
+                                uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
+                                uint32_t row_words32, cudaStream_t s) {
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
-    // consumer warps: as few rounds as possible, then as few idle lanes as possible
-    const int cw = (plan.consumer_warps > 0 && plan.consumer_warps <= kProbeConsumerWarps) ? plan.consumer_warps
-                                                                                          : kProbeConsumerWarps;
-    const uint32_t cthreads = cw * 32;
-    const uint32_t kpt = (n_keys + cthreads - 1) / cthreads;
+    if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
-    const dim3 grid(plan.grid), block((cw + 1) * 32);
-#define BSG_LAUNCH(KPT)                                                                                        \
-    probe_staged_kernel<KPT><<<grid, block, plan.smem_bytes, s>>>(d_udesc, d_utab, d_words, d_unit_list, n_list, \
-                                                                  d_hashes, d_kinds, key_base, n_keys, kind_mask, \
-                                                                  d_matrix32, row_words32, plan.n_stages, stage_bytes)
-    if (kpt <= 1) BSG_LAUNCH(1);
-    else if (kpt <= 2) BSG_LAUNCH(2);
-    else if (kpt <= 4) BSG_LAUNCH(4);
-    else return cudaErrorInvalidValue;
-#undef BSG_LAUNCH
+    // one key per thread; at least 4 warps so a tiny batch still has some latency hiding
+    uint32_t warps = (n_keys + 31) / 32;
+    if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
+    if (warps < 4) warps = 4;
+    if (warps > 32) warps = 32;
+    probe_staged_kernel<1, 1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
+        d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+        plan.n_stages, stage_bytes);
     return cudaGetLastError();
 }
 
@@ -278,7 +299,11 @@ probe_gather_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restr
                 res = true;
             } else {
                 const uint32_t* w32 = reinterpret_cast<const uint32_t*>(words + word_off);
-                res = test_hashes(a.x, a.y, b.x, b.y, m, inv, k, [&](uint64_t idx) { return __ldg(w32 + idx); });
+                if (m < kSmallModLimit)
+                    res = test_hashes_g32(a.x, a.y, b.x, b.y, static_cast<uint32_t>(m), static_cast<uint32_t>(inv >> 32),
+                                          static_cast<uint32_t>(inv), k, w32);
+                else
+                    res = test_hashes(a.x, a.y, b.x, b.y, m, inv, k, [&](uint64_t idx) { return __ldg(w32 + idx); });
             }
         }
     }
