@@ -456,7 +456,14 @@ int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter
             r.unit = static_cast<uint32_t>(u);
             r.total_words = L.utab[u].total;
             r.word_base = L.utab[u].word_base;
-            for (int k = 0; k < 3; ++k) { r.nw[k] = L.utab[u].nw[k]; r.f[k] = L.udesc[u * 3 + k]; }
+            uint32_t rel = 0;
+            for (int k = 0; k < 3; ++k) {
+                const DevFilter& d = L.udesc[u * 3 + k];
+                r.nw[k] = L.utab[u].nw[k];
+                r.f[k] = StageFilter{static_cast<uint32_t>(d.m), d.k, static_cast<uint32_t>(d.inv >> 32),
+                                     static_cast<uint32_t>(d.inv), rel, {0, 0, 0}};
+                rel += L.utab[u].nw[k] * 8u;
+            }
             r.pad = 0;
             stab.push_back(r);
         } else {

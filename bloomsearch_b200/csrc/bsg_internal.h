@@ -32,13 +32,21 @@ static_assert(sizeof(UnitTab) == 32, "UnitTab must be 32 bytes");
 // One row per staged unit, in staged order: the probe kernel bulk-copies the whole row
 // (descriptors + where the words live) into the stage header, and the 32-byte head of
 // the row of the unit that will occupy the same stage next.
+struct __align__(16) StageFilter {  // staged filters always have m < 2^30 (they fit shared memory)
+    uint32_t m;          // bits; 0 = filter absent
+    uint32_t k;          // hash functions
+    uint32_t ih, il;     // hi/lo halves of floor(2^64/m), see mod_m32
+    uint32_t rel_bytes;  // byte offset of the filter's words inside the stage data area
+    uint32_t pad[3];
+};
+static_assert(sizeof(StageFilter) == 32, "StageFilter must be 32 bytes");
 struct __align__(16) StageRow {
     uint32_t unit;         // global unit id (matrix row)
     uint32_t total_words;  // nw[0] + nw[1] + nw[2]
     uint64_t word_base;    // first word of the unit's words (even)
     uint32_t nw[3];        // padded word count per kind
     uint32_t pad;
-    DevFilter f[3];
+    StageFilter f[3];
 };
 static_assert(sizeof(StageRow) == 128, "StageRow must be 128 bytes");
 constexpr uint32_t kStageRowBytes = 128;

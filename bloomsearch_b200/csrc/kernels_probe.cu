@@ -82,32 +82,8 @@ __device__ __forceinline__ void fill_stage(uint8_t* st, uint64_t* full_bar, cons
     }
 }
 
-// One membership test, m < 2^30, bitset in shared memory.
-__device__ __forceinline__ bool test_bit_s32(uint64_t loc, uint32_t m, uint32_t ih, uint32_t il,
-                                             const uint32_t* __restrict__ w32) {
-    const uint32_t bit = mod_m32(loc, m, ih, il);
-    return (w32[bit >> 5] >> (bit & 31u)) & 1u;
-}
-
-__device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
-                                                uint32_t ih, uint32_t il, uint32_t k,
-                                                const uint32_t* __restrict__ w32) {
-    uint64_t ih2 = 0, ih3 = 0;  // i*h2, i*h3 at i = multiple of 4
-    for (uint32_t i = 0; i < k; i += 4) {
-        if (!test_bit_s32(h0 + ih2, m, ih, il, w32)) return false;
-        if (i + 1 >= k) break;
-        if (!test_bit_s32(h1 + ih3 + h3, m, ih, il, w32)) return false;
-        if (i + 2 >= k) break;
-        if (!test_bit_s32(h0 + ih3 + 2 * h3, m, ih, il, w32)) return false;
-        if (i + 3 >= k) break;
-        if (!test_bit_s32(h1 + ih2 + 3 * h2, m, ih, il, w32)) return false;
-        ih2 += 4 * h2;
-        ih3 += 4 * h3;
-    }
-    return true;
-}
-
-// Same as test_hashes_s32 with the bitset read from global memory (gather path).
+// Same as test_hashes with the 32-bit modulo and the bitset read from global memory
+// (gather path, m < 2^30).
 __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
                                                 uint32_t ih, uint32_t il, uint32_t k,
                                                 const uint32_t* __restrict__ w32) {
@@ -130,12 +106,18 @@ __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64
     return true;
 }
 
-template <int KPT, int MAXT>
+// The staged probe.  One key per thread; every lane walks this CTA's units at its own
+// pace (a per-lane state machine: one bit test per loop iteration) inside the window of
+// resident stages, so a lane whose key fails on its first bit moves on to the next unit
+// instead of idling until the slowest lane of its warp finishes (TestString's early
+// exit, query_exec.go:128-159, makes per-probe work geometric: mean 2 tests, max-of-32
+// about 6).  A warp releases a stage once its slowest lane has passed it.
+template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
-                    int n_stages, uint32_t stage_bytes) {
+                    uint32_t n_stages, uint32_t stage_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
@@ -146,9 +128,10 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t warp = tid >> 5;
     const uint32_t n_warps = blockDim.x >> 5;
     const uint32_t G = gridDim.x;
+    const uint32_t S = n_stages;
 
     if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) {
+        for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             done[s] = 0;
         }
@@ -159,84 +142,108 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
     // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit ----
-    if (warp == 0 && lane < static_cast<uint32_t>(n_stages) && lane < my_count) {
+    if (warp == 0 && lane < S && lane < my_count) {
         const uint32_t li = blockIdx.x + lane * G;
         const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
         const uint4 a = __ldg(hp), b = __ldg(hp + 1);
         const uint64_t word_base = (static_cast<uint64_t>(a.w) << 32) | a.z;
-        const bool has_next = lane + n_stages < my_count;
-        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, has_next,
-                   li + n_stages * G, words, word_base, b.x, b.y, b.z, kind_mask);
+        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
+                   li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
 
-    // ---- this thread's keys: key_base + j*blockDim + tid ----
-    uint64_t h[KPT][4];
-    uint32_t kd[KPT];
-    bool valid[KPT];
-#pragma unroll
-    for (int j = 0; j < KPT; ++j) {
-        const uint32_t qrel = j * blockDim.x + tid;
-        valid[j] = qrel < n_keys;
-        kd[j] = 0;
-        h[j][0] = h[j][1] = h[j][2] = h[j][3] = 0;
-        if (valid[j]) {
-            const uint32_t q = key_base + qrel;
-            const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-            const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-            h[j][0] = a.x; h[j][1] = a.y; h[j][2] = b.x; h[j][3] = b.y;
-            kd[j] = __ldg(&kinds[q]);
-        }
+    // ---- this thread's key ----
+    const bool valid = tid < n_keys;
+    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    uint32_t kd = 0;
+    if (valid) {
+        const uint32_t q = key_base + tid;
+        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+        const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+        h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
+        kd = __ldg(&kinds[q]);
     }
+    const bool warp_has_keys = warp * 32 < n_keys;
+    const uint32_t out_word = (key_base + warp * 32) >> 5;
 
-    for (uint32_t it = 0; it < my_count; ++it) {
-        const int s = it % n_stages;
-        const uint32_t ph = (it / n_stages) & 1u;
-        mbar_wait(&full[s], ph);
-        uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
-        const StageRow* row = reinterpret_cast<const StageRow*>(st);
-        const uint32_t unit = row->unit;
-        const uint64_t word_base = row->word_base;
-        const uint32_t* data32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes);
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-            const uint32_t group_first = j * blockDim.x + warp * 32;  // warp-uniform
-            if (group_first >= n_keys) break;
-            bool res = false;
-            if (valid[j]) {
-                const DevFilter f = row->f[kd[j]];
-                if (f.m == 0) {
-                    res = true;  // absent filter cannot disqualify (query_exec.go:137-151)
-                } else {
-                    const uint32_t* w32 = data32 + static_cast<uint32_t>(f.word_off - word_base) * 2u;
-                    res = test_hashes_s32(h[j][0], h[j][1], h[j][2], h[j][3], static_cast<uint32_t>(f.m),
-                                          static_cast<uint32_t>(f.inv >> 32), static_cast<uint32_t>(f.inv), f.k, w32);
-                }
+    // per-lane cursor
+    uint32_t u = valid ? 0u : 0xffffffffu;  // unit (index in this CTA's sequence) the lane is working on
+    uint32_t su = 0;                        // u % S
+    uint32_t i = 0;                         // next test index
+    bool need = true;                       // filter parameters of unit u not loaded yet
+    uint32_t fm = 0, fk = 0, fih = 0, fil = 0;
+    const uint32_t* w32 = nullptr;
+    uint32_t resbits = 0;                   // bit (unit - base) = result for that unit
+    // warp-uniform window
+    uint32_t base = 0, sbase = 0;           // oldest unit not yet released by this warp
+    uint32_t ready = 0, sready = 0, phready = 0;  // units [0, ready) are known to be resident
+
+    while (base < my_count) {
+        // (A) observe one more arrived stage, without blocking
+        if (ready < my_count && ready < base + S) {
+            if (mbar_try_wait(&full[sready], phready)) {
+                ++ready;
+                if (++sready == S) { sready = 0; phready ^= 1u; }
             }
-            const uint32_t bits = __ballot_sync(0xffffffffu, res);
-            if (lane == 0) matrix32[static_cast<size_t>(unit) * row_words32 + ((key_base + group_first) >> 5)] = bits;
         }
-        // ---- release: the last warp out refills this stage with unit it + n_stages ----
-        __syncwarp();
-        if (lane == 0) {
-            const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
-            if (old == n_warps - 1) {
-                done[s] = 0;
-                const uint32_t nxt = it + n_stages;
-                if (nxt < my_count) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
-                    const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
-                    const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
-                    fence_proxy_async();
-                    fill_stage(st, &full[s], stab, blockIdx.x + nxt * G, nxt + n_stages < my_count,
-                               blockIdx.x + (nxt + n_stages) * G, words, nwb, b.x, b.y, b.z, kind_mask);
+        // (B) one step of this lane's probe
+        if (u < ready) {
+            if (need) {
+                const uint8_t* st = stages + static_cast<size_t>(su) * stage_bytes;
+                const StageFilter f = reinterpret_cast<const StageRow*>(st)->f[kd];
+                fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
+                w32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + f.rel_bytes);
+                need = false;
+                i = 0;
+            }
+            bool pass = true, fin = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
+            if (fm != 0) {
+                // location(h,i) = h[i%2] + i*h[2+(((i+(i%2))%4)/2)]
+                const uint64_t a = (i & 1u) ? h1 : h0;
+                const uint64_t b = (((i + (i & 1u)) & 3u) >> 1) ? h3 : h2;
+                const uint32_t bit = mod_m32(a + static_cast<uint64_t>(i) * b, fm, fih, fil);
+                pass = (w32[bit >> 5] >> (bit & 31u)) & 1u;
+                ++i;
+                fin = !pass || i == fk;
+            }
+            if (fin) {
+                resbits |= (pass ? 1u : 0u) << (u - base);
+                ++u;
+                if (++su == S) su = 0;
+                need = true;
+            }
+        }
+        // (C) release every unit the whole warp has passed (never before its fill was observed)
+        uint32_t mu = __reduce_min_sync(0xffffffffu, u);
+        mu = min(mu, ready);
+        while (base < mu) {
+            uint8_t* st = stages + static_cast<size_t>(sbase) * stage_bytes;
+            const uint32_t bits = __ballot_sync(0xffffffffu, resbits & 1u);
+            resbits >>= 1;
+            if (lane == 0) {
+                const uint32_t unit = reinterpret_cast<const StageRow*>(st)->unit;
+                if (warp_has_keys) matrix32[static_cast<size_t>(unit) * row_words32 + out_word] = bits;
+                const uint32_t old = atom_add_acq_rel_shared(&done[sbase], 1u);
+                if (old == n_warps - 1) {  // last warp out refills the stage with unit base + S
+                    done[sbase] = 0;
+                    const uint32_t nxt = base + S;
+                    if (nxt < my_count) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
+                        const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
+                        const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
+                        fence_proxy_async();
+                        fill_stage(st, &full[sbase], stab, blockIdx.x + nxt * G, nxt + S < my_count,
+                                   blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask);
+                    }
                 }
             }
+            ++base;
+            if (++sbase == S) sbase = 0;
         }
     }
 }
 
 cudaError_t probe_staged_configure(int max_smem_optin) {
-    return cudaFuncSetAttribute(probe_staged_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(probe_staged_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 max_smem_optin);
 }
 
@@ -252,9 +259,9 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
-    probe_staged_kernel<1, 1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
+    probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
         d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-        plan.n_stages, stage_bytes);
+        static_cast<uint32_t>(plan.n_stages), stage_bytes);
     return cudaGetLastError();
 }
 
