@@ -106,12 +106,15 @@ __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64
     return true;
 }
 
-// The staged probe.  One key per thread; every lane walks this CTA's units at its own
+// The staged probe.  Each warp owns 32 keys; every lane walks this CTA's units at its own
 // pace (a per-lane state machine: one bit test per loop iteration) inside the window of
-// resident stages, so a lane whose key fails on its first bit moves on to the next unit
-// instead of idling until the slowest lane of its warp finishes (TestString's early
-// exit, query_exec.go:128-159, makes per-probe work geometric: mean 2 tests, max-of-32
-// about 6).  A warp releases a stage once its slowest lane has passed it.
+// resident stages, so a lane whose probe fails on its first bit moves on to the next unit
+// instead of idling until the slowest lane of its warp finishes (TestString's early exit,
+// query_exec.go:128-159, makes per-probe work geometric: mean 2 tests, max-of-32 about 6).
+// The key a lane probes ROTATES with the unit — lane l takes key (l + unit) mod 32 of its
+// warp's group — so a key that is present in every unit (always k tests) never pins one
+// lane as a permanent straggler.  A warp releases a stage once its slowest lane has
+// passed it; the last warp to release refills it.
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
@@ -151,52 +154,60 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                    li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
 
-    // ---- this thread's key ----
-    const bool valid = tid < n_keys;
-    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    uint32_t kd = 0;
-    if (valid) {
-        const uint32_t q = key_base + tid;
-        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-        const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-        h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
-        kd = __ldg(&kinds[q]);
-    }
-    const bool warp_has_keys = warp * 32 < n_keys;
-    const uint32_t out_word = (key_base + warp * 32) >> 5;
+    const uint32_t group_first = warp * 32;              // this warp's keys: [group_first, group_first + 32)
+    const bool warp_has_keys = group_first < n_keys;
+    const uint32_t out_word = (key_base + group_first) >> 5;
 
     // per-lane cursor
-    uint32_t u = valid ? 0u : 0xffffffffu;  // unit (index in this CTA's sequence) the lane is working on
-    uint32_t su = 0;                        // u % S
-    uint32_t i = 0;                         // next test index
-    bool need = true;                       // filter parameters of unit u not loaded yet
+    uint32_t u = warp_has_keys ? 0u : 0xffffffffu;  // unit (index in this CTA's sequence) the lane works on
+    uint32_t su = 0;                                // u % S
+    uint32_t i = 0;                                 // next test index
+    bool need = true;                               // key + filter parameters of item (u, key) not loaded yet
+    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
     uint32_t fm = 0, fk = 0, fih = 0, fil = 0;
     const uint32_t* w32 = nullptr;
-    uint32_t resbits = 0;                   // bit (unit - base) = result for that unit
+    uint32_t resbits = 0;                           // bit (unit - base) = this lane's result for that unit
     // warp-uniform window
-    uint32_t base = 0, sbase = 0;           // oldest unit not yet released by this warp
-    uint32_t ready = 0, sready = 0, phready = 0;  // units [0, ready) are known to be resident
+    uint32_t base = 0, sbase = 0;                   // oldest unit not yet released by this warp
+    uint32_t ready = 0, sready = 0, phready = 0;    // units [0, ready) are known to be resident
 
     while (base < my_count) {
-        // (A) observe one more arrived stage, without blocking
-        if (ready < my_count && ready < base + S) {
-            if (mbar_try_wait(&full[sready], phready)) {
-                ++ready;
-                if (++sready == S) { sready = 0; phready ^= 1u; }
+        // (A) poll (non-blocking) whether one more stage has arrived; the answer is consumed
+        //     after this iteration's lane step so the poll's latency overlaps it.  When no lane
+        //     can work at all, block on the barrier instead of spinning.
+        const bool can_poll = ready < my_count && ready < base + S;
+        bool arrived = false;
+        if (can_poll) {
+            if (__all_sync(0xffffffffu, u >= ready)) {
+                mbar_wait(&full[sready], phready);
+                arrived = true;
+            } else {
+                arrived = mbar_test_wait(&full[sready], phready);
             }
         }
         // (B) one step of this lane's probe
         if (u < ready) {
+            bool pass = false, fin = true;
             if (need) {
-                const uint8_t* st = stages + static_cast<size_t>(su) * stage_bytes;
-                const StageFilter f = reinterpret_cast<const StageRow*>(st)->f[kd];
-                fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
-                w32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + f.rel_bytes);
+                const uint32_t qrel = group_first + ((lane + u) & 31u);  // rotated key assignment
+                fm = 0xffffffffu;                                        // marks "no key": result 0, no tests
+                if (qrel < n_keys) {
+                    const uint32_t q = key_base + qrel;
+                    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+                    const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+                    h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
+                    const uint32_t kd = __ldg(&kinds[q]);
+                    const uint8_t* st = stages + static_cast<size_t>(su) * stage_bytes;
+                    const StageFilter f = reinterpret_cast<const StageRow*>(st)->f[kd];
+                    fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
+                    w32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + f.rel_bytes);
+                }
                 need = false;
                 i = 0;
             }
-            bool pass = true, fin = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
-            if (fm != 0) {
+            if (fm == 0) {
+                pass = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
+            } else if (fm != 0xffffffffu) {
                 // location(h,i) = h[i%2] + i*h[2+(((i+(i%2))%4)/2)]
                 const uint64_t a = (i & 1u) ? h1 : h0;
                 const uint64_t b = (((i + (i & 1u)) & 3u) >> 1) ? h3 : h2;
@@ -212,16 +223,23 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                 need = true;
             }
         }
+        if (arrived) {
+            ++ready;
+            if (++sready == S) { sready = 0; phready ^= 1u; }
+        }
         // (C) release every unit the whole warp has passed (never before its fill was observed)
         uint32_t mu = __reduce_min_sync(0xffffffffu, u);
         mu = min(mu, ready);
         while (base < mu) {
             uint8_t* st = stages + static_cast<size_t>(sbase) * stage_bytes;
+            // lane l held key (l + base) mod 32: rotate the ballot back into key order
             const uint32_t bits = __ballot_sync(0xffffffffu, resbits & 1u);
             resbits >>= 1;
             if (lane == 0) {
                 const uint32_t unit = reinterpret_cast<const StageRow*>(st)->unit;
-                if (warp_has_keys) matrix32[static_cast<size_t>(unit) * row_words32 + out_word] = bits;
+                const uint32_t r = base & 31u;
+                const uint32_t key_bits = r ? ((bits << r) | (bits >> (32u - r))) : bits;
+                if (warp_has_keys) matrix32[static_cast<size_t>(unit) * row_words32 + out_word] = key_bits;
                 const uint32_t old = atom_add_acq_rel_shared(&done[sbase], 1u);
                 if (old == n_warps - 1) {  // last warp out refills the stage with unit base + S
                     done[sbase] = 0;
