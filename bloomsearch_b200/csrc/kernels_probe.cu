@@ -106,15 +106,15 @@ __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64
     return true;
 }
 
-// The staged probe.  Each warp owns 32 keys; every lane walks this CTA's units at its own
-// pace (a per-lane state machine: one bit test per loop iteration) inside the window of
-// resident stages, so a lane whose probe fails on its first bit moves on to the next unit
-// instead of idling until the slowest lane of its warp finishes (TestString's early exit,
-// query_exec.go:128-159, makes per-probe work geometric: mean 2 tests, max-of-32 about 6).
-// The key a lane probes ROTATES with the unit — lane l takes key (l + unit) mod 32 of its
-// warp's group — so a key that is present in every unit (always k tests) never pins one
-// lane as a permanent straggler.  A warp releases a stage once its slowest lane has
-// passed it; the last warp to release refills it.
+// The staged probe.  All warps of the CTA work on the same resident unit; thread t owns keys
+// t, t+T, t+2T, ... (T = blockDim.x).  Within a unit each lane runs a small state machine over
+// ITS keys — one bit test per loop iteration, moving on to its next key as soon as a probe
+// fails or completes — so the warp's iteration count for the unit is the max over lanes of a
+// SUM of per-probe test counts, not (keys per lane) x (max over lanes of one probe's count).
+// TestString's early exit (query_exec.go:128-159) makes a probe's cost geometric (mean 2 tests
+// for an absent key, k for a present one): with 4 keys per lane the sum is ~8 +- 3 while the
+// per-probe maximum over 32 lanes is 6-10, i.e. ~2x fewer warp iterations per probe.
+// No producer warp: the warp whose release frees a stage refills it (fill_stage).
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
@@ -129,7 +129,8 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
     const uint32_t warp = tid >> 5;
-    const uint32_t n_warps = blockDim.x >> 5;
+    const uint32_t T = blockDim.x;
+    const uint32_t n_warps = T >> 5;
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
 
@@ -154,60 +155,52 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                    li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
 
-    const uint32_t group_first = warp * 32;              // this warp's keys: [group_first, group_first + 32)
-    const bool warp_has_keys = group_first < n_keys;
-    const uint32_t out_word = (key_base + group_first) >> 5;
+    // ---- this thread's keys: tid + j*T, j < my_keys.  Key 0 lives in registers for the whole kernel.
+    const uint32_t my_keys = tid < n_keys ? (n_keys - tid + T - 1) / T : 0;
+    const uint32_t kpt = (n_keys + T - 1) / T;  // key groups per warp (uniform)
+    const ulonglong2* hq = reinterpret_cast<const ulonglong2*>(hashes + 4ull * key_base);
+    const uint8_t* kq = kinds + key_base;
+    uint64_t k0h0 = 0, k0h1 = 0, k0h2 = 0, k0h3 = 0;
+    uint32_t k0kd = 0;
+    if (my_keys) {
+        const ulonglong2 a = __ldg(hq + 2 * tid), b = __ldg(hq + 2 * tid + 1);
+        k0h0 = a.x; k0h1 = a.y; k0h2 = b.x; k0h3 = b.y;
+        k0kd = __ldg(kq + tid);
+    }
+    uint32_t* out_base = matrix32 + ((key_base + warp * 32) >> 5);  // + unit*row_words32 + j*n_warps
 
-    // per-lane cursor
-    uint32_t u = warp_has_keys ? 0u : 0xffffffffu;  // unit (index in this CTA's sequence) the lane works on
-    uint32_t su = 0;                                // u % S
-    uint32_t i = 0;                                 // next test index
-    bool need = true;                               // key + filter parameters of item (u, key) not loaded yet
-    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    uint32_t fm = 0, fk = 0, fih = 0, fil = 0;
-    const uint32_t* w32 = nullptr;
-    uint32_t resbits = 0;                           // bit (unit - base) = this lane's result for that unit
-    // warp-uniform window
-    uint32_t base = 0, sbase = 0;                   // oldest unit not yet released by this warp
-    uint32_t ready = 0, sready = 0, phready = 0;    // units [0, ready) are known to be resident
+    uint32_t s = 0, ph = 0;
+    for (uint32_t it = 0; it < my_count; ++it) {
+        mbar_wait(&full[s], ph);
+        uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
+        const StageRow* row = reinterpret_cast<const StageRow*>(st);
+        const uint8_t* data = st + kProbeStageHeaderBytes;
 
-    while (base < my_count) {
-        // (A) poll (non-blocking) whether one more stage has arrived; the answer is consumed
-        //     after this iteration's lane step so the poll's latency overlaps it.  When no lane
-        //     can work at all, block on the barrier instead of spinning.
-        const bool can_poll = ready < my_count && ready < base + S;
-        bool arrived = false;
-        if (can_poll) {
-            if (__all_sync(0xffffffffu, u >= ready)) {
-                mbar_wait(&full[sready], phready);
-                arrived = true;
-            } else {
-                arrived = mbar_test_wait(&full[sready], phready);
-            }
+        // per-lane state machine over this lane's keys
+        uint32_t j = 0, i = 0, resbits = 0;
+        uint64_t h0 = k0h0, h1 = k0h1, h2 = k0h2, h3 = k0h3;
+        uint32_t kd = k0kd;
+        // prefetch key 1 (hashes live in L1/L2; the loads overlap key 0's tests)
+        ulonglong2 na = make_ulonglong2(0, 0), nb = make_ulonglong2(0, 0);
+        uint32_t nkd = 0;
+        if (my_keys > 1) {
+            na = __ldg(hq + 2 * (tid + T));
+            nb = __ldg(hq + 2 * (tid + T) + 1);
+            nkd = __ldg(kq + tid + T);
         }
-        // (B) one step of this lane's probe
-        if (u < ready) {
-            bool pass = false, fin = true;
+        bool need = true;
+        uint32_t fm = 0, fk = 0, fih = 0, fil = 0;
+        const uint32_t* w32 = nullptr;
+        while (j < my_keys) {
             if (need) {
-                const uint32_t qrel = group_first + ((lane + u) & 31u);  // rotated key assignment
-                fm = 0xffffffffu;                                        // marks "no key": result 0, no tests
-                if (qrel < n_keys) {
-                    const uint32_t q = key_base + qrel;
-                    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-                    const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-                    h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
-                    const uint32_t kd = __ldg(&kinds[q]);
-                    const uint8_t* st = stages + static_cast<size_t>(su) * stage_bytes;
-                    const StageFilter f = reinterpret_cast<const StageRow*>(st)->f[kd];
-                    fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
-                    w32 = reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + f.rel_bytes);
-                }
+                const StageFilter f = row->f[kd];
+                fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
+                w32 = reinterpret_cast<const uint32_t*>(data + f.rel_bytes);
                 need = false;
                 i = 0;
             }
-            if (fm == 0) {
-                pass = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
-            } else if (fm != 0xffffffffu) {
+            bool pass = true, fin = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
+            if (fm != 0) {
                 // location(h,i) = h[i%2] + i*h[2+(((i+(i%2))%4)/2)]
                 const uint64_t a = (i & 1u) ? h1 : h0;
                 const uint64_t b = (((i + (i & 1u)) & 3u) >> 1) ? h3 : h2;
@@ -217,46 +210,43 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                 fin = !pass || i == fk;
             }
             if (fin) {
-                resbits |= (pass ? 1u : 0u) << (u - base);
-                ++u;
-                if (++su == S) su = 0;
+                resbits |= (pass ? 1u : 0u) << j;
+                ++j;
                 need = true;
-            }
-        }
-        if (arrived) {
-            ++ready;
-            if (++sready == S) { sready = 0; phready ^= 1u; }
-        }
-        // (C) release every unit the whole warp has passed (never before its fill was observed)
-        uint32_t mu = __reduce_min_sync(0xffffffffu, u);
-        mu = min(mu, ready);
-        while (base < mu) {
-            uint8_t* st = stages + static_cast<size_t>(sbase) * stage_bytes;
-            // lane l held key (l + base) mod 32: rotate the ballot back into key order
-            const uint32_t bits = __ballot_sync(0xffffffffu, resbits & 1u);
-            resbits >>= 1;
-            if (lane == 0) {
-                const uint32_t unit = reinterpret_cast<const StageRow*>(st)->unit;
-                const uint32_t r = base & 31u;
-                const uint32_t key_bits = r ? ((bits << r) | (bits >> (32u - r))) : bits;
-                if (warp_has_keys) matrix32[static_cast<size_t>(unit) * row_words32 + out_word] = key_bits;
-                const uint32_t old = atom_add_acq_rel_shared(&done[sbase], 1u);
-                if (old == n_warps - 1) {  // last warp out refills the stage with unit base + S
-                    done[sbase] = 0;
-                    const uint32_t nxt = base + S;
-                    if (nxt < my_count) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
-                        const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
-                        const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
-                        fence_proxy_async();
-                        fill_stage(st, &full[sbase], stab, blockIdx.x + nxt * G, nxt + S < my_count,
-                                   blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask);
-                    }
+                // rotate in the prefetched key and prefetch the one after it
+                h0 = na.x; h1 = na.y; h2 = nb.x; h3 = nb.y; kd = nkd;
+                if (j + 1 < my_keys) {
+                    const uint32_t q = tid + (j + 1) * T;
+                    na = __ldg(hq + 2 * q);
+                    nb = __ldg(hq + 2 * q + 1);
+                    nkd = __ldg(kq + q);
                 }
             }
-            ++base;
-            if (++sbase == S) sbase = 0;
         }
+        // ---- results: one ballot word per key group ----
+        const uint32_t unit = row->unit;
+        uint32_t* out = out_base + static_cast<size_t>(unit) * row_words32;
+        for (uint32_t jj = 0; jj < kpt; ++jj) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, (resbits >> jj) & 1u);
+            if (lane == 0 && jj * T + warp * 32 < n_keys) out[jj * n_warps] = bits;
+        }
+        // ---- release: the last warp out refills this stage with unit it + S ----
+        if (lane == 0) {
+            const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
+            if (old == n_warps - 1) {
+                done[s] = 0;
+                const uint32_t nxt = it + S;
+                if (nxt < my_count) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
+                    const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
+                    const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
+                    fence_proxy_async();
+                    fill_stage(st, &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
+                               blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask);
+                }
+            }
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
     }
 }
 
@@ -272,11 +262,14 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
-    // one key per thread; at least 4 warps so a tiny batch still has some latency hiding
-    uint32_t warps = (n_keys + 31) / 32;
-    if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
-    if (warps < 4) warps = 4;
+    // warps: default 8 (4 keys per thread at 1k keys); never more warps than 32-key groups
+    uint32_t warps = plan.warps > 0 ? static_cast<uint32_t>(plan.warps) : 8u;
+    const uint32_t groups = (n_keys + 31) / 32;
+    if (warps > groups) warps = groups;
     if (warps > 32) warps = 32;
+    if (warps < 1) warps = 1;
+    // resbits holds one bit per key of a thread: at most 32 keys per thread
+    while (static_cast<uint64_t>(warps) * 32 * 32 < n_keys) ++warps;
     probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
         d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
         static_cast<uint32_t>(plan.n_stages), stage_bytes);
