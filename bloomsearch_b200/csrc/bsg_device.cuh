@@ -138,12 +138,14 @@ __device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) 
 // (proof in DESIGN.md; m == 1 works through inv = 2^64-1.)
 __device__ __forceinline__ uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih, uint32_t il) {
     const uint32_t xh = static_cast<uint32_t>(x >> 32), xl = static_cast<uint32_t>(x);
-    uint32_t t = xh - __umulhi(xh, ih) * m;
-    if (t >= m) t -= m;
-    const uint32_t q = t * ih + __umulhi(t, il) + __umulhi(xl, ih);
-    uint32_t r = xl - q * m;
-    if (r >= 2u * m) r -= 2u * m;
-    if (r >= m) r -= m;
+    const uint32_t nm = 0u - m;
+    // conditional subtraction as min(v, v - c): v - c wraps above v exactly when v < c
+    uint32_t t = __umulhi(xh, ih) * nm + xh;  // xh - floor-ish(xh/m)*m, in [0, 2m)
+    t = min(t, t - m);
+    const uint32_t q = __umulhi(xl, ih) + __umulhi(t, il) + t * ih;
+    uint32_t r = q * nm + xl;                 // y - q*m, in [0, 4m)
+    r = min(r, r - 2u * m);
+    r = min(r, r - m);
     return r;
 }
 constexpr uint64_t kSmallModLimit = 1ull << 30;

@@ -69,7 +69,7 @@ inline uint64_t reciprocal(uint64_t m) {
 constexpr int kProbeMaxStages = 16;
 constexpr int kProbeSmemPrefixBytes = 256;     // 16 mbarriers (128 B) + 16 done counters (64 B) + pad
 constexpr int kProbeStageHeaderBytes = 160;    // StageRow (128 B) + next unit's head (32 B)
-constexpr uint32_t kProbeMaxKeysPerPass = 4096;  // keys per pass over the corpus (<= 32 per thread)
+constexpr uint32_t kProbeMaxKeysPerPass = 1024;  // one key per thread, up to 32 warps per CTA
 
 // ---- launch wrappers (defined in the kernels_*.cu files) -------------------
 cudaError_t launch_hash_keys(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,

@@ -106,15 +106,39 @@ __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64
     return true;
 }
 
-// The staged probe.  All warps of the CTA work on the same resident unit; thread t owns keys
-// t, t+T, t+2T, ... (T = blockDim.x).  Within a unit each lane runs a small state machine over
-// ITS keys — one bit test per loop iteration, moving on to its next key as soon as a probe
-// fails or completes — so the warp's iteration count for the unit is the max over lanes of a
-// SUM of per-probe test counts, not (keys per lane) x (max over lanes of one probe's count).
-// TestString's early exit (query_exec.go:128-159) makes a probe's cost geometric (mean 2 tests
-// for an absent key, k for a present one): with 4 keys per lane the sum is ~8 +- 3 while the
-// per-probe maximum over 32 lanes is 6-10, i.e. ~2x fewer warp iterations per probe.
-// No producer warp: the warp whose release frees a stage refills it (fill_stage).
+// TestString with precomputed base hashes on a bitset resident in shared memory, m < 2^30.
+// Compile-time unrolled in groups of four locations (i%4 pattern of location()), early exit
+// on the first clear bit exactly like BloomFilter.Test.
+__device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
+                                                uint32_t ih, uint32_t il, uint32_t k,
+                                                const uint32_t* __restrict__ w32) {
+    auto test = [&](uint64_t loc) {
+        const uint32_t bit = mod_m32(loc, m, ih, il);
+        return (w32[bit >> 5] & (1u << (bit & 31u))) != 0u;
+    };
+    uint64_t ih2 = 0, ih3 = 0;  // i*h2, i*h3 at i = multiple of 4
+    uint32_t i = 0;
+    for (; i + 4 <= k; i += 4) {  // full groups: no per-test bound check
+        if (!test(h0 + ih2)) return false;
+        if (!test(h1 + ih3 + h3)) return false;
+        if (!test(h0 + ih3 + 2 * h3)) return false;
+        if (!test(h1 + ih2 + 3 * h2)) return false;
+        ih2 += 4 * h2;
+        ih3 += 4 * h3;
+    }
+    if (i < k && !test(h0 + ih2)) return false;
+    if (i + 1 < k && !test(h1 + ih3 + h3)) return false;
+    if (i + 2 < k && !test(h0 + ih3 + 2 * h3)) return false;
+    return true;
+}
+
+// The staged probe.  All warps of the CTA work on the same resident unit; thread t owns key
+// key_base + t for the whole kernel (hashes in registers) and tests it against every unit this
+// CTA streams through its shared-memory ring.  No producer warp: the warp whose release frees
+// a stage refills it at once (fill_stage), using the next unit's row head that travelled in
+// with the current unit.  (Measured alternatives — per-lane state machines that decouple lanes
+// across units or across several keys per lane — executed fewer iterations but 2.5x more
+// instructions per iteration and lost; see DESIGN.md.)
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
@@ -129,8 +153,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
     const uint32_t warp = tid >> 5;
-    const uint32_t T = blockDim.x;
-    const uint32_t n_warps = T >> 5;
+    const uint32_t n_warps = blockDim.x >> 5;
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
 
@@ -155,83 +178,40 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                    li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
 
-    // ---- this thread's keys: tid + j*T, j < my_keys.  Key 0 lives in registers for the whole kernel.
-    const uint32_t my_keys = tid < n_keys ? (n_keys - tid + T - 1) / T : 0;
-    const uint32_t kpt = (n_keys + T - 1) / T;  // key groups per warp (uniform)
-    const ulonglong2* hq = reinterpret_cast<const ulonglong2*>(hashes + 4ull * key_base);
-    const uint8_t* kq = kinds + key_base;
-    uint64_t k0h0 = 0, k0h1 = 0, k0h2 = 0, k0h3 = 0;
-    uint32_t k0kd = 0;
-    if (my_keys) {
-        const ulonglong2 a = __ldg(hq + 2 * tid), b = __ldg(hq + 2 * tid + 1);
-        k0h0 = a.x; k0h1 = a.y; k0h2 = b.x; k0h3 = b.y;
-        k0kd = __ldg(kq + tid);
+    // ---- this thread's key ----
+    const bool valid = tid < n_keys;
+    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    uint32_t f_off = 0;  // byte offset of this key's StageFilter inside a stage row
+    if (valid) {
+        const uint32_t q = key_base + tid;
+        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+        const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+        h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
+        f_off = 32u + 32u * __ldg(&kinds[q]);
     }
-    uint32_t* out_base = matrix32 + ((key_base + warp * 32) >> 5);  // + unit*row_words32 + j*n_warps
+    const bool warp_has_keys = warp * 32 < n_keys;
+    uint32_t* out_base = matrix32 + ((key_base + warp * 32) >> 5);
 
     uint32_t s = 0, ph = 0;
+    const uint8_t* st = stages;
     for (uint32_t it = 0; it < my_count; ++it) {
         mbar_wait(&full[s], ph);
-        uint8_t* st = stages + static_cast<size_t>(s) * stage_bytes;
-        const StageRow* row = reinterpret_cast<const StageRow*>(st);
-        const uint8_t* data = st + kProbeStageHeaderBytes;
-
-        // per-lane state machine over this lane's keys
-        uint32_t j = 0, i = 0, resbits = 0;
-        uint64_t h0 = k0h0, h1 = k0h1, h2 = k0h2, h3 = k0h3;
-        uint32_t kd = k0kd;
-        // prefetch key 1 (hashes live in L1/L2; the loads overlap key 0's tests)
-        ulonglong2 na = make_ulonglong2(0, 0), nb = make_ulonglong2(0, 0);
-        uint32_t nkd = 0;
-        if (my_keys > 1) {
-            na = __ldg(hq + 2 * (tid + T));
-            nb = __ldg(hq + 2 * (tid + T) + 1);
-            nkd = __ldg(kq + tid + T);
-        }
-        bool need = true;
-        uint32_t fm = 0, fk = 0, fih = 0, fil = 0;
-        const uint32_t* w32 = nullptr;
-        while (j < my_keys) {
-            if (need) {
-                const StageFilter f = row->f[kd];
-                fm = f.m; fk = f.k; fih = f.ih; fil = f.il;
-                w32 = reinterpret_cast<const uint32_t*>(data + f.rel_bytes);
-                need = false;
-                i = 0;
-            }
-            bool pass = true, fin = true;  // absent filter: cannot disqualify (query_exec.go:137-151)
-            if (fm != 0) {
-                // location(h,i) = h[i%2] + i*h[2+(((i+(i%2))%4)/2)]
-                const uint64_t a = (i & 1u) ? h1 : h0;
-                const uint64_t b = (((i + (i & 1u)) & 3u) >> 1) ? h3 : h2;
-                const uint32_t bit = mod_m32(a + static_cast<uint64_t>(i) * b, fm, fih, fil);
-                pass = (w32[bit >> 5] >> (bit & 31u)) & 1u;
-                ++i;
-                fin = !pass || i == fk;
-            }
-            if (fin) {
-                resbits |= (pass ? 1u : 0u) << j;
-                ++j;
-                need = true;
-                // rotate in the prefetched key and prefetch the one after it
-                h0 = na.x; h1 = na.y; h2 = nb.x; h3 = nb.y; kd = nkd;
-                if (j + 1 < my_keys) {
-                    const uint32_t q = tid + (j + 1) * T;
-                    na = __ldg(hq + 2 * q);
-                    nb = __ldg(hq + 2 * q + 1);
-                    nkd = __ldg(kq + q);
-                }
+        bool res = false;
+        if (valid) {
+            const uint4 f = *reinterpret_cast<const uint4*>(st + f_off);  // m, k, ih, il
+            if (f.x == 0) {
+                res = true;  // absent filter cannot disqualify (query_exec.go:137-151)
+            } else {
+                const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + f_off + 16);
+                res = test_hashes_s32(h0, h1, h2, h3, f.x, f.z, f.w, f.y,
+                                      reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + rel));
             }
         }
-        // ---- results: one ballot word per key group ----
-        const uint32_t unit = row->unit;
-        uint32_t* out = out_base + static_cast<size_t>(unit) * row_words32;
-        for (uint32_t jj = 0; jj < kpt; ++jj) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, (resbits >> jj) & 1u);
-            if (lane == 0 && jj * T + warp * 32 < n_keys) out[jj * n_warps] = bits;
-        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, res);
         // ---- release: the last warp out refills this stage with unit it + S ----
         if (lane == 0) {
+            const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
+            if (warp_has_keys) out_base[static_cast<size_t>(unit) * row_words32] = bits;
             const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
             if (old == n_warps - 1) {
                 done[s] = 0;
@@ -241,12 +221,13 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
                     const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
                     const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
                     fence_proxy_async();
-                    fill_stage(st, &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
+                    fill_stage(const_cast<uint8_t*>(st), &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
                                blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask);
                 }
             }
         }
-        if (++s == S) { s = 0; ph ^= 1u; }
+        st += stage_bytes;
+        if (++s == S) { s = 0; ph ^= 1u; st = stages; }
     }
 }
 
@@ -262,14 +243,11 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
-    // warps: default 8 (4 keys per thread at 1k keys); never more warps than 32-key groups
-    uint32_t warps = plan.warps > 0 ? static_cast<uint32_t>(plan.warps) : 8u;
-    const uint32_t groups = (n_keys + 31) / 32;
-    if (warps > groups) warps = groups;
+    // one key per thread; at least 4 warps so a small batch still has some latency hiding
+    uint32_t warps = (n_keys + 31) / 32;
+    if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
+    if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
-    if (warps < 1) warps = 1;
-    // resbits holds one bit per key of a thread: at most 32 keys per thread
-    while (static_cast<uint64_t>(warps) * 32 * 32 < n_keys) ++warps;
     probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
         d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
         static_cast<uint32_t>(plan.n_stages), stage_bytes);
