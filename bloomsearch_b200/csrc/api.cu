@@ -67,6 +67,8 @@ struct bsg_ctx {
     std::mutex mu;
     std::vector<cudaStream_t> stream_pool;
     void* comm = nullptr;  // bsg_comm.cpp
+    uint64_t* d_trace = nullptr;  // profiling timeline (bsg_debug_trace_*), [n_ctas][slots]
+    uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
 };
@@ -708,7 +710,8 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
                 CUDA_TRY(launch_probe_staged(plan, c->d_stab, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
-                                             q->kind_mask, q->d_matrix32, q->row_words32, s));
+                                             q->kind_mask, q->d_matrix32, q->row_words32, s, ctx->d_trace,
+                                             ctx->trace_slots));
                 ++launches;
             }
         } else if (c->n_staged) {
@@ -771,6 +774,29 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     bsg_query_free(q);
     pool_put(ctx, s);
     return rc;
+}
+
+// ---- profiling-only hooks (not part of include/bloomgpu.h): per-CTA timeline of the staged probe
+extern "C" int bsg_debug_trace_enable(bsg_ctx* ctx, uint32_t slots) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_trace);
+    ctx->d_trace = nullptr;
+    ctx->trace_slots = slots;
+    if (slots) {
+        const size_t bytes = static_cast<size_t>(ctx->sm_count) * slots * 8;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), bytes));
+        CUDA_TRY(cudaMemset(ctx->d_trace, 0, bytes));
+    }
+    return BSG_OK;
+}
+extern "C" int bsg_debug_trace_read(bsg_ctx* ctx, uint64_t* out /* sm_count * slots */) {
+    if (!ctx || !ctx->d_trace || !out) return fail(BSG_ERR_INVALID, "trace not enabled");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, ctx->d_trace, static_cast<size_t>(ctx->sm_count) * ctx->trace_slots * 8,
+                        cudaMemcpyDeviceToHost));
+    return BSG_OK;
 }
 
 // ---- hooks for bsg_comm.cpp (keeps bsg_ctx's layout private to this file) ----

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
-                    uint32_t n_stages, uint32_t stage_bytes) {
+                    uint32_t n_stages, uint32_t stage_bytes, uint64_t* __restrict__ trace, uint32_t trace_slots) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
@@ -154,6 +154,10 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t lane = tid & 31;
     const uint32_t warp = tid >> 5;
     const uint32_t n_warps = blockDim.x >> 5;
+    // optional timeline (profiling only): per CTA [0]=start, [1+2*it]=unit it seen resident by
+    // warp 0, [2+2*it]=unit it released by the last warp; globaltimer nanoseconds
+    uint64_t* tr = trace ? trace + static_cast<size_t>(blockIdx.x) * trace_slots : nullptr;
+    if (tr && tid == 0) tr[0] = globaltimer_ns();
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
 
@@ -196,6 +200,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint8_t* st = stages;
     for (uint32_t it = 0; it < my_count; ++it) {
         mbar_wait(&full[s], ph);
+        if (tr && tid == 0 && 1 + 2 * it < trace_slots) tr[1 + 2 * it] = globaltimer_ns();
         bool res = false;
         if (valid) {
             const uint4 f = *reinterpret_cast<const uint4*>(st + f_off);  // m, k, ih, il
@@ -215,6 +220,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
             const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
             if (old == n_warps - 1) {
                 done[s] = 0;
+                if (tr && 2 + 2 * it < trace_slots) tr[2 + 2 * it] = globaltimer_ns();
                 const uint32_t nxt = it + S;
                 if (nxt < my_count) {
                     const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
@@ -239,7 +245,7 @@ cudaError_t probe_staged_configure(int max_smem_optin) {
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
                                 uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
-                                uint32_t row_words32, cudaStream_t s) {
+                                uint32_t row_words32, cudaStream_t s, uint64_t* d_trace, uint32_t trace_slots) {
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
@@ -250,7 +256,7 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (warps > 32) warps = 32;
     probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
         d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-        static_cast<uint32_t>(plan.n_stages), stage_bytes);
+        static_cast<uint32_t>(plan.n_stages), stage_bytes, d_trace, trace_slots);
     return cudaGetLastError();
 }
 
