@@ -71,6 +71,7 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
+    int stagger_pct = 100; // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
 extern "C" void bsg_comm_destroy_internal(void* comm);
@@ -124,6 +125,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(build_configure(ctx->max_smem_optin));
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
+    if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     *out = ctx;
     return BSG_OK;
 }
@@ -707,6 +709,12 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             plan.smem_bytes = kProbeSmemPrefixBytes + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(c->n_staged, ctx->sm_count));
             plan.warps = ctx->probe_warps;
+            // time for the whole chip to stream one stage per SM at ~6.5 TB/s, capped at 2 us
+            {
+                const double ns = static_cast<double>(stage_bytes) * plan.grid / 6500.0;
+                plan.stagger_ns = ctx->stagger_pct < 0 ? 0u
+                                                       : static_cast<uint32_t>(std::min(2000.0, ns * ctx->stagger_pct / 100.0));
+            }
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
                 CUDA_TRY(launch_probe_staged(plan, c->d_stab, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,

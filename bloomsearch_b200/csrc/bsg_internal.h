@@ -80,7 +80,8 @@ struct ProbeStagedPlan {
     uint32_t stage_data_bytes;  // per-stage capacity for filter words
     size_t smem_bytes;
     int grid;
-    int warps;  // 0 = auto
+    int warps;            // 0 = auto
+    uint32_t stagger_ns;  // delay between the prologue's stage fills (0 = none)
 };
 cudaError_t probe_staged_configure(int max_smem_optin);
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
-                    uint32_t n_stages, uint32_t stage_bytes, uint64_t* __restrict__ trace, uint32_t trace_slots) {
+                    uint32_t n_stages, uint32_t stage_bytes, uint32_t stagger_ns, uint64_t* __restrict__ trace,
+                    uint32_t trace_slots) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
@@ -172,12 +173,18 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
 
     const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
-    // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit ----
-    if (warp == 0 && lane < S && lane < my_count) {
+    // ---- prologue: lane l of the LAST warp fills stage l with this CTA's l-th unit.  The fills
+    //      are staggered by stagger_ns each so that, chip-wide, every SM's first unit is served
+    //      before anybody's second (otherwise late-served SMs start late and finish last). ----
+    if (warp == n_warps - 1 && lane < S && lane < my_count) {
+        const uint64_t t_start = globaltimer_ns();
         const uint32_t li = blockIdx.x + lane * G;
         const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
         const uint4 a = __ldg(hp), b = __ldg(hp + 1);
         const uint64_t word_base = (static_cast<uint64_t>(a.w) << 32) | a.z;
+        const uint64_t t_go = t_start + static_cast<uint64_t>(lane) * stagger_ns;
+        while (stagger_ns && globaltimer_ns() < t_go) {
+        }
         fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
                    li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
@@ -256,7 +263,7 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (warps > 32) warps = 32;
     probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
         d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-        static_cast<uint32_t>(plan.n_stages), stage_bytes, d_trace, trace_slots);
+        static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_trace, trace_slots);
     return cudaGetLastError();
 }
 
