@@ -71,7 +71,7 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int stagger_pct = 100; // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
+    int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
 extern "C" void bsg_comm_destroy_internal(void* comm);

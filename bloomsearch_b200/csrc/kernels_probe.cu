@@ -173,10 +173,10 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
 
     const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
-    // ---- prologue: lane l of the LAST warp fills stage l with this CTA's l-th unit.  The fills
-    //      are staggered by stagger_ns each so that, chip-wide, every SM's first unit is served
-    //      before anybody's second (otherwise late-served SMs start late and finish last). ----
-    if (warp == n_warps - 1 && lane < S && lane < my_count) {
+    // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit.  stagger_ns > 0
+    //      delays fill l by l*stagger_ns (experiment knob BSG_PROBE_STAGGER; measured: staggering
+    //      does not help, the default is 0). ----
+    if (warp == 0 && lane < S && lane < my_count) {
         const uint64_t t_start = globaltimer_ns();
         const uint32_t li = blockIdx.x + lane * G;
         const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
