@@ -123,6 +123,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(probe_staged_configure(ctx->max_smem_optin));
     CUDA_TRY(build_configure(ctx->max_smem_optin));
+    CUDA_TRY(sections_configure());
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
@@ -552,6 +553,68 @@ extern "C" int bsg_corpus_load(bsg_ctx* ctx, const bsg_filter_desc* desc, uint64
     return BSG_OK;
 }
 
+extern "C" int bsg_corpus_load_sections(bsg_ctx* ctx, const uint8_t* sections, const uint64_t* sec_off,
+                                        uint64_t n_units, int verify_crc, int32_t* unit_status, uint64_t* n_bad,
+                                        bsg_corpus** out) {
+    if (!ctx || !out || (n_units && (!sec_off || !sections))) return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (n_bad) *n_bad = 0;
+    if (n_units > 0xfffffff0ull / 3) return fail(BSG_ERR_INVALID, "too many units");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (uint64_t u = 0; u < n_units; ++u)
+        if (sec_off[u + 1] < sec_off[u]) return fail(BSG_ERR_INVALID, "sec_off not monotone at %llu", (unsigned long long)u);
+    const uint64_t total = n_units ? sec_off[n_units] : 0;
+
+    bsg_corpus* c = new (std::nothrow) bsg_corpus();
+    if (!c) return fail(BSG_ERR_NOMEM, "corpus alloc");
+    c->device = ctx->device;
+    c->n_units = n_units;
+    cudaStream_t s = pool_get(ctx);
+    if (!s) { delete c; return fail(BSG_ERR_CUDA, "stream create failed"); }
+    DevBuf<uint8_t> d_sec;
+    DevBuf<uint64_t> d_off;
+    DevBuf<SectionInfo> d_info;
+    std::vector<SectionInfo> info(n_units);
+    std::vector<bsg_filter_desc> desc(n_units * 3);
+    uint64_t bad = 0;
+    auto body = [&]() -> int {
+        CUDA_TRY(d_sec.alloc(total + kKeyPad));
+        CUDA_TRY(d_off.alloc(n_units + 1));
+        CUDA_TRY(d_info.alloc(n_units));
+        CUDA_TRY(cudaMemsetAsync(d_sec.p + total, 0, kKeyPad, s));
+        if (total) CUDA_TRY(cudaMemcpyAsync(d_sec.p, sections, total, cudaMemcpyHostToDevice, s));
+        if (n_units) CUDA_TRY(cudaMemcpyAsync(d_off.p, sec_off, (n_units + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_parse_sections(d_sec.p, d_off.p, n_units, verify_crc, d_info.p, s));
+        if (n_units) CUDA_TRY(cudaMemcpyAsync(info.data(), d_info.p, n_units * sizeof(SectionInfo), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (uint64_t u = 0; u < n_units; ++u) {
+            if (info[u].status != 0) ++bad;
+            if (unit_status) unit_status[u] = info[u].status;
+            for (int k = 0; k < 3; ++k) desc[u * 3 + k] = bsg_filter_desc{info[u].m[k], info[u].k[k], 0};
+        }
+        Layout L;
+        int r = make_layout(desc.data(), n_units, L);
+        if (r) return r;
+        c->total_words = L.total_words;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_udesc), std::max<uint64_t>(n_units * 3, 1) * sizeof(DevFilter)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_words), (L.total_words + 2) * 8));
+        CUDA_TRY(cudaMemsetAsync(c->d_words, 0, (L.total_words + 2) * 8, s));
+        if (n_units)
+            CUDA_TRY(cudaMemcpyAsync(c->d_udesc, L.udesc.data(), n_units * 3 * sizeof(DevFilter), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_repack_sections(d_sec.p, d_info.p, c->d_udesc, n_units, c->d_words, s));
+        r = finish_corpus(ctx, c, L, desc.data(), s);
+        if (r) return r;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return BSG_OK;
+    };
+    int rc = body();
+    pool_put(ctx, s);
+    if (rc) { bsg_corpus_free(c); return rc; }
+    if (n_bad) *n_bad = bad;
+    *out = c;
+    return BSG_OK;
+}
+
 // ------------------------------------------------------------------- query ---
 struct bsg_query {
     int device = 0;
@@ -811,5 +874,3 @@ extern "C" int bsg_debug_trace_read(bsg_ctx* ctx, uint64_t* out /* sm_count * sl
 extern "C" int bsg_ctx_device_internal(bsg_ctx* ctx) { return ctx->device; }
 extern "C" void** bsg_ctx_comm_slot_internal(bsg_ctx* ctx) { return &ctx->comm; }
 extern "C" int bsg_set_last_error_internal(int code, const char* msg) { return fail(code, "%s", msg); }
-
-// ---- section loader: see sections.cu ----

@@ -113,6 +113,7 @@ struct SectionInfo {          // written by the parse kernel, one per unit
     uint64_t m[3], k[3];      // per present filter
     uint64_t words_byte_off[3];  // offset of the first BE word inside `sections`
 };
+cudaError_t sections_configure();
 cudaError_t launch_parse_sections(const uint8_t* d_sections, const uint64_t* d_sec_off, uint64_t n_units,
                                   int verify_crc, SectionInfo* d_info, cudaStream_t s);
 cudaError_t launch_repack_sections(const uint8_t* d_sections, const SectionInfo* d_info, const DevFilter* d_udesc,

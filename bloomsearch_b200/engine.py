@@ -243,6 +243,31 @@ class Corpus:
                                         len(words), 1 if big_endian else 0, C.byref(self._h)))
 
     @classmethod
+    def from_sections(cls, ctx: Context, sections: np.ndarray, sec_off: np.ndarray, verify_crc: bool = True):
+        """Load straight from raw on-disk filter sections (file_format.go:343-385 framing): framing
+        parse, CRC32C check and big-endian decode all run on the device.  Returns (corpus, status)
+        where status[u] is 0 or the negative reason unit u failed to parse; failed units keep no
+        filters and therefore can never be disqualified (query_exec.go:580-590 error isolation)."""
+        sections = np.ascontiguousarray(sections, dtype=np.uint8)
+        sec_off = np.ascontiguousarray(sec_off, dtype=np.uint64)
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.n_units = len(sec_off) - 1
+        self._h = C.c_void_p()
+        status = np.zeros(max(self.n_units, 1), dtype=np.int32)
+        n_bad = C.c_uint64()
+        N.check(N.lib().bsg_corpus_load_sections(ctx.handle, N.ptr(sections) if len(sections) else None, N.ptr(sec_off),
+                                                 self.n_units, 1 if verify_crc else 0, N.ptr(status), C.byref(n_bad),
+                                                 C.byref(self._h)))
+        self.n_bad = n_bad.value
+        return self, status[:self.n_units]
+
+    def unit_desc(self, unit: int) -> np.ndarray:
+        out = np.zeros(3, dtype=N.DESC_DTYPE)
+        N.check(N.lib().bsg_corpus_unit_desc(self._h, unit, N.ptr(out)))
+        return out
+
+    @classmethod
     def from_filters(cls, ctx: Context, units: Sequence[BloomFilters]) -> "Corpus":
         desc = np.zeros(len(units) * 3, dtype=N.DESC_DTYPE)
         chunks = []

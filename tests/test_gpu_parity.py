@@ -351,3 +351,90 @@ def test_example_config1_roundtrip(ctx):
     assert not corpus.evaluate_bloom_filters(bs.NewQuery().FieldToken("service", "billing").Build())[0]
     assert not corpus.evaluate_bloom_filters(bs.NewQuery().Token("nonexistent-token").Build())[0]
     corpus.close()
+
+
+# ------------------------------------------------ raw filter sections (A6/A7) ---
+def test_load_sections_matches_oracle_decode(ctx):
+    """bsg_corpus_load_sections == parseFilterSection per unit (file_format.go:392-448): framing,
+    CRC32C, BE decode on the device; probe results equal the oracle's decode+probe."""
+    rng = random.Random(31)
+    unit_keys = [(rand_keys(rng, 3 + u % 7, 2, 9), rand_keys(rng, 100 + 37 * u, 1, 14), rand_keys(rng, 90 + 11 * u, 4, 25))
+                 for u in range(23)]
+    absent = {(1, 0), (2, 1), (3, 2), (4, 0), (4, 1), (4, 2)}
+    desc, words = oracle_units(unit_keys, 0.001, absent)
+    sec, sec_off = cref.encode_sections(desc, words, len(unit_keys))
+    keys, kinds = _mixed_keys(rng, unit_keys, 40, 40)
+    blob, off = N.pack_keys(keys)
+    kinds = np.asarray(kinds, np.uint8)
+    want, errs = cref.probe_sections_matrix(sec, sec_off, blob, off, kinds)
+    assert errs == 0
+    corpus, status = bs.Corpus.from_sections(ctx, sec, sec_off)
+    assert corpus.n_bad == 0 and not status.any()
+    for u in (0, 1, 4, 22):
+        d = corpus.unit_desc(u)
+        for k in range(3):
+            assert (int(d[k]["m"]), int(d[k]["k"])) == (int(desc[u * 3 + k]["m"]), int(desc[u * 3 + k]["k"]) if desc[u * 3 + k]["m"] else 0)
+    m, _ = corpus.probe(keys, kinds)
+    corpus.close()
+    assert np.array_equal(m, want)
+    # unaligned section starts: shift everything by 3 bytes
+    sec2 = np.concatenate([np.zeros(3, np.uint8), sec])
+    off2 = sec_off.copy()
+    off2[0] = 0
+    sec2_off = np.concatenate([[np.uint64(3)], sec_off[1:] + np.uint64(3)]).astype(np.uint64)
+    sec2_off = np.concatenate([[np.uint64(0)], sec2_off])  # unit 0 = the 3 junk bytes (too small -> error, kept)
+    corpus, status = bs.Corpus.from_sections(ctx, sec2, sec2_off)
+    assert status[0] == -1 and not status[1:].any() and corpus.n_bad == 1
+    m2, _ = corpus.probe(keys, kinds)
+    corpus.close()
+    assert bs.unpack_matrix(m2, len(keys))[0].all()      # failed unit cannot be disqualified
+    assert np.array_equal(m2[1:], want)
+
+
+def test_load_sections_corruption_is_isolated_per_unit(ctx):
+    # file_format_test.go:583-802 style corruption: byte flips, truncation, bad flags, trailing bytes
+    rng = random.Random(32)
+    unit_keys = [(rand_keys(rng, 4, 2, 9), rand_keys(rng, 60, 1, 14), rand_keys(rng, 60, 4, 25)) for _ in range(8)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    secs = []
+    for u in range(8):
+        s1, _ = cref.encode_sections(desc[u * 3:u * 3 + 3], words, 1)
+        secs.append(bytearray(s1.tobytes()))
+    secs[1][len(secs[1]) // 2] ^= 0x10            # payload flip -> CRC mismatch (-2)
+    secs[2][-1] ^= 0xFF                           # CRC field flip (-2)
+    secs[3] = secs[3][:len(secs[3]) - 9]          # truncated (-2: CRC no longer matches)
+    bad_flags = bytearray(secs[4]); bad_flags[0] |= 0x80
+    import struct
+    bad_flags[-4:] = struct.pack("<I", cref.crc32c(bytes(bad_flags[:-4])))
+    secs[4] = bad_flags                           # valid CRC, unknown flag bit (-3)
+    trailing = bytearray(secs[5][:-4]) + b"\x00\x01"
+    trailing += struct.pack("<I", cref.crc32c(bytes(trailing)))
+    secs[5] = trailing                            # valid CRC, trailing bytes (-7)
+    blob_sec = np.frombuffer(b"".join(bytes(x) for x in secs), dtype=np.uint8)
+    sec_off = np.cumsum([0] + [len(x) for x in secs]).astype(np.uint64)
+    corpus, status = bs.Corpus.from_sections(ctx, blob_sec, sec_off)
+    assert list(status) == [0, -2, -2, -2, -3, -7, 0, 0]
+    assert corpus.n_bad == 5
+    # the oracle (and the reference) reject the same sections
+    for u in range(8):
+        ok = True
+        try:
+            cref.section_parse(bytes(secs[u]))
+        except ValueError:
+            ok = False
+        assert ok == (status[u] == 0)
+    keys = [unit_keys[0][1][0], unit_keys[6][2][3], b"definitely-absent"]
+    kinds = [1, 2, 1]
+    m, _ = corpus.probe(keys, kinds)
+    bits = bs.unpack_matrix(m, 3)
+    corpus.close()
+    assert bits[1:6].all()                        # failed units: fail open
+    blob, off = N.pack_keys(keys)
+    want = cref.probe_matrix(desc, words, 8, blob, off, np.asarray(kinds, np.uint8))
+    wbits = bs.unpack_matrix(want, 3)
+    for u in (0, 6, 7):
+        assert np.array_equal(bits[u], wbits[u])
+    # verify_crc=False accepts the payload-flipped section (like skipping the CRC would)
+    corpus, status = bs.Corpus.from_sections(ctx, blob_sec, sec_off, verify_crc=False)
+    assert status[1] == 0 and status[4] == -3
+    corpus.close()
