@@ -1,0 +1,91 @@
+"""-m gpu tests of the two real exchange steps of the path over NCCL, one
+process per GPU: OR-combination of equal-(m,k) partial file-level bitsets built from
+disjoint shards of a file's entries, and the all-gather of per-rank candidate masks of a
+corpus sharded by file.  Needs >= 2 GPUs (skipped otherwise; the driver's 1-GPU box skips,
+`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu` runs them)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, uid_q, res_q):
+    import bloomsearch_b200 as bs
+    from bloomsearch_b200 import _native as N
+    from bloomsearch_b200.sharding import FileSharding, sharded_candidates, split_entries
+    from oracle import cref
+    from oracle.corpus import SynthCorpus
+    try:
+        torch.cuda.set_device(rank)
+        ctx = bs.Context(rank)
+        if rank == 0:
+            uid = bs.Context.comm_unique_id()
+            for _ in range(world - 1):
+                uid_q.put(uid)
+        else:
+            uid = uid_q.get(timeout=120)
+        ctx.comm_init(rank, world, uid)
+
+        # ---- (1) file-level build: each rank inserts its shard of the union, then OR across ranks ----
+        c = SynthCorpus(42, 0, 8, 400, 8)  # one file of 8 blocks
+        union = sorted({c.key(i) for b in range(8) for i in range(int(c.group_begin[3 * b + 1]), int(c.group_begin[3 * b + 2]))})
+        assert len(union) == int(c.file_counts[0][1])
+        m, k = bs.estimate_parameters(len(union), 0.001)
+        nw = (m + 63) // 64
+        mine = union[split_entries(len(union), world, rank)]
+        blob, off = N.pack_keys(mine)
+        desc = np.array([(m, k, 0)], dtype=N.DESC_DTYPE)
+        part = ctx.build(blob, off, np.array([0, len(mine)], np.uint64), np.zeros(1, np.uint32), None, desc, nw)
+        full = ctx.or_reduce(part.copy())
+        want = cref.Filter.build_sized(union, 0.001)
+        ok_or = bool(np.array_equal(full, want.words())) and not np.array_equal(part, want.words())
+
+        # ---- (2) probe sharded by file: local mask per rank, NCCL all-gather, assemble ----
+        c2 = SynthCorpus(7, 0, 24, 300, 4)  # 6 files x 4 blocks
+        counts = c2.group_counts().reshape(-1)
+        d2 = np.zeros(len(counts), dtype=N.DESC_DTYPE)
+        wo = 0
+        for g, n in enumerate(counts):
+            mm, kk = bs.estimate_parameters(max(int(n), 1), 0.001)
+            d2[g] = (mm, kk, wo)
+            wo += (mm + 63) // 64
+        words = cref.build_filters(c2.blob, c2.key_off, c2.group_begin, np.arange(len(d2), dtype=np.uint32), None, d2, wo)
+        sh = FileSharding([c2.blocks_per_file] * c2.n_files, world)
+        units = sh.units_of(rank)
+        local = bs.Corpus(ctx, d2.reshape(-1, 3)[units].reshape(-1), words)
+        q = bs.BloomQuery(bs.Or(bs.Token(c2.key(int(c2.group_begin[3 * 5 + 1]) + 3)),
+                                bs.And(bs.Field(b"nested.az"), bs.FieldToken(b"level", b"nope")),
+                                bs.FieldToken(b"timestamp", b"%d" % (1700000000 + 300 * 17 + 5))))
+        cq = bs.compile_bloom_query(q)
+        _, lmask = local.probe(cq.keys, cq.kinds, cq.prog, want_matrix=False)
+        got = sharded_candidates(sh, rank, lmask, lambda x: ctx.allgather_masks(x, world))
+        b2, o2 = N.pack_keys(cq.keys)
+        wmask = cref.probe_mask(d2, words, c2.n_blocks, b2, o2, cq.kinds, cq.prog)
+        want_bits = bs.unpack_mask(wmask, c2.n_blocks)
+        ok_probe = bool(np.array_equal(got, want_bits)) and bool(want_bits.any()) and not bool(want_bits.all())
+        local.close()
+        ctx.close()
+        res_q.put((rank, ok_or, ok_probe, ""))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        res_q.put((rank, False, False, traceback.format_exc()))
+
+
+def test_or_reduce_and_mask_allgather_over_nccl():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctxmp = mp.get_context("spawn")
+    uid_q, res_q = ctxmp.Queue(), ctxmp.Queue()
+    procs = [ctxmp.Process(target=_worker, args=(r, world, uid_q, res_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(res_q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_or, ok_probe, err in res:
+        assert ok_or and ok_probe, f"rank {rank}: or={ok_or} probe={ok_probe}\n{err}"
