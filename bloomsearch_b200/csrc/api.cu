@@ -66,6 +66,7 @@ struct bsg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     std::vector<cudaStream_t> stream_pool;
+    std::vector<bsg_query*> scratch_pool;  // reusable per-call query objects for bsg_probe
     void* comm = nullptr;  // bsg_comm.cpp
     uint64_t* d_trace = nullptr;  // profiling timeline (bsg_debug_trace_*), [n_ctas][slots]
     uint32_t trace_slots = 0;
@@ -75,6 +76,7 @@ struct bsg_ctx {
 };
 
 extern "C" void bsg_comm_destroy_internal(void* comm);
+extern "C" void bsg_query_free(bsg_query* q);
 
 static cudaStream_t pool_get(bsg_ctx* ctx) {
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -137,6 +139,8 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
     for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
+    for (bsg_query* q : ctx->scratch_pool) bsg_query_free(q);
+    cudaFree(ctx->d_trace);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -618,6 +622,9 @@ extern "C" int bsg_corpus_load_sections(bsg_ctx* ctx, const uint8_t* sections, c
 // ------------------------------------------------------------------- query ---
 struct bsg_query {
     int device = 0;
+    // capacities (bytes) of the device buffers below: a query object can be re-prepared for
+    // another batch without reallocating (bsg_probe keeps one per pooled stream)
+    size_t cap_keys = 0, cap_key_off = 0, cap_kinds = 0, cap_hashes = 0, cap_prog = 0, cap_matrix = 0, cap_mask = 0;
     uint32_t n_keys = 0;
     uint32_t prog_len = 0;
     uint32_t kind_mask = 0;
@@ -670,12 +677,25 @@ static int validate_program(const bsg_expr_op* prog, uint32_t prog_len, uint32_t
     return BSG_OK;
 }
 
-static int query_create_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
-                           uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
-                           cudaStream_t s, bsg_query** out) {
-    if (!ctx || !corpus || !out || (n_keys && (!key_off || !key_kind)) || (prog_len && !prog))
+template <typename T>
+static cudaError_t ensure_cap(T*& p, size_t& cap, size_t need_bytes) {
+    if (need_bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(need_bytes + need_bytes / 2, 256);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+// Validates a batch and (re)fills query object q for it: uploads keys / kinds / program and
+// launches the hash kernel on stream s.  Buffers only grow.
+static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                            uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                            cudaStream_t s, bsg_query* q) {
+    if (!ctx || !corpus || !q || (n_keys && (!key_off || !key_kind)) || (prog_len && !prog))
         return fail(BSG_ERR_INVALID, "NULL argument");
-    *out = nullptr;
     const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
     if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
     uint32_t kind_mask = 0;
@@ -689,37 +709,43 @@ static int query_create_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t
         int rc = validate_program(prog, prog_len, n_keys);
         if (rc) return rc;
     }
-    bsg_query* q = new (std::nothrow) bsg_query();
-    if (!q) return fail(BSG_ERR_NOMEM, "query alloc");
     q->device = ctx->device;
     q->n_keys = n_keys;
     q->prog_len = prog_len;
     q->kind_mask = kind_mask;
     q->n_units = corpus->n_units;
     q->row_words32 = 2 * ((n_keys + 63) / 64);
-    auto body = [&]() -> int {
-        const uint64_t matrix_words32 = std::max<uint64_t>(q->n_units * q->row_words32, 1);
-        const uint64_t mask_words32 = std::max<uint64_t>(2 * ((q->n_units + 63) / 64), 1);
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_keys), nbytes + kKeyPad));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_key_off), (static_cast<uint64_t>(n_keys) + 1) * 8));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_kinds), std::max<uint32_t>(n_keys, 1)));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_hashes), std::max<uint64_t>(n_keys, 1) * 32));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_prog), std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_matrix32), matrix_words32 * 4));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_mask32), mask_words32 * 4));
-        CUDA_TRY(cudaMemsetAsync(q->d_matrix32, 0, matrix_words32 * 4, s));
-        CUDA_TRY(cudaMemsetAsync(q->d_mask32, 0, mask_words32 * 4, s));
-        CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
-        if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
-        if (n_keys) {
-            CUDA_TRY(cudaMemcpyAsync(q->d_key_off, key_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(launch_hash_keys(q->d_keys, q->d_key_off, n_keys, q->d_hashes, s));
-        }
-        if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
-        return BSG_OK;
-    };
-    int rc = body();
+    const uint64_t matrix_words32 = std::max<uint64_t>(q->n_units * q->row_words32, 1);
+    const uint64_t mask_words32 = std::max<uint64_t>(2 * ((q->n_units + 63) / 64), 1);
+    CUDA_TRY(ensure_cap(q->d_keys, q->cap_keys, nbytes + kKeyPad));
+    CUDA_TRY(ensure_cap(q->d_key_off, q->cap_key_off, (static_cast<uint64_t>(n_keys) + 1) * 8));
+    CUDA_TRY(ensure_cap(q->d_kinds, q->cap_kinds, std::max<uint32_t>(n_keys, 1)));
+    CUDA_TRY(ensure_cap(q->d_hashes, q->cap_hashes, std::max<uint64_t>(n_keys, 1) * 32));
+    CUDA_TRY(ensure_cap(q->d_prog, q->cap_prog, std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
+    CUDA_TRY(ensure_cap(q->d_matrix32, q->cap_matrix, matrix_words32 * 4));
+    CUDA_TRY(ensure_cap(q->d_mask32, q->cap_mask, mask_words32 * 4));
+    // the kernels overwrite every word that carries a key / unit; only padding words rely on this
+    CUDA_TRY(cudaMemsetAsync(q->d_matrix32, 0, matrix_words32 * 4, s));
+    CUDA_TRY(cudaMemsetAsync(q->d_mask32, 0, mask_words32 * 4, s));
+    CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
+    if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
+    if (n_keys) {
+        CUDA_TRY(cudaMemcpyAsync(q->d_key_off, key_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_hash_keys(q->d_keys, q->d_key_off, n_keys, q->d_hashes, s));
+    }
+    if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+    return BSG_OK;
+}
+
+static int query_create_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                           uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                           cudaStream_t s, bsg_query** out) {
+    if (!out) return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    bsg_query* q = new (std::nothrow) bsg_query();
+    if (!q) return fail(BSG_ERR_NOMEM, "query alloc");
+    int rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q);
     if (rc) { bsg_query_free(q); return rc; }
     *out = q;
     return BSG_OK;
@@ -838,11 +864,22 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     cudaStream_t s = pool_get(ctx);
     if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
     bsg_query* q = nullptr;
-    int rc = query_create_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, &q);
-    if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, BSG_PROBE_AUTO, out_matrix != nullptr, s);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->scratch_pool.empty()) { q = ctx->scratch_pool.back(); ctx->scratch_pool.pop_back(); }
+    }
+    if (!q) q = new (std::nothrow) bsg_query();
+    int rc = q ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q);
+    // the mask kernel is skipped when the caller wants no mask
+    const int path = BSG_PROBE_AUTO | (out_mask ? 0 : BSG_RUN_MATRIX_ONLY);
+    if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, path, out_matrix != nullptr, s);
     if (rc == BSG_OK) rc = query_fetch_on(q, corpus->n_units, out_matrix, out_mask, s);
     else cudaStreamSynchronize(s);
-    bsg_query_free(q);
+    if (q) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->scratch_pool.push_back(q);
+    }
     pool_put(ctx, s);
     return rc;
 }
