@@ -1,0 +1,213 @@
+// Package bloomgpu is the cgo binding of libbloomgpu.so (include/bloomgpu.h) that a
+// bloomsearch maintainer would vendor next to the engine to route the bloom build /
+// probe hot path to a B200.  It is SOURCE ONLY in this repository: the build image
+// has no Go toolchain, so the same C ABI is exercised from tests/ through ctypes.
+//
+// Call sites it replaces in danthegoodman1/bloomsearch @ 10735cf9 (see INTEGRATION.md):
+//
+//	ingest.go:127-145   buildFilters / buildSizedBloomFilter  -> BuildFilters
+//	query_exec.go:75-159 evaluateBloomFilters (file + block)  -> Corpus.Probe
+//	file_format.go:392-448 parseFilterSection per block/query -> LoadSections (once)
+//
+// Go pointers are never retained by C after a call returns (cgo rule); every
+// []byte / []uint64 passed below is pinned only for the duration of the call.
+package bloomgpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../bloomsearch_b200/_build -lbloomgpu
+#include <stdlib.h>
+#include "bloomgpu.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Kind selects which of a unit's three filters a key is tested against (query.go:478-484).
+type Kind uint8
+
+const (
+	KindField      Kind = C.BSG_KIND_FIELD
+	KindToken      Kind = C.BSG_KIND_TOKEN
+	KindFieldToken Kind = C.BSG_KIND_FIELDTOKEN
+)
+
+// FilterDesc mirrors bsg_filter_desc: m bits, k hashes, offset of the words (uint64 units).
+type FilterDesc struct {
+	M, K, WordOff uint64
+}
+
+// Op mirrors bsg_expr_op (postfix BloomExpression).
+type Op struct {
+	Op, Arg uint32
+}
+
+const (
+	OpLeaf  = C.BSG_OP_LEAF
+	OpAnd   = C.BSG_OP_AND
+	OpOr    = C.BSG_OP_OR
+	OpTrue  = C.BSG_OP_TRUE
+	OpFalse = C.BSG_OP_FALSE
+)
+
+func check(rc C.int) error {
+	if rc == C.BSG_OK {
+		return nil
+	}
+	return fmt.Errorf("bloomgpu: %s: %s", C.GoString(C.bsg_strerror(rc)), C.GoString(C.bsg_last_error()))
+}
+
+// Context owns one GPU (bsg_ctx).  Safe for concurrent use by many goroutines.
+type Context struct{ h *C.bsg_ctx }
+
+func NewContext(device int) (*Context, error) {
+	var h *C.bsg_ctx
+	if err := check(C.bsg_create(C.int(device), &h)); err != nil {
+		return nil, err
+	}
+	c := &Context{h}
+	runtime.SetFinalizer(c, func(c *Context) { c.Close() })
+	return c, nil
+}
+
+func (c *Context) Close() {
+	if c.h != nil {
+		C.bsg_destroy(c.h)
+		c.h = nil
+	}
+}
+
+// PackedKeys is the ABI's key layout: bytes back to back + n+1 offsets.
+type PackedKeys struct {
+	Bytes []byte
+	Off   []uint64
+}
+
+func Pack(keys []string) PackedKeys {
+	p := PackedKeys{Off: make([]uint64, 1, len(keys)+1)}
+	for _, k := range keys {
+		p.Bytes = append(p.Bytes, k...) // []byte(string): no normalisation (row_matcher.go:228-231)
+		p.Off = append(p.Off, uint64(len(p.Bytes)))
+	}
+	if len(p.Bytes) == 0 {
+		p.Bytes = []byte{0}
+	}
+	return p
+}
+
+// Build is bsg_build: groups of keys -> filters described by desc, all in one launch.
+// groupFilter2 may be nil; NoFilter marks "no secondary (file-level) filter".
+const NoFilter = uint32(C.BSG_NO_FILTER)
+
+func (c *Context) Build(keys PackedKeys, groupBegin []uint64, groupFilter, groupFilter2 []uint32,
+	desc []FilterDesc, nWords uint64) ([]uint64, error) {
+	out := make([]uint64, nWords+1)
+	var gf2 *C.uint32_t
+	if groupFilter2 != nil {
+		gf2 = (*C.uint32_t)(unsafe.Pointer(&groupFilter2[0]))
+	}
+	if len(groupFilter) == 0 || len(desc) == 0 {
+		return out[:nWords], nil
+	}
+	rc := C.bsg_build(c.h, (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0])), (*C.uint64_t)(unsafe.Pointer(&keys.Off[0])),
+		C.uint64_t(len(keys.Off)-1), (*C.uint64_t)(unsafe.Pointer(&groupBegin[0])), C.uint32_t(len(groupFilter)),
+		(*C.uint32_t)(unsafe.Pointer(&groupFilter[0])), gf2,
+		(*C.bsg_filter_desc)(unsafe.Pointer(&desc[0])), C.uint32_t(len(desc)),
+		(*C.uint64_t)(unsafe.Pointer(&out[0])), C.uint64_t(nWords))
+	runtime.KeepAlive(keys)
+	return out[:nWords], check(rc)
+}
+
+// Corpus is a set of units (data blocks, or files) whose filters are resident in HBM.
+type Corpus struct {
+	h     *C.bsg_corpus
+	Units uint64
+}
+
+// LoadSections uploads raw filter sections exactly as they sit in a file's block filter
+// region (file_format.go:343-385); framing, CRC32C and big-endian decode run on the GPU.
+// status[u] != 0 marks a section that failed to parse: that unit keeps no filters and is
+// never disqualified, which is the reference's per-block error isolation
+// (query_exec.go:580-590) — the caller still records the error for the block.
+func (c *Context) LoadSections(sections []byte, secOff []uint64, verifyCRC bool) (*Corpus, []int32, error) {
+	n := uint64(len(secOff) - 1)
+	status := make([]int32, n+1)
+	var h *C.bsg_corpus
+	var bad C.uint64_t
+	v := C.int(0)
+	if verifyCRC {
+		v = 1
+	}
+	var sp *C.uint8_t
+	if len(sections) > 0 {
+		sp = (*C.uint8_t)(unsafe.Pointer(&sections[0]))
+	}
+	rc := C.bsg_corpus_load_sections(c.h, sp, (*C.uint64_t)(unsafe.Pointer(&secOff[0])), C.uint64_t(n), v,
+		(*C.int32_t)(unsafe.Pointer(&status[0])), &bad, &h)
+	if err := check(rc); err != nil {
+		return nil, nil, err
+	}
+	cp := &Corpus{h, n}
+	runtime.SetFinalizer(cp, func(cp *Corpus) { cp.Close() })
+	return cp, status[:n], nil
+}
+
+// Load uploads already-decoded filters (desc[3*u+kind], native-endian words).
+func (c *Context) Load(desc []FilterDesc, words []uint64) (*Corpus, error) {
+	if len(desc)%3 != 0 {
+		return nil, errors.New("bloomgpu: desc must hold 3 slots per unit")
+	}
+	var h *C.bsg_corpus
+	var wp *C.uint64_t
+	if len(words) > 0 {
+		wp = (*C.uint64_t)(unsafe.Pointer(&words[0]))
+	}
+	var dp *C.bsg_filter_desc
+	if len(desc) > 0 {
+		dp = (*C.bsg_filter_desc)(unsafe.Pointer(&desc[0]))
+	}
+	rc := C.bsg_corpus_load(c.h, dp, C.uint64_t(len(desc)/3), wp, C.uint64_t(len(words)), 0, &h)
+	if err := check(rc); err != nil {
+		return nil, err
+	}
+	cp := &Corpus{h, uint64(len(desc) / 3)}
+	runtime.SetFinalizer(cp, func(cp *Corpus) { cp.Close() })
+	return cp, nil
+}
+
+func (cp *Corpus) Close() {
+	if cp.h != nil {
+		C.bsg_corpus_free(cp.h)
+		cp.h = nil
+	}
+}
+
+// Probe is bsg_probe: every key against every unit; prog (nil = no expression: every unit
+// survives, query_exec.go:81-83) folds the leaf bits into the candidate mask.
+// mask bit u = unit u survives; matrix (optional) row u, bit q = TestString(key q) on unit u.
+func (c *Context) Probe(cp *Corpus, keys PackedKeys, kinds []Kind, prog []Op, wantMatrix bool) (mask []uint64, matrix []uint64, err error) {
+	n := uint32(len(keys.Off) - 1)
+	mask = make([]uint64, (cp.Units+63)/64+1)
+	var mp *C.uint64_t
+	if wantMatrix {
+		matrix = make([]uint64, cp.Units*uint64((n+63)/64)+1)
+		mp = (*C.uint64_t)(unsafe.Pointer(&matrix[0]))
+	}
+	var pp *C.bsg_expr_op
+	if len(prog) > 0 {
+		pp = (*C.bsg_expr_op)(unsafe.Pointer(&prog[0]))
+	}
+	var kp *C.uint8_t
+	if n > 0 {
+		kp = (*C.uint8_t)(unsafe.Pointer(&kinds[0]))
+	}
+	rc := C.bsg_probe(c.h, cp.h, (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0])), (*C.uint64_t)(unsafe.Pointer(&keys.Off[0])),
+		C.uint32_t(n), kp, pp, C.uint32_t(len(prog)), mp, (*C.uint64_t)(unsafe.Pointer(&mask[0])))
+	runtime.KeepAlive(keys)
+	return mask[:(cp.Units+63)/64], matrix, check(rc)
+}

@@ -1,0 +1,149 @@
+// engine_shim.go — the glue a maintainer adds INSIDE package bloomsearch (shown here in
+// package bloomgpu's directory only so it travels with the binding; it references the
+// engine's unexported types and therefore compiles only in the engine's package).
+// SOURCE ONLY: no Go toolchain in the build image.  Every function names the reference
+// line it replaces.
+//
+//go:build ignore
+
+package bloomsearch
+
+import (
+	"github.com/bits-and-blooms/bloom/v3"
+
+	"github.com/danthegoodman1/bloomsearch/bloomgpu"
+)
+
+// gpu is set by NewBloomSearchEngine when BloomSearchEngineConfig.GPUDevice >= 0.
+var gpu *bloomgpu.Context
+
+// ---------------------------------------------------------------------------
+// BUILD — replaces bloomEntrySets.buildFilters (ingest.go:127-133) for ALL partition
+// buffers of one flush (flush.go:138-282) plus the file-level union filter
+// (flush.go:221,253) in ONE bsg_build call.  (m,k) still come from the bloom library's
+// float64 formula on the host, exactly as ingest.go:139-140 does.
+// ---------------------------------------------------------------------------
+func buildFlushFiltersGPU(blocks []*bloomEntrySets, file *bloomEntrySets, fpr float64) (blockFilters []BloomFilters, fileFilters BloomFilters, err error) {
+	var keys []string
+	groupBegin := []uint64{0}
+	var groupFilter, groupFilter2 []uint32
+	var desc []bloomgpu.FilterDesc
+	wordOff := uint64(0)
+	newFilter := func(n int) uint32 {
+		m, k := bloom.EstimateParameters(uint(max(n, 1)), fpr) // ingest.go:140
+		desc = append(desc, bloomgpu.FilterDesc{M: uint64(max(m, 1)), K: uint64(max(k, 1)), WordOff: wordOff})
+		wordOff += (uint64(max(m, 1)) + 63) / 64
+		return uint32(len(desc) - 1)
+	}
+	fileIDs := [3]uint32{newFilter(len(file.fields)), newFilter(len(file.tokens)), newFilter(len(file.fieldTokens))}
+	blockIDs := make([][3]uint32, len(blocks))
+	for b, es := range blocks {
+		for kind, set := range []map[string]struct{}{es.fields, es.tokens, es.fieldTokens} {
+			id := newFilter(len(set))
+			blockIDs[b][kind] = id
+			for entry := range set { // ingest.go:141-143: the AddString loop moves to the GPU
+				keys = append(keys, entry)
+			}
+			groupBegin = append(groupBegin, uint64(len(keys)))
+			groupFilter = append(groupFilter, id)
+			groupFilter2 = append(groupFilter2, fileIDs[kind]) // unionInto(fileEntries), flush.go:221
+		}
+	}
+	words, err := gpu.Build(bloomgpu.Pack(keys), groupBegin, groupFilter, groupFilter2, desc, wordOff)
+	if err != nil {
+		return nil, BloomFilters{}, err
+	}
+	mk := func(id uint32) *bloom.BloomFilter {
+		d := desc[id]
+		return bloom.FromWithM(words[d.WordOff:d.WordOff+(d.M+63)/64], uint(d.M), uint(d.K)) // same words, no copy
+	}
+	for b := range blocks {
+		blockFilters = append(blockFilters, BloomFilters{mk(blockIDs[b][0]), mk(blockIDs[b][1]), mk(blockIDs[b][2])})
+	}
+	fileFilters = BloomFilters{mk(fileIDs[0]), mk(fileIDs[1]), mk(fileIDs[2])}
+	return
+}
+
+// ---------------------------------------------------------------------------
+// PROBE — replaces the per-block loop of evaluateBlockFilters (query_exec.go:572-615):
+// the ≤4 MiB chunks the blockFilterCursor already reads (file_format.go:618-662) are
+// handed to the GPU as raw sections; parseFilterSection + evaluateBloomFilters for every
+// block of the file become one LoadSections + one Probe.
+// ---------------------------------------------------------------------------
+func evaluateBlockFiltersGPU(sections []byte, secOff []uint64, q *BloomQuery) (keep []bool, perBlockErr []int32, err error) {
+	corpus, status, err := gpu.LoadSections(sections, secOff, true)
+	if err != nil {
+		return nil, nil, err
+	}
+	defer corpus.Close()
+	keys, kinds, prog := compileBloomQuery(q) // postfix lowering, see bloomsearch_b200/query.py:compile_bloom_query
+	mask, _, err := gpu.Probe(corpus, bloomgpu.Pack(keys), kinds, prog, false)
+	if err != nil {
+		return nil, nil, err
+	}
+	keep = make([]bool, corpus.Units)
+	for u := range keep {
+		keep[u] = mask[u/64]>>(uint(u)%64)&1 == 1 // BloomFilterSkipped = !keep[u] (query_exec.go:599-606)
+	}
+	return keep, status, nil
+}
+
+// compileBloomQuery lowers a BloomExpression tree (query.go:505-509) to distinct leaf keys,
+// their kinds and a postfix program with the exact semantics of query_exec.go:89-159:
+// nil Condition -> TRUE, unknown types -> FALSE, OR [] -> false, AND [] -> true,
+// FieldToken keys joined by makeFieldTokenKey (tokenizer.go:508-511).
+func compileBloomQuery(q *BloomQuery) (keys []string, kinds []bloomgpu.Kind, prog []bloomgpu.Op) {
+	if q == nil || q.Expression == nil {
+		return nil, nil, nil
+	}
+	index := map[string]uint32{}
+	leaf := func(kind bloomgpu.Kind, key string) uint32 {
+		id := string(rune('0'+kind)) + key
+		if i, ok := index[id]; ok {
+			return i
+		}
+		index[id] = uint32(len(keys))
+		keys = append(keys, key)
+		kinds = append(kinds, kind)
+		return uint32(len(keys) - 1)
+	}
+	var emit func(e *BloomExpression)
+	emit = func(e *BloomExpression) {
+		switch {
+		case e == nil:
+			prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpTrue})
+		case e.ExpressionType == BloomExpressionCondition:
+			c := e.Condition
+			switch {
+			case c == nil:
+				prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpTrue})
+			case c.Type == BloomField:
+				prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpLeaf, Arg: leaf(bloomgpu.KindField, c.Field)})
+			case c.Type == BloomToken:
+				prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpLeaf, Arg: leaf(bloomgpu.KindToken, c.Token)})
+			case c.Type == BloomFieldToken:
+				prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpLeaf, Arg: leaf(bloomgpu.KindFieldToken, makeFieldTokenKey(c.Field, c.Token))})
+			default:
+				prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpFalse})
+			}
+		case e.ExpressionType == BloomExpressionAnd || e.ExpressionType == BloomExpressionOr:
+			op := uint32(bloomgpu.OpAnd)
+			if e.ExpressionType == BloomExpressionOr {
+				op = bloomgpu.OpOr
+			}
+			pending := uint32(0)
+			for i := range e.Children {
+				emit(&e.Children[i])
+				if pending++; pending == 32 { // fold wide nodes: evaluation stack stays <= 64
+					prog = append(prog, bloomgpu.Op{Op: op, Arg: 32})
+					pending = 1
+				}
+			}
+			prog = append(prog, bloomgpu.Op{Op: op, Arg: pending})
+		default:
+			prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpFalse})
+		}
+	}
+	emit(q.Expression)
+	return
+}
