@@ -68,6 +68,7 @@ struct bsg_ctx {
     std::vector<cudaStream_t> stream_pool;
     std::vector<bsg_query*> scratch_pool;  // reusable per-call query objects for bsg_probe
     void* comm = nullptr;  // bsg_comm.cpp
+    float last_build_kernel_ms = 0.f;  // profiling: device time of the last bsg_build's kernel
     uint64_t* d_trace = nullptr;  // profiling timeline (bsg_debug_trace_*), [n_ctas][slots]
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
@@ -348,9 +349,18 @@ extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_
         if (e == cudaSuccess && n_filters)
             e = cudaMemcpyAsync(d_bf.p, bf.data(), n_filters * sizeof(BuildFilter), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_out.p, 0, std::max<uint64_t>(n_words, 1) * 8, s);
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+        if (e == cudaSuccess) e = cudaEventRecord(ev0, s);
         if (e == cudaSuccess)
             e = launch_build(d_keys.p, d_off.p, d_gb.p, n_sub, d_gf.p, group_filter2 ? d_gf2.p : nullptr, d_bf.p,
                              d_out.p, smem_cap, s);
+        if (e == cudaSuccess) e = cudaEventRecord(ev1, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+        if (e == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_kernel_ms, ev0, ev1);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (e == cudaSuccess && n_words) e = cudaMemcpyAsync(out_words, d_out.p, n_words * 8, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_build: %s", cudaGetErrorString(e));
@@ -906,6 +916,8 @@ extern "C" int bsg_debug_trace_read(bsg_ctx* ctx, uint64_t* out /* sm_count * sl
                         cudaMemcpyDeviceToHost));
     return BSG_OK;
 }
+
+extern "C" float bsg_debug_last_build_kernel_ms(bsg_ctx* ctx) { return ctx ? ctx->last_build_kernel_ms : 0.f; }
 
 // ---- hooks for bsg_comm.cpp (keeps bsg_ctx's layout private to this file) ----
 extern "C" int bsg_ctx_device_internal(bsg_ctx* ctx) { return ctx->device; }
