@@ -139,7 +139,7 @@ __device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64
 // with the current unit.  (Measured alternatives — per-lane state machines that decouple lanes
 // across units or across several keys per lane — executed fewer iterations but 2.5x more
 // instructions per iteration and lost; see DESIGN.md.)
-template <int MAXT>
+template <int MAXT, bool TRACE>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
@@ -157,8 +157,8 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint32_t n_warps = blockDim.x >> 5;
     // optional timeline (profiling only): per CTA [0]=start, [1+2*it]=unit it seen resident by
     // warp 0, [2+2*it]=unit it released by the last warp; globaltimer nanoseconds
-    uint64_t* tr = trace ? trace + static_cast<size_t>(blockIdx.x) * trace_slots : nullptr;
-    if (tr && tid == 0) tr[0] = globaltimer_ns();
+    uint64_t* tr = (TRACE && trace) ? trace + static_cast<size_t>(blockIdx.x) * trace_slots : nullptr;
+    if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
 
@@ -207,7 +207,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     const uint8_t* st = stages;
     for (uint32_t it = 0; it < my_count; ++it) {
         mbar_wait(&full[s], ph);
-        if (tr && tid == 0 && 1 + 2 * it < trace_slots) tr[1 + 2 * it] = globaltimer_ns();
+        if (TRACE && tr && tid == 0 && 1 + 2 * it < trace_slots) tr[1 + 2 * it] = globaltimer_ns();
         bool res = false;
         if (valid) {
             const uint4 f = *reinterpret_cast<const uint4*>(st + f_off);  // m, k, ih, il
@@ -227,7 +227,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
             const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
             if (old == n_warps - 1) {
                 done[s] = 0;
-                if (tr && 2 + 2 * it < trace_slots) tr[2 + 2 * it] = globaltimer_ns();
+                if (TRACE && tr && 2 + 2 * it < trace_slots) tr[2 + 2 * it] = globaltimer_ns();
                 const uint32_t nxt = it + S;
                 if (nxt < my_count) {
                     const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
@@ -245,7 +245,10 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
 }
 
 cudaError_t probe_staged_configure(int max_smem_optin) {
-    return cudaFuncSetAttribute(probe_staged_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(probe_staged_kernel<1024, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(probe_staged_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 max_smem_optin);
 }
 
@@ -261,9 +264,14 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
-    probe_staged_kernel<1024><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
-        d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-        static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_trace, trace_slots);
+    if (d_trace)
+        probe_staged_kernel<1024, true><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
+            d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_trace, trace_slots);
+    else
+        probe_staged_kernel<1024, false><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
+            d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, nullptr, 0);
     return cudaGetLastError();
 }
 
