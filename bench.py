@@ -282,24 +282,34 @@ def main():
         #      A step = the batch's (block x key) membership matrix: one probe_staged launch
         #      (no expression tree -> no mask kernel; the all-ones mask is not materialised). ----
         RUN = N.PROBE_AUTO | N.RUN_MATRIX_ONLY
-        for i in range(args.warmup):
-            queries[i % n_rep].run(RUN)
+        import ctypes as C
+        L = N.lib()
+        L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        cp_arr = (C.c_void_p * n_rep)(*[cp.handle for cp in corpora])
+        q_arr = (C.c_void_p * n_rep)(*[q._h for q in queries])
+
+        def run_steps(k):
+            # the K launches are issued from C (ctypes drops the GIL): no interpreter jitter
+            N.check(L.bsg_debug_run_cycle(ctx.handle, cp_arr, q_arr, n_rep, k, RUN))
+
+        run_steps(args.warmup)
         barrier()
         with ClockSampler(local_rank) as clk:
+            # load the GPU for >= 0.5 s first so the sampler sees clocks under load, then the
+            # timed K steps inside the same sampled, loaded period, then >= 1 s more load
+            t_end = time.time() + 0.5
+            while time.time() < t_end:
+                run_steps(256)
+                ctx.synchronize()
+            barrier()
             ctx.timer_begin()
-            for i in range(args.steps):
-                queries[i % n_rep].run(RUN)
+            run_steps(args.steps)
             ms = ctx.timer_end()
             barrier()
-            # keep the sampler alive for at least ~1.5 s of load so it sees clocks under load
-            t_end = time.time() + max(0.0, 1.5 - ms / 1e3)
-            i = 0
+            t_end = time.time() + 1.0
             while time.time() < t_end:
-                queries[i % n_rep].run(RUN)
-                i += 1
-                if i % 64 == 0:
-                    ctx.synchronize()
-            ctx.synchronize()
+                run_steps(256)
+                ctx.synchronize()
         launches_per_step = queries[0].launches()
         k_ms = ms / args.steps  # this rank's probe-kernel time per launch (events on the launching stream)
         ms = max_over_ranks(ms)

@@ -917,6 +917,19 @@ extern "C" int bsg_debug_trace_read(bsg_ctx* ctx, uint64_t* out /* sm_count * sl
     return BSG_OK;
 }
 
+// Measurement helper: enqueue `steps` runs back to back from C (no interpreter between
+// launches), cycling over n (corpus, query) pairs so consecutive steps touch different HBM.
+extern "C" int bsg_debug_run_cycle(bsg_ctx* ctx, bsg_corpus* const* corpora, bsg_query* const* queries, uint32_t n,
+                                   uint32_t steps, int path) {
+    if (!ctx || !corpora || !queries || n == 0) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < steps; ++i) {
+        int rc = query_run_on(ctx, corpora[i % n], queries[i % n], path, 1, ctx->cur_stream);
+        if (rc) return rc;
+    }
+    return BSG_OK;
+}
+
 extern "C" float bsg_debug_last_build_kernel_ms(bsg_ctx* ctx) { return ctx ? ctx->last_build_kernel_ms : 0.f; }
 
 // ---- hooks for bsg_comm.cpp (keeps bsg_ctx's layout private to this file) ----
