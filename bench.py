@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--workload", default="2b", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=8, help="distinct HBM copies cycled so every step misses L2")
+    ap.add_argument("--streams", type=int, default=2, help="streams the timed batches are issued on (round-robin)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary layout")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -284,13 +285,15 @@ def main():
         RUN = N.PROBE_AUTO | N.RUN_MATRIX_ONLY
         import ctypes as C
         L = N.lib()
-        L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
         cp_arr = (C.c_void_p * n_rep)(*[cp.handle for cp in corpora])
         q_arr = (C.c_void_p * n_rep)(*[q._h for q in queries])
 
-        def run_steps(k):
-            # the K launches are issued from C (ctypes drops the GIL): no interpreter jitter
-            N.check(L.bsg_debug_run_cycle(ctx.handle, cp_arr, q_arr, n_rep, k, RUN))
+        def run_steps(k, streams=None):
+            # the K launches are issued from C (ctypes drops the GIL): no interpreter jitter.
+            # Consecutive batches go round-robin on args.streams streams (independent batches overlap
+            # tail-to-head, as concurrent bsg_probe() callers on their pool streams do).
+            N.check(L.bsg_debug_run_cycle(ctx.handle, cp_arr, q_arr, n_rep, k, RUN, streams or args.streams))
 
         run_steps(args.warmup)
         barrier()
@@ -305,6 +308,10 @@ def main():
             ctx.timer_begin()
             run_steps(args.steps)
             ms = ctx.timer_end()
+            barrier()
+            ctx.timer_begin()          # same K steps serialised on ONE stream, for reference
+            run_steps(args.steps, 1)
+            ms_single = ctx.timer_end() / args.steps
             barrier()
             t_end = time.time() + 1.0
             while time.time() < t_end:
@@ -328,6 +335,8 @@ def main():
         achieved = algo_bytes / (k_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": TRAFFIC_NCU.get(wl), "kernel": "probe_staged_kernel", "kernel_ms": k_ms,
+                    "kernel_ms_single_stream": ms_single, "frac_single_stream": algo_bytes / (ms_single / 1e3) / 1e9 / peak,
+                    "launch_streams": args.streams,
                     "algorithmic_bytes_per_launch": algo_bytes,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
 

@@ -68,6 +68,9 @@ struct bsg_ctx {
     std::vector<cudaStream_t> stream_pool;
     std::vector<bsg_query*> scratch_pool;  // reusable per-call query objects for bsg_probe
     void* comm = nullptr;  // bsg_comm.cpp
+    std::vector<cudaStream_t> aux_streams;  // bsg_debug_run_cycle
+    std::vector<cudaEvent_t> aux_events;
+    cudaEvent_t fork_event = nullptr;
     float last_build_kernel_ms = 0.f;  // profiling: device time of the last bsg_build's kernel
     uint64_t* d_trace = nullptr;  // profiling timeline (bsg_debug_trace_*), [n_ctas][slots]
     uint32_t trace_slots = 0;
@@ -141,6 +144,9 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
     for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
     for (bsg_query* q : ctx->scratch_pool) bsg_query_free(q);
+    for (cudaStream_t s : ctx->aux_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : ctx->aux_events) cudaEventDestroy(e);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     cudaFree(ctx->d_trace);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -917,15 +923,44 @@ extern "C" int bsg_debug_trace_read(bsg_ctx* ctx, uint64_t* out /* sm_count * sl
     return BSG_OK;
 }
 
-// Measurement helper: enqueue `steps` runs back to back from C (no interpreter between
-// launches), cycling over n (corpus, query) pairs so consecutive steps touch different HBM.
+// Measurement helper: enqueue `steps` runs from C (no interpreter between launches), cycling
+// over n (corpus, query) pairs so consecutive steps touch different HBM.  n_streams > 1 issues
+// consecutive steps round-robin on that many internal streams, forked from / joined to the ctx
+// stream with events, so independent batches overlap tail-to-head exactly as concurrent
+// bsg_probe() callers (one pool stream each) do.
 extern "C" int bsg_debug_run_cycle(bsg_ctx* ctx, bsg_corpus* const* corpora, bsg_query* const* queries, uint32_t n,
-                                   uint32_t steps, int path) {
+                                   uint32_t steps, int path, uint32_t n_streams) {
     if (!ctx || !corpora || !queries || n == 0) return fail(BSG_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n_streams <= 1) {
+        for (uint32_t i = 0; i < steps; ++i) {
+            int rc = query_run_on(ctx, corpora[i % n], queries[i % n], path, 1, ctx->cur_stream);
+            if (rc) return rc;
+        }
+        return BSG_OK;
+    }
+    if (n_streams > 8) n_streams = 8;
+    if (n_streams > n) n_streams = n;  // a query object must never be in flight twice
+    while (ctx->aux_streams.size() < n_streams) {
+        cudaStream_t st = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(st);
+        cudaEvent_t ev = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->aux_events.push_back(ev);
+    }
+    if (!ctx->fork_event) CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ctx->fork_event, ctx->cur_stream));
+    for (uint32_t k = 0; k < n_streams; ++k) CUDA_TRY(cudaStreamWaitEvent(ctx->aux_streams[k], ctx->fork_event, 0));
     for (uint32_t i = 0; i < steps; ++i) {
-        int rc = query_run_on(ctx, corpora[i % n], queries[i % n], path, 1, ctx->cur_stream);
+        // step i uses pair i % n on stream i % n_streams; with n a multiple of n_streams a pair is
+        // always replayed on the same stream, so its own runs stay ordered
+        int rc = query_run_on(ctx, corpora[i % n], queries[i % n], path, 1, ctx->aux_streams[i % n_streams]);
         if (rc) return rc;
+    }
+    for (uint32_t k = 0; k < n_streams; ++k) {
+        CUDA_TRY(cudaEventRecord(ctx->aux_events[k], ctx->aux_streams[k]));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->cur_stream, ctx->aux_events[k], 0));
     }
     return BSG_OK;
 }
