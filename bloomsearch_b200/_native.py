@@ -38,8 +38,13 @@ class BloomGpuError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libbloomgpu.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "bloomgpu.h")]
-    stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    host = os.path.join(_HERE, "host")
+    srcs = ([os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(host, f) for f in os.listdir(host)] +
+            [os.path.join(_HERE, "..", "include", "bloomgpu.h")])
+    newest_out = min((os.path.getmtime(p) if os.path.exists(p) else 0.0) for p in
+                     (SO_PATH, os.path.join(_HERE, "_build", "libbloomsearch_host.so"),
+                      os.path.join(_HERE, "_build", "host_selftest")))
+    stale = newest_out == 0.0 or any(os.path.getmtime(s) > newest_out for s in srcs)
     if force or stale:
         cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
         res = subprocess.run(cmd, capture_output=True, text=True)
