@@ -641,6 +641,13 @@ struct bsg_query {
     // capacities (bytes) of the device buffers below: a query object can be re-prepared for
     // another batch without reallocating (bsg_probe keeps one per pooled stream)
     size_t cap_keys = 0, cap_key_off = 0, cap_kinds = 0, cap_hashes = 0, cap_prog = 0, cap_matrix = 0, cap_mask = 0;
+    // pinned host staging (bsg_probe path): small inputs go up in async copies from here and the
+    // results come down into it, then are memcpy'd to the caller's (pageable) buffers
+    uint8_t* h_pin = nullptr;
+    size_t cap_pin = 0;
+    // output shape the pad words were last zeroed for (kernels never write pad words)
+    uint64_t zeroed_units = ~0ull;
+    uint32_t zeroed_row_words32 = ~0u, zeroed_groups = ~0u;
     uint32_t n_keys = 0;
     uint32_t prog_len = 0;
     uint32_t kind_mask = 0;
@@ -666,6 +673,7 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_prog);
     cudaFree(q->d_matrix32);
     cudaFree(q->d_mask32);
+    if (q->h_pin) cudaFreeHost(q->h_pin);
     delete q;
 }
 
@@ -709,7 +717,7 @@ static cudaError_t ensure_cap(T*& p, size_t& cap, size_t need_bytes) {
 // launches the hash kernel on stream s.  Buffers only grow.
 static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
                             uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
-                            cudaStream_t s, bsg_query* q) {
+                            cudaStream_t s, bsg_query* q, bool use_pinned = false) {
     if (!ctx || !corpus || !q || (n_keys && (!key_off || !key_kind)) || (prog_len && !prog))
         return fail(BSG_ERR_INVALID, "NULL argument");
     const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
@@ -733,6 +741,7 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
     q->row_words32 = 2 * ((n_keys + 63) / 64);
     const uint64_t matrix_words32 = std::max<uint64_t>(q->n_units * q->row_words32, 1);
     const uint64_t mask_words32 = std::max<uint64_t>(2 * ((q->n_units + 63) / 64), 1);
+    const size_t cap_matrix_before = q->cap_matrix, cap_mask_before = q->cap_mask;
     CUDA_TRY(ensure_cap(q->d_keys, q->cap_keys, nbytes + kKeyPad));
     CUDA_TRY(ensure_cap(q->d_key_off, q->cap_key_off, (static_cast<uint64_t>(n_keys) + 1) * 8));
     CUDA_TRY(ensure_cap(q->d_kinds, q->cap_kinds, std::max<uint32_t>(n_keys, 1)));
@@ -740,17 +749,58 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
     CUDA_TRY(ensure_cap(q->d_prog, q->cap_prog, std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
     CUDA_TRY(ensure_cap(q->d_matrix32, q->cap_matrix, matrix_words32 * 4));
     CUDA_TRY(ensure_cap(q->d_mask32, q->cap_mask, mask_words32 * 4));
-    // the kernels overwrite every word that carries a key / unit; only padding words rely on this
-    CUDA_TRY(cudaMemsetAsync(q->d_matrix32, 0, matrix_words32 * 4, s));
-    CUDA_TRY(cudaMemsetAsync(q->d_mask32, 0, mask_words32 * 4, s));
-    CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
-    if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
+    // The kernels overwrite every word that carries a key / unit; pad words are never written, so
+    // they only need zeroing when the buffers were reallocated or the output shape changed.
+    const uint32_t groups = (n_keys + 31) / 32;  // 32-key words a row really carries (the rest is pad)
+    const bool reshaped = q->zeroed_units != q->n_units || q->zeroed_row_words32 != q->row_words32 ||
+                          q->zeroed_groups != groups || q->cap_matrix != cap_matrix_before ||
+                          q->cap_mask != cap_mask_before;
+    if (reshaped) {
+        CUDA_TRY(cudaMemsetAsync(q->d_matrix32, 0, matrix_words32 * 4, s));
+        CUDA_TRY(cudaMemsetAsync(q->d_mask32, 0, mask_words32 * 4, s));
+        q->zeroed_units = q->n_units;
+        q->zeroed_row_words32 = q->row_words32;
+        q->zeroed_groups = groups;
+    }
+    const uint8_t* src_keys = keys;
+    const uint64_t* src_off = key_off;
+    const uint8_t* src_kinds = key_kind;
+    const bsg_expr_op* src_prog = prog;
+    if (use_pinned) {
+        // one pinned block: [keys + pad][offsets][kinds][program]
+        const size_t o_off = (nbytes + kKeyPad + 15) & ~size_t(15);
+        const size_t o_kind = o_off + (static_cast<size_t>(n_keys) + 1) * 8;
+        const size_t o_prog = (o_kind + n_keys + 15) & ~size_t(15);
+        const size_t need = o_prog + static_cast<size_t>(prog_len) * sizeof(bsg_expr_op) + 16;
+        if (need > q->cap_pin) {
+            if (q->h_pin) cudaFreeHost(q->h_pin);
+            q->h_pin = nullptr;
+            q->cap_pin = 0;
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&q->h_pin), need * 2, cudaHostAllocDefault));
+            q->cap_pin = need * 2;
+        }
+        if (nbytes) memcpy(q->h_pin, keys, nbytes);
+        memset(q->h_pin + nbytes, 0, kKeyPad);
+        if (n_keys) {
+            memcpy(q->h_pin + o_off, key_off, (static_cast<size_t>(n_keys) + 1) * 8);
+            memcpy(q->h_pin + o_kind, key_kind, n_keys);
+        }
+        if (prog_len) memcpy(q->h_pin + o_prog, prog, prog_len * sizeof(bsg_expr_op));
+        src_keys = q->h_pin;
+        src_off = reinterpret_cast<const uint64_t*>(q->h_pin + o_off);
+        src_kinds = q->h_pin + o_kind;
+        src_prog = reinterpret_cast<const bsg_expr_op*>(q->h_pin + o_prog);
+        CUDA_TRY(cudaMemcpyAsync(q->d_keys, src_keys, nbytes + kKeyPad, cudaMemcpyHostToDevice, s));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
+        if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, src_keys, nbytes, cudaMemcpyHostToDevice, s));
+    }
     if (n_keys) {
-        CUDA_TRY(cudaMemcpyAsync(q->d_key_off, key_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(q->d_key_off, src_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(q->d_kinds, src_kinds, n_keys, cudaMemcpyHostToDevice, s));
         CUDA_TRY(launch_hash_keys(q->d_keys, q->d_key_off, n_keys, q->d_hashes, s));
     }
-    if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+    if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, src_prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
     return BSG_OK;
 }
 
@@ -856,6 +906,30 @@ extern "C" int bsg_query_run(bsg_ctx* ctx, const bsg_corpus* corpus, bsg_query* 
     return query_run_on(ctx, corpus, q, path, want_matrix, ctx->cur_stream);
 }
 
+// D2H through the query's pinned block (true async DMA), then memcpy into the caller's buffers.
+static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s) {
+    const size_t mbytes = (out_matrix && q->n_keys) ? n_units * q->row_words32 * 4 : 0;
+    const size_t kbytes = out_mask ? ((n_units + 63) / 64) * 8 : 0;
+    const size_t need = mbytes + kbytes + 16;
+    if (need > q->cap_pin) {  // grow, keeping nothing (inputs were already consumed by the copies on s)
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (q->h_pin) cudaFreeHost(q->h_pin);
+        q->h_pin = nullptr;
+        q->cap_pin = 0;
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&q->h_pin), need * 2, cudaHostAllocDefault));
+        q->cap_pin = need * 2;
+    } else {
+        // the input staging area is reused for the outputs: the H2D copies must have been consumed
+        // -> they precede the kernels on s, and the D2H copies below follow the kernels on s.
+    }
+    if (mbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin, q->d_matrix32, mbytes, cudaMemcpyDeviceToHost, s));
+    if (kbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin + mbytes, q->d_mask32, kbytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (mbytes) memcpy(out_matrix, q->h_pin, mbytes);
+    if (kbytes) memcpy(out_mask, q->h_pin + mbytes, kbytes);
+    return BSG_OK;
+}
+
 static int query_fetch_on(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s) {
     if (n_units != q->n_units) return fail(BSG_ERR_INVALID, "n_units mismatch");
     if (out_matrix && q->n_keys && n_units)
@@ -886,11 +960,11 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     }
     if (!q) q = new (std::nothrow) bsg_query();
     int rc = q ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
-    if (rc == BSG_OK) rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q);
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q, true);
     // the mask kernel is skipped when the caller wants no mask
     const int path = BSG_PROBE_AUTO | (out_mask ? 0 : BSG_RUN_MATRIX_ONLY);
     if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, path, out_matrix != nullptr, s);
-    if (rc == BSG_OK) rc = query_fetch_on(q, corpus->n_units, out_matrix, out_mask, s);
+    if (rc == BSG_OK) rc = query_fetch_pinned(q, corpus->n_units, out_matrix, out_mask, s);
     else cudaStreamSynchronize(s);
     if (q) {
         std::lock_guard<std::mutex> lk(ctx->mu);

@@ -438,3 +438,23 @@ def test_load_sections_corruption_is_isolated_per_unit(ctx):
     corpus, status = bs.Corpus.from_sections(ctx, blob_sec, sec_off, verify_crc=False)
     assert status[1] == 0 and status[4] == -3
     corpus.close()
+
+
+def test_bsg_probe_scratch_reuse_across_shapes(ctx):
+    """bsg_probe keeps its device scratch between calls; pad words must never leak bits from a
+    previous, differently shaped batch (1000 -> 970 -> 20 -> 1000 keys; with / without program)."""
+    rng = random.Random(55)
+    unit_keys = [(rand_keys(rng, 5, 3, 8), rand_keys(rng, 120, 1, 10), rand_keys(rng, 130, 4, 20)) for _ in range(41)]
+    desc, words = oracle_units(unit_keys, 0.01)
+    corpus = bs.Corpus(ctx, desc, words)
+    all_keys, all_kinds = _mixed_keys(rng, unit_keys, 700, 400)
+    for n in (1000, 970, 20, 1000, 33, 961):
+        keys, kinds = all_keys[:n], np.asarray(all_kinds[:n], np.uint8)
+        blob, off = N.pack_keys(keys)
+        want = cref.probe_matrix(desc, words, len(unit_keys), blob, off, kinds)
+        prog = np.array([(N.OP_LEAF, 0), (N.OP_LEAF, n - 1), (N.OP_OR, 2)], dtype=N.OP_DTYPE) if n % 2 else None
+        want_mask = cref.probe_mask(desc, words, len(unit_keys), blob, off, kinds, prog)
+        m, mask = corpus.probe(keys, kinds, prog)
+        assert np.array_equal(m, want), n
+        assert np.array_equal(mask, want_mask), n
+    corpus.close()
