@@ -313,6 +313,14 @@ class Corpus:
                                   N.ptr(matrix), N.ptr(mask)))
         return matrix, mask
 
+    def probe_packed(self, blob: np.ndarray, off: np.ndarray, kinds: np.ndarray, prog: Optional[np.ndarray],
+                     out_matrix: Optional[np.ndarray], out_mask: Optional[np.ndarray]) -> None:
+        """bsg_probe on caller-packed host buffers, results into caller-allocated host arrays
+        (exactly the C-ABI call, no Python-side packing)."""
+        pp, pl = (None, 0) if prog is None else (N.ptr(prog), len(prog))
+        N.check(N.lib().bsg_probe(self.ctx.handle, self._h, N.ptr(blob), N.ptr(off), len(off) - 1, N.ptr(kinds), pp, pl,
+                                  N.ptr(out_matrix), N.ptr(out_mask)))
+
     def evaluate_bloom_filters(self, query: Optional[BloomQuery]) -> np.ndarray:
         """evaluateBloomFilters (query_exec.go:75-87) for every unit at once -> bool[n_units]."""
         cq = compile_bloom_query(query)
