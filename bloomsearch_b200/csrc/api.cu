@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bsg_internal.h"
@@ -68,6 +69,12 @@ struct bsg_ctx {
     std::vector<cudaStream_t> stream_pool;
     std::vector<bsg_query*> scratch_pool;  // reusable per-call query objects for bsg_probe
     void* comm = nullptr;  // bsg_comm.cpp
+    // large host<->device transfers of pageable caller memory (bsg_build): worker threads copy
+    // slices through pinned double buffers on their own streams (see staged_copy)
+    std::mutex stage_mu;
+    std::vector<uint8_t*> stage_pin;       // kStageWorkers * 2 buffers of kStageChunk bytes
+    std::vector<cudaStream_t> stage_streams;
+    std::vector<cudaEvent_t> stage_events;
     std::vector<cudaStream_t> aux_streams;  // bsg_debug_run_cycle
     std::vector<cudaEvent_t> aux_events;
     cudaEvent_t fork_event = nullptr;
@@ -144,6 +151,9 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
     for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
     for (bsg_query* q : ctx->scratch_pool) bsg_query_free(q);
+    for (uint8_t* p : ctx->stage_pin) cudaFreeHost(p);
+    for (cudaStream_t s : ctx->stage_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
     for (cudaStream_t s : ctx->aux_streams) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->aux_events) cudaEventDestroy(e);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
@@ -242,6 +252,101 @@ int validate_filter(const bsg_filter_desc& d, uint64_t n_words, const char* what
 
 }  // namespace
 
+// ------------------------------------------------------------ staged copies ---
+// cudaMemcpy from/to pageable memory runs at ~5 GB/s; the caller's buffers (Go heap) cannot be
+// pinned in place.  staged_copy moves a large array with kStageWorkers host threads, each copying
+// its chunks through two pinned buffers (memcpy overlapped with the previous chunk's DMA) on its
+// own stream.  Blocks until the whole transfer is complete.
+namespace {
+constexpr int kStageWorkers = 4;
+constexpr size_t kStageChunk = 8u << 20;
+constexpr size_t kStageThreshold = 4u << 20;  // below this a plain cudaMemcpyAsync is used
+
+cudaError_t stage_init(bsg_ctx* ctx) {
+    if (!ctx->stage_pin.empty()) return cudaSuccess;
+    for (int i = 0; i < kStageWorkers * 2; ++i) {
+        uint8_t* p = nullptr;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), kStageChunk, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        ctx->stage_pin.push_back(p);
+        cudaEvent_t ev = nullptr;
+        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        ctx->stage_events.push_back(ev);
+    }
+    for (int i = 0; i < kStageWorkers; ++i) {
+        cudaStream_t st = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        ctx->stage_streams.push_back(st);
+    }
+    return cudaSuccess;
+}
+
+// to_device: dev <- host ; else host <- dev.  Caller holds ctx->stage_mu.
+cudaError_t staged_copy(bsg_ctx* ctx, void* dev, void* host, size_t bytes, bool to_device) {
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = stage_init(ctx);
+    if (e != cudaSuccess) return e;
+    const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    std::vector<cudaError_t> errs(kStageWorkers, cudaSuccess);
+    auto worker = [&](int w) {
+        cudaSetDevice(ctx->device);
+        cudaStream_t st = ctx->stage_streams[w];
+        int j = 0;
+        size_t pending_off[2] = {0, 0}, pending_len[2] = {0, 0};
+        bool pending[2] = {false, false};
+        for (size_t c = w; c < n_chunks; c += kStageWorkers, ++j) {
+            const int b = j & 1;
+            uint8_t* pin = ctx->stage_pin[w * 2 + b];
+            cudaEvent_t ev = ctx->stage_events[w * 2 + b];
+            const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+            if (pending[b]) {  // this buffer's previous DMA must be done before it is reused
+                cudaError_t r = cudaEventSynchronize(ev);
+                if (r != cudaSuccess) { errs[w] = r; return; }
+                if (!to_device) memcpy(static_cast<uint8_t*>(host) + pending_off[b], pin, pending_len[b]);
+                pending[b] = false;
+            }
+            cudaError_t r;
+            if (to_device) {
+                memcpy(pin, static_cast<const uint8_t*>(host) + off, len);
+                r = cudaMemcpyAsync(static_cast<uint8_t*>(dev) + off, pin, len, cudaMemcpyHostToDevice, st);
+            } else {
+                r = cudaMemcpyAsync(pin, static_cast<const uint8_t*>(dev) + off, len, cudaMemcpyDeviceToHost, st);
+            }
+            if (r == cudaSuccess) r = cudaEventRecord(ev, st);
+            if (r != cudaSuccess) { errs[w] = r; return; }
+            pending[b] = true;
+            pending_off[b] = off;
+            pending_len[b] = len;
+        }
+        for (int b = 0; b < 2; ++b) {
+            // drain in issue order: the older buffer first
+            const int bb = (j + b) & 1;
+            if (!pending[bb]) continue;
+            cudaError_t r = cudaEventSynchronize(ctx->stage_events[w * 2 + bb]);
+            if (r != cudaSuccess) { errs[w] = r; return; }
+            if (!to_device) memcpy(static_cast<uint8_t*>(host) + pending_off[bb], ctx->stage_pin[w * 2 + bb], pending_len[bb]);
+        }
+    };
+    std::vector<std::thread> th;
+    const int n_workers = static_cast<int>(std::min<size_t>(kStageWorkers, n_chunks));
+    for (int w = 1; w < n_workers; ++w) th.emplace_back(worker, w);
+    worker(0);
+    for (auto& t : th) t.join();
+    for (cudaError_t r : errs)
+        if (r != cudaSuccess) return r;
+    return cudaSuccess;
+}
+
+// host -> device on stream s for small arrays, staged (and synchronous) for large ones
+cudaError_t upload(bsg_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < kStageThreshold) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s);
+    return staged_copy(ctx, dev, const_cast<void*>(host), bytes, true);
+}
+}  // namespace
+
 // -------------------------------------------------------------------- hash ---
 extern "C" int bsg_hash_keys(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
                              uint64_t* out_hashes) {
@@ -262,9 +367,11 @@ extern "C" int bsg_hash_keys(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* 
         if (d_keys.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_keys + 1) != cudaSuccess ||
             d_h.alloc(n_keys * 4) != cudaSuccess) { rc = fail(BSG_ERR_NOMEM, "device alloc"); break; }
         cudaError_t e = cudaSuccess;
-        if (nbytes) e = cudaMemcpyAsync(d_keys.p, keys, nbytes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, key_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);  // one staged transfer set at a time
+        // memsets first: the staged uploads below block, the small async copies after them do not
+        e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = upload(ctx, d_keys.p, keys, nbytes, s);
+        if (e == cudaSuccess) e = upload(ctx, d_off.p, key_off, (n_keys + 1) * 8, s);
         if (e == cudaSuccess) e = launch_hash_keys(d_keys.p, d_off.p, n_keys, d_h.p, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_hashes, d_h.p, n_keys * 32, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -345,16 +452,18 @@ extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_
             d_gf.alloc(n_sub) != cudaSuccess || d_bf.alloc(n_filters) != cudaSuccess ||
             (group_filter2 && d_gf2.alloc(n_sub) != cudaSuccess)) { rc = fail(BSG_ERR_NOMEM, "device alloc"); break; }
         cudaError_t e = cudaSuccess;
-        if (nbytes) e = cudaMemcpyAsync(d_keys.p, keys, nbytes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, key_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);  // one staged transfer set at a time
+        // memsets first: the staged uploads below block, the small async copies after them do not
+        e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_out.p, 0, std::max<uint64_t>(n_words, 1) * 8, s);
+        if (e == cudaSuccess) e = upload(ctx, d_keys.p, keys, nbytes, s);
+        if (e == cudaSuccess) e = upload(ctx, d_off.p, key_off, (n_keys + 1) * 8, s);
         if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gb.p, gbe.data(), gbe.size() * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gf.p, gf.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && n_sub && group_filter2)
             e = cudaMemcpyAsync(d_gf2.p, gf2.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && n_filters)
             e = cudaMemcpyAsync(d_bf.p, bf.data(), n_filters * sizeof(BuildFilter), cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_out.p, 0, std::max<uint64_t>(n_words, 1) * 8, s);
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (e == cudaSuccess) e = cudaEventCreate(&ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&ev1);
@@ -367,7 +476,15 @@ extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_
         if (e == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_kernel_ms, ev0, ev1);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (e == cudaSuccess && n_words) e = cudaMemcpyAsync(out_words, d_out.p, n_words * 8, cudaMemcpyDeviceToHost, s);
+        // ev1 was synchronised above: the kernel is done, d_out is final
+        if (e == cudaSuccess && n_words) {
+            if (n_words * 8 < kStageThreshold) {
+                e = cudaMemcpyAsync(out_words, d_out.p, n_words * 8, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            } else {
+                e = staged_copy(ctx, d_out.p, out_words, n_words * 8, false);
+            }
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_build: %s", cudaGetErrorString(e));
     } while (0);
@@ -559,7 +676,10 @@ extern "C" int bsg_corpus_load(bsg_ctx* ctx, const bsg_filter_desc* desc, uint64
             CUDA_TRY(cudaMemcpyAsync(c->d_udesc, L.udesc.data(), n_units * 3 * sizeof(DevFilter), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(d_src_off.p, src_off.data(), n_units * 3 * 8, cudaMemcpyHostToDevice, s));
         }
-        if (n_words) CUDA_TRY(cudaMemcpyAsync(d_src.p, words, n_words * 8, cudaMemcpyHostToDevice, s));
+        if (n_words) {
+            std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+            CUDA_TRY(upload(ctx, d_src.p, words, n_words * 8, s));
+        }
         CUDA_TRY(launch_repack(d_src.p, d_src_off.p, c->d_udesc, n_units * 3, c->d_words, big_endian, s));
         int r = finish_corpus(ctx, c, L, desc, s);
         if (r) return r;
@@ -602,7 +722,10 @@ extern "C" int bsg_corpus_load_sections(bsg_ctx* ctx, const uint8_t* sections, c
         CUDA_TRY(d_off.alloc(n_units + 1));
         CUDA_TRY(d_info.alloc(n_units));
         CUDA_TRY(cudaMemsetAsync(d_sec.p + total, 0, kKeyPad, s));
-        if (total) CUDA_TRY(cudaMemcpyAsync(d_sec.p, sections, total, cudaMemcpyHostToDevice, s));
+        if (total) {
+            std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+            CUDA_TRY(upload(ctx, d_sec.p, sections, total, s));
+        }
         if (n_units) CUDA_TRY(cudaMemcpyAsync(d_off.p, sec_off, (n_units + 1) * 8, cudaMemcpyHostToDevice, s));
         CUDA_TRY(launch_parse_sections(d_sec.p, d_off.p, n_units, verify_crc, d_info.p, s));
         if (n_units) CUDA_TRY(cudaMemcpyAsync(info.data(), d_info.p, n_units * sizeof(SectionInfo), cudaMemcpyDeviceToHost, s));
