@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "bsg_abi_version", "bsg_strerror", "bsg_last_error", "bsg_create", "bsg_destroy", "bsg_set_stream",
     "bsg_synchronize", "bsg_device_info", "bsg_estimate", "bsg_hash_keys", "bsg_build", "bsg_corpus_load",
     "bsg_corpus_load_sections", "bsg_corpus_free", "bsg_corpus_units", "bsg_corpus_bitset_bytes",
-    "bsg_corpus_unit_desc", "bsg_probe", "bsg_query_create", "bsg_query_run", "bsg_query_fetch", "bsg_query_free",
+    "bsg_corpus_unit_desc", "bsg_corpus_set_parents", "bsg_probe_hierarchical", "bsg_probe", "bsg_query_create", "bsg_query_run", "bsg_query_fetch", "bsg_query_free",
     "bsg_query_last_launches", "bsg_timer_begin", "bsg_timer_end", "bsg_comm_unique_id", "bsg_comm_init",
     "bsg_or_reduce", "bsg_allgather_masks",
 ]
@@ -104,6 +104,8 @@ def lib():
     L.bsg_corpus_bitset_bytes.restype = u64
     L.bsg_corpus_unit_desc.argtypes = [vp, u64, vp]
     L.bsg_probe.argtypes = [vp, vp, vp, vp, u32, vp, vp, u32, vp, vp]
+    L.bsg_corpus_set_parents.argtypes = [vp, vp, vp, u64, u64]
+    L.bsg_probe_hierarchical.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, u32, vp, vp]
     L.bsg_query_create.argtypes = [vp, vp, vp, vp, u32, vp, vp, u32, C.POINTER(vp)]
     L.bsg_query_run.argtypes = [vp, vp, vp, i32, i32]
     L.bsg_query_fetch.argtypes = [vp, vp, u64, vp, vp]

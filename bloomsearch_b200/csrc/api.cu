@@ -504,6 +504,8 @@ struct bsg_corpus {
     uint32_t n_staged = 0;
     uint32_t* d_gather_list = nullptr;
     uint32_t n_gather = 0;
+    uint32_t* d_parent = nullptr;  // optional: unit -> index of its parent unit in another corpus (block -> file)
+    uint64_t n_parents = 0;        // number of units in the parent corpus
     uint32_t stage_cap_bytes = 0;  // largest staged unit (all kinds), 16-byte multiple
     uint64_t kind_bytes[3] = {0, 0, 0};         // Σ 8*ceil(m/64) per kind
     uint64_t staged_kind_bytes[3] = {0, 0, 0};  // same, staged units only (padded words)
@@ -518,6 +520,7 @@ extern "C" void bsg_corpus_free(bsg_corpus* c) {
     cudaFree(c->d_words);
     cudaFree(c->d_staged_list);
     cudaFree(c->d_gather_list);
+    cudaFree(c->d_parent);
     delete c;
 }
 
@@ -768,6 +771,10 @@ struct bsg_query {
     // results come down into it, then are memcpy'd to the caller's (pageable) buffers
     uint8_t* h_pin = nullptr;
     size_t cap_pin = 0;
+    // hierarchical probes: stage rows of the units whose parent survived + their count
+    StageRow* d_rows = nullptr;
+    size_t cap_rows = 0;
+    uint32_t* d_n_rows = nullptr;
     // output shape the pad words were last zeroed for (kernels never write pad words)
     uint64_t zeroed_units = ~0ull;
     uint32_t zeroed_row_words32 = ~0u, zeroed_groups = ~0u;
@@ -797,6 +804,8 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_matrix32);
     cudaFree(q->d_mask32);
     if (q->h_pin) cudaFreeHost(q->h_pin);
+    cudaFree(q->d_rows);
+    cudaFree(q->d_n_rows);
     delete q;
 }
 
@@ -952,7 +961,12 @@ extern "C" int bsg_query_create(bsg_ctx* ctx, const bsg_corpus* corpus, const ui
     return BSG_OK;
 }
 
-static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int path, int want_matrix, cudaStream_t s) {
+static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int path, int want_matrix, cudaStream_t s,
+                        const uint32_t* d_parent_mask32 = nullptr) {
+    // d_parent_mask32 != nullptr: hierarchical stage — unit u is probed only if bit c->d_parent[u] of
+    // the mask is set; its result is forced to "disqualified" otherwise.
+    const uint32_t* d_parent = d_parent_mask32 ? c->d_parent : nullptr;
+    if (d_parent_mask32 && !d_parent) return fail(BSG_ERR_INVALID, "corpus has no parents (bsg_corpus_set_parents)");
     (void)want_matrix;  // the matrix is always materialised (it is the tree kernel's input)
     if (!ctx || !c || !q) return fail(BSG_ERR_INVALID, "NULL argument");
     const bool matrix_only = (path & BSG_RUN_MATRIX_ONLY) != 0;
@@ -993,27 +1007,42 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
                 plan.stagger_ns = ctx->stagger_pct < 0 ? 0u
                                                        : static_cast<uint32_t>(std::min(2000.0, ns * ctx->stagger_pct / 100.0));
             }
+            const StageRow* rows = c->d_stab;
+            const uint32_t* d_n_rows = nullptr;
+            if (d_parent) {  // compact the surviving units' stage rows on the device
+                CUDA_TRY(ensure_cap(q->d_rows, q->cap_rows, static_cast<size_t>(c->n_staged) * sizeof(StageRow)));
+                if (!q->d_n_rows) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_n_rows), 4));
+                CUDA_TRY(launch_compact_rows(c->d_stab, c->n_staged, d_parent, d_parent_mask32, q->d_rows, q->d_n_rows, s));
+                ++launches;
+                rows = q->d_rows;
+                d_n_rows = q->d_n_rows;
+            }
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
-                CUDA_TRY(launch_probe_staged(plan, c->d_stab, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
+                CUDA_TRY(launch_probe_staged(plan, rows, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
                                              q->kind_mask, q->d_matrix32, q->row_words32, s, ctx->d_trace,
-                                             ctx->trace_slots));
+                                             ctx->trace_slots, d_n_rows));
                 ++launches;
             }
         } else if (c->n_staged) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_staged_list, c->n_staged, q->d_hashes,
-                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s));
+                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         d_parent_mask32));
             ++launches;
         }
         if (c->n_gather) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_gather_list, c->n_gather, q->d_hashes,
-                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s));
+                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         d_parent_mask32));
             ++launches;
         }
     }
     if (c->n_units && !matrix_only) {
         if (q->prog_len) {
-            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->d_prog, q->prog_len, q->d_mask32, s));
+            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->d_prog, q->prog_len, q->d_mask32, s,
+                                      d_parent, d_parent_mask32));
+        } else if (d_parent) {
+            CUDA_TRY(launch_parent_mask(q->d_mask32, c->n_units, d_parent, d_parent_mask32, s));
         } else {
             CUDA_TRY(launch_fill_mask(q->d_mask32, c->n_units, s));
         }
@@ -1093,6 +1122,67 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->scratch_pool.push_back(q);
     }
+    pool_put(ctx, s);
+    return rc;
+}
+
+extern "C" int bsg_corpus_set_parents(bsg_ctx* ctx, bsg_corpus* corpus, const uint32_t* parent, uint64_t n_units,
+                                      uint64_t n_parent_units) {
+    if (!ctx || !corpus || (n_units && !parent)) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (n_units != corpus->n_units) return fail(BSG_ERR_INVALID, "parent array must have one entry per unit");
+    for (uint64_t u = 0; u < n_units; ++u)
+        if (parent[u] >= n_parent_units) return fail(BSG_ERR_INVALID, "unit %llu: parent %u out of range", (unsigned long long)u, parent[u]);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaFree(corpus->d_parent);
+    corpus->d_parent = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&corpus->d_parent), std::max<uint64_t>(n_units, 1) * 4));
+    if (n_units) CUDA_TRY(cudaMemcpy(corpus->d_parent, parent, n_units * 4, cudaMemcpyHostToDevice));
+    corpus->n_parents = n_parent_units;
+    return BSG_OK;
+}
+
+static bsg_query* scratch_get(bsg_ctx* ctx) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->scratch_pool.empty()) {
+            bsg_query* q = ctx->scratch_pool.back();
+            ctx->scratch_pool.pop_back();
+            return q;
+        }
+    }
+    return new (std::nothrow) bsg_query();
+}
+static void scratch_put(bsg_ctx* ctx, bsg_query* q) {
+    if (!q) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->scratch_pool.push_back(q);
+}
+
+extern "C" int bsg_probe_hierarchical(bsg_ctx* ctx, const bsg_corpus* files, const bsg_corpus* blocks,
+                                      const uint8_t* keys, const uint64_t* key_off, uint32_t n_keys,
+                                      const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                                      uint64_t* out_file_mask, uint64_t* out_block_mask) {
+    if (!ctx || !files || !blocks) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!blocks->d_parent || blocks->n_parents != files->n_units)
+        return fail(BSG_ERR_INVALID, "blocks corpus has no parents into this files corpus (bsg_corpus_set_parents)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    bsg_query* qf = scratch_get(ctx);
+    bsg_query* qb = scratch_get(ctx);
+    int rc = (qf && qb) ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
+    // stage 1: file level (query_exec.go:399-406)
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, files, keys, key_off, n_keys, key_kind, prog, prog_len, s, qf, true);
+    if (rc == BSG_OK) rc = query_run_on(ctx, files, qf, BSG_PROBE_AUTO, 0, s);
+    // stage 2: block level, only blocks of surviving files (query_exec.go:572-615)
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, blocks, keys, key_off, n_keys, key_kind, prog, prog_len, s, qb, true);
+    if (rc == BSG_OK) rc = query_run_on(ctx, blocks, qb, BSG_PROBE_AUTO, 0, s, qf->d_mask32);
+    if (rc == BSG_OK && out_file_mask)
+        rc = query_fetch_on(qf, files->n_units, nullptr, out_file_mask, s);
+    if (rc == BSG_OK) rc = query_fetch_pinned(qb, blocks->n_units, nullptr, out_block_mask, s);
+    else cudaStreamSynchronize(s);
+    scratch_put(ctx, qf);
+    scratch_put(ctx, qb);
     pool_put(ctx, s);
     return rc;
 }

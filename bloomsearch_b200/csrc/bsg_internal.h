@@ -88,12 +88,18 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
                                 uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
                                 uint32_t row_words32, cudaStream_t s, uint64_t* d_trace = nullptr,
-                                uint32_t trace_slots = 0);
+                                uint32_t trace_slots = 0, const uint32_t* d_n_list = nullptr);
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
-                                uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s);
+                                uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s,
+                                const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr);
 cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
-                             const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s);
+                             const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s,
+                             const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr);
+cudaError_t launch_parent_mask(uint32_t* d_mask32, uint64_t n_units, const uint32_t* d_parent,
+                               const uint32_t* d_parent_mask32, cudaStream_t s);
+cudaError_t launch_compact_rows(const StageRow* d_stab, uint32_t n_rows, const uint32_t* d_parent,
+                                const uint32_t* d_parent_mask32, StageRow* d_out, uint32_t* d_n_out, cudaStream_t s);
 cudaError_t launch_fill_mask(uint32_t* d_mask32, uint64_t n_units, cudaStream_t s);
 
 cudaError_t build_configure(int max_smem_optin);

@@ -141,7 +141,8 @@ __device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64
 // instructions per iteration and lost; see DESIGN.md.)
 template <int MAXT, bool TRACE>
 __global__ void __launch_bounds__(MAXT, 1)
-probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const uint64_t* __restrict__ words,
+probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
+                    const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
                     uint32_t n_stages, uint32_t stage_bytes, uint32_t stagger_ns, uint64_t* __restrict__ trace,
@@ -171,6 +172,8 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list, const ui
     }
     __syncthreads();
 
+    // hierarchical probes compact the surviving units on the device: their count lives there too
+    const uint32_t n_list = n_list_dev ? __ldg(n_list_dev) : n_list_host;
     const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
     // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit.  stagger_ns > 0
@@ -255,8 +258,9 @@ cudaError_t probe_staged_configure(int max_smem_optin) {
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
                                 uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
-                                uint32_t row_words32, cudaStream_t s, uint64_t* d_trace, uint32_t trace_slots) {
-    if (n_list == 0 || n_keys == 0) return cudaSuccess;
+                                uint32_t row_words32, cudaStream_t s, uint64_t* d_trace, uint32_t trace_slots,
+                                const uint32_t* d_n_list) {
+    if ((n_list == 0 && !d_n_list) || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
     // one key per thread; at least 4 warps so a small batch still has some latency hiding
@@ -266,11 +270,11 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (warps > 32) warps = 32;
     if (d_trace)
         probe_staged_kernel<1024, true><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
-            d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
             static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_trace, trace_slots);
     else
         probe_staged_kernel<1024, false><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
-            d_stab, n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
             static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, nullptr, 0);
     return cudaGetLastError();
 }
@@ -283,7 +287,8 @@ __global__ void __launch_bounds__(256)
 probe_gather_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restrict__ words,
                     const uint32_t* __restrict__ unit_list, uint32_t n_list, const uint64_t* __restrict__ hashes,
                     const uint8_t* __restrict__ kinds, uint32_t n_keys, uint32_t g_log2, uint32_t chunks,
-                    uint32_t* __restrict__ matrix32, uint32_t row_words32) {
+                    uint32_t* __restrict__ matrix32, uint32_t row_words32, const uint32_t* __restrict__ parent,
+                    const uint32_t* __restrict__ parent_mask32) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t gwarp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     uint32_t list_idx, key, grp = 0;
@@ -302,7 +307,12 @@ probe_gather_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restr
     uint32_t unit = 0;
     if (unit_ok) {
         unit = unit_list ? __ldg(&unit_list[list_idx]) : list_idx;
-        if (key < n_keys) {
+        bool alive = true;  // hierarchical probe: a block whose file was disqualified is not read at all
+        if (parent) {
+            const uint32_t f = __ldg(&parent[unit]);
+            alive = (__ldg(&parent_mask32[f >> 5]) >> (f & 31u)) & 1u;
+        }
+        if (alive && key < n_keys) {
             const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * key);
             const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
             const uint32_t kd = __ldg(&kinds[key]);
@@ -338,7 +348,8 @@ probe_gather_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restr
 
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
-                                uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s) {
+                                uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s, const uint32_t* d_parent,
+                                const uint32_t* d_parent_mask32) {
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
     uint32_t g_log2 = 5, chunks = 1;
     uint64_t n_warps;
@@ -355,7 +366,8 @@ cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_word
     const uint64_t n_blocks = (n_warps + warps_per_block - 1) / warps_per_block;
     if (n_blocks > 0x7fffffffull) return cudaErrorInvalidValue;
     probe_gather_kernel<<<static_cast<uint32_t>(n_blocks), warps_per_block * 32, 0, s>>>(
-        d_udesc, d_words, d_unit_list, n_list, d_hashes, d_kinds, n_keys, g_log2, chunks, d_matrix32, row_words32);
+        d_udesc, d_words, d_unit_list, n_list, d_hashes, d_kinds, n_keys, g_log2, chunks, d_matrix32, row_words32,
+        d_parent, d_parent_mask32);
     return cudaGetLastError();
 }
 
@@ -363,13 +375,19 @@ cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_word
 // One thread per unit; evaluation stack is a 64-bit bit-stack (BSG_MAX_STACK).
 __global__ void __launch_bounds__(256)
 tree_eval_kernel(const uint32_t* __restrict__ matrix32, uint32_t row_words32, uint64_t n_units,
-                 const bsg_expr_op* __restrict__ prog, uint32_t prog_len, uint32_t* __restrict__ mask32) {
+                 const bsg_expr_op* __restrict__ prog, uint32_t prog_len, uint32_t* __restrict__ mask32,
+                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ parent_mask32) {
     extern __shared__ bsg_expr_op sprog[];
     for (uint32_t i = threadIdx.x; i < prog_len; i += blockDim.x) sprog[i] = prog[i];
     __syncthreads();
     const uint64_t unit = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool alive = false;
-    if (unit < n_units) {
+    bool parent_alive = true;
+    if (unit < n_units && parent) {
+        const uint32_t f = __ldg(&parent[unit]);
+        parent_alive = (__ldg(&parent_mask32[f >> 5]) >> (f & 31u)) & 1u;
+    }
+    if (unit < n_units && parent_alive) {  // rows of disqualified parents were never written
         const uint32_t* row = matrix32 + unit * row_words32;
         uint64_t stack = 0;
         for (uint32_t pc = 0; pc < prog_len; ++pc) {
@@ -396,12 +414,13 @@ tree_eval_kernel(const uint32_t* __restrict__ matrix32, uint32_t row_words32, ui
 }
 
 cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
-                             const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s) {
+                             const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s,
+                             const uint32_t* d_parent, const uint32_t* d_parent_mask32) {
     if (n_units == 0) return cudaSuccess;
     const uint64_t n_blocks = (n_units + 255) / 256;
     if (n_blocks > 0x7fffffffull) return cudaErrorInvalidValue;
     tree_eval_kernel<<<static_cast<uint32_t>(n_blocks), 256, prog_len * sizeof(bsg_expr_op), s>>>(
-        d_matrix32, row_words32, n_units, d_prog, prog_len, d_mask32);
+        d_matrix32, row_words32, n_units, d_prog, prog_len, d_mask32, d_parent, d_parent_mask32);
     return cudaGetLastError();
 }
 
@@ -411,6 +430,60 @@ __global__ void fill_mask_kernel(uint32_t* __restrict__ mask32, uint64_t n_units
     if (w >= n_words) return;
     const uint64_t rem = n_units - w * 32;
     mask32[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+}
+
+// mask[u] = parent_mask[parent[u]]  (no expression: a block survives iff its file did)
+__global__ void __launch_bounds__(256)
+parent_mask_kernel(uint32_t* __restrict__ mask32, uint64_t n_units, const uint32_t* __restrict__ parent,
+                   const uint32_t* __restrict__ parent_mask32) {
+    const uint64_t unit = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (unit < n_units) {
+        const uint32_t f = __ldg(&parent[unit]);
+        alive = (__ldg(&parent_mask32[f >> 5]) >> (f & 31u)) & 1u;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && (unit - (threadIdx.x & 31)) < n_units) mask32[unit >> 5] = bits;
+}
+
+cudaError_t launch_parent_mask(uint32_t* d_mask32, uint64_t n_units, const uint32_t* d_parent,
+                               const uint32_t* d_parent_mask32, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
+    parent_mask_kernel<<<static_cast<uint32_t>((n_units + 255) / 256), 256, 0, s>>>(d_mask32, n_units, d_parent,
+                                                                                      d_parent_mask32);
+    return cudaGetLastError();
+}
+
+// Stream compaction between the two stages of a hierarchical probe: keeps the stage rows of the
+// units whose parent (file) survived.  Order is not preserved (no consumer needs it).
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const StageRow* __restrict__ stab, uint32_t n_rows, const uint32_t* __restrict__ parent,
+                    const uint32_t* __restrict__ parent_mask32, StageRow* __restrict__ out, uint32_t* __restrict__ n_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n_rows) {
+        const uint32_t f = __ldg(&parent[stab[i].unit]);
+        keep = (__ldg(&parent_mask32[f >> 5]) >> (f & 31u)) & 1u;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && bal) base = atomicAdd(n_out, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+        const uint4* src = reinterpret_cast<const uint4*>(&stab[i]);
+        uint4* dst = reinterpret_cast<uint4*>(&out[base + __popc(bal & ((1u << lane) - 1u))]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = __ldg(src + j);
+    }
+}
+
+cudaError_t launch_compact_rows(const StageRow* d_stab, uint32_t n_rows, const uint32_t* d_parent,
+                                const uint32_t* d_parent_mask32, StageRow* d_out, uint32_t* d_n_out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_n_out, 0, 4, s);
+    if (e != cudaSuccess || n_rows == 0) return e;
+    compact_rows_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(d_stab, n_rows, d_parent, d_parent_mask32, d_out, d_n_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill_mask(uint32_t* d_mask32, uint64_t n_units, cudaStream_t s) {

@@ -321,11 +321,31 @@ class Corpus:
         N.check(N.lib().bsg_probe(self.ctx.handle, self._h, N.ptr(blob), N.ptr(off), len(off) - 1, N.ptr(kinds), pp, pl,
                                   N.ptr(out_matrix), N.ptr(out_mask)))
 
+    def set_parents(self, parent: np.ndarray, n_parent_units: int) -> None:
+        """Record, for every unit (block), the index of its parent unit (file) in another corpus."""
+        parent = np.ascontiguousarray(parent, dtype=np.uint32)
+        N.check(N.lib().bsg_corpus_set_parents(self.ctx.handle, self._h, N.ptr(parent), len(parent), n_parent_units))
+
     def evaluate_bloom_filters(self, query: Optional[BloomQuery]) -> np.ndarray:
         """evaluateBloomFilters (query_exec.go:75-87) for every unit at once -> bool[n_units]."""
         cq = compile_bloom_query(query)
         _, mask = self.probe(cq.keys, cq.kinds, cq.prog, want_matrix=False)
         return unpack_mask(mask, self.n_units)
+
+
+def probe_hierarchical(files: Corpus, blocks: Corpus, query: Optional[BloomQuery]):
+    """The reference's two-stage pruning in one call: file-level filters first (query_exec.go:399-406),
+    then block-level filters only for blocks of surviving files (query_exec.go:572-615).
+    Returns (file_survives bool[n_files], block_survives bool[n_blocks])."""
+    cq = compile_bloom_query(query)
+    blob, off = N.pack_keys(cq.keys)
+    kinds = np.ascontiguousarray(cq.kinds, dtype=np.uint8)
+    fmask = np.zeros((files.n_units + 63) // 64, dtype=np.uint64)
+    bmask = np.zeros((blocks.n_units + 63) // 64, dtype=np.uint64)
+    pp, pl = (None, 0) if cq.prog is None else (N.ptr(cq.prog), len(cq.prog))
+    N.check(N.lib().bsg_probe_hierarchical(files.ctx.handle, files.handle, blocks.handle, N.ptr(blob), N.ptr(off),
+                                           len(cq.keys), N.ptr(kinds), pp, pl, N.ptr(fmask), N.ptr(bmask)))
+    return unpack_mask(fmask, files.n_units), unpack_mask(bmask, blocks.n_units)
 
 
 class Query:

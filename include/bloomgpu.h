@@ -161,6 +161,19 @@ int bsg_probe(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys, const
               uint32_t n_keys, const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
               uint64_t *out_matrix, uint64_t *out_mask);
 
+/* Hierarchical probe — the reference's two stages in one call: file-level filters first
+ * (query_exec.go:399-406), then block-level filters only for blocks whose file survived
+ * (query_exec.go:572-615); the surviving units are compacted on the device between the stages.
+ * bsg_corpus_set_parents records, for every unit of `blocks`, the index of its file in `files`.
+ * out_file_mask (nullable): ceil(files/64) words; out_block_mask: ceil(blocks/64) words,
+ * bit u = block u survives (its file survived AND its own filters pass the expression). */
+int bsg_corpus_set_parents(bsg_ctx *ctx, bsg_corpus *corpus, const uint32_t *parent, uint64_t n_units,
+                           uint64_t n_parent_units);
+int bsg_probe_hierarchical(bsg_ctx *ctx, const bsg_corpus *files, const bsg_corpus *blocks,
+                           const uint8_t *keys, const uint64_t *key_off, uint32_t n_keys,
+                           const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
+                           uint64_t *out_file_mask, uint64_t *out_block_mask);
+
 /* Resident form of the same call, for callers that keep a query on the device
  * and for measurement: create uploads + hashes the keys once; run launches the
  * probe (asynchronously, on the ctx stream); fetch copies results to the host. */

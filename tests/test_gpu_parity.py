@@ -458,3 +458,55 @@ def test_bsg_probe_scratch_reuse_across_shapes(ctx):
         assert np.array_equal(m, want), n
         assert np.array_equal(mask, want_mask), n
     corpus.close()
+
+
+# ------------------------------------------------------ hierarchical probe ---
+@pytest.mark.parametrize("n_extra_keys", [0, 60])
+def test_hierarchical_probe_matches_two_stage_reference(ctx, n_extra_keys):
+    """File stage (query_exec.go:399-406) then block stage only for blocks of surviving files
+    (query_exec.go:572-615): block survives iff file filters pass AND its own filters pass."""
+    c = SynthCorpus(11, 0, 48, 300, 6)   # 8 files x 6 blocks
+    counts = c.group_counts().reshape(-1)
+    bdesc = np.zeros(len(counts), dtype=N.DESC_DTYPE)
+    wo = 0
+    for g, n in enumerate(counts):
+        m, k = bs.estimate_parameters(max(int(n), 1), 0.001)
+        bdesc[g] = (m, k, wo)
+        wo += (m + 63) // 64
+    n_bw = wo
+    fdesc = np.zeros(c.n_files * 3, dtype=N.DESC_DTYPE)
+    for f in range(c.n_files):
+        for kind in range(3):
+            m, k = bs.estimate_parameters(max(int(c.file_counts[f][kind]), 1), 0.001)
+            fdesc[f * 3 + kind] = (m, k, wo)
+            wo += (m + 63) // 64
+    gf = np.arange(len(bdesc), dtype=np.uint32)
+    gf2 = np.array([len(bdesc) + (b // c.blocks_per_file) * 3 + kind for b in range(c.n_blocks) for kind in range(3)], np.uint32)
+    words = ctx.build(c.blob, c.key_off, c.group_begin, gf, gf2, np.concatenate([bdesc, fdesc]), wo)
+    want_words = cref.build_filters(c.blob, c.key_off, c.group_begin, gf, gf2, np.concatenate([bdesc, fdesc]), wo)
+    assert np.array_equal(words, want_words)
+    files = bs.Corpus(ctx, fdesc, words)      # descriptors index into the same words array
+    blocks = bs.Corpus(ctx, bdesc, words)
+    parent = (np.arange(c.n_blocks) // c.blocks_per_file).astype(np.uint32)
+    blocks.set_parents(parent, c.n_files)
+    ts_key = b"%d" % (1700000000 + 300 * 20 + 7)        # lives in block 20 (file 3) only
+    uid = c.key(int(c.group_begin[3 * 40 + 1]) + 300 + 5)  # some user id token of block 40 (file 6)
+    q = bs.BloomQuery(bs.Or(bs.Token(ts_key), bs.And(bs.Token(uid), bs.Field(b"nested.az")),
+                            *[bs.Token(b"zz-absent-%d" % i) for i in range(n_extra_keys)]))
+    got_f, got_b = bs.probe_hierarchical(files, blocks, q)
+    cq = bs.compile_bloom_query(q)
+    blob, off = N.pack_keys(cq.keys)
+    wf = bs.unpack_mask(cref.probe_mask(fdesc, words, c.n_files, blob, off, cq.kinds, cq.prog), c.n_files)
+    wb = bs.unpack_mask(cref.probe_mask(bdesc, words, c.n_blocks, blob, off, cq.kinds, cq.prog), c.n_blocks)
+    assert np.array_equal(got_f, wf)
+    assert np.array_equal(got_b, wb & wf[parent])
+    assert got_b[20] and got_f[3] and 0 < got_f.sum() < c.n_files
+    # no expression: everything survives both stages
+    f_all, b_all = bs.probe_hierarchical(files, blocks, None)
+    assert f_all.all() and b_all.all()
+    # a corpus without parents is rejected
+    with pytest.raises(bs.BloomGpuError):
+        bs.probe_hierarchical(files, bs.Corpus(ctx, bdesc, words), q)
+    files.close()
+    blocks.close()
+    assert n_bw > 0
