@@ -258,8 +258,8 @@ int validate_filter(const bsg_filter_desc& d, uint64_t n_words, const char* what
 // its chunks through two pinned buffers (memcpy overlapped with the previous chunk's DMA) on its
 // own stream.  Blocks until the whole transfer is complete.
 namespace {
-constexpr int kStageWorkers = 4;
-constexpr size_t kStageChunk = 8u << 20;
+constexpr int kStageWorkers = 12;
+constexpr size_t kStageChunk = 4u << 20;
 constexpr size_t kStageThreshold = 4u << 20;  // below this a plain cudaMemcpyAsync is used
 
 cudaError_t stage_init(bsg_ctx* ctx) {

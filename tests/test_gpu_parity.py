@@ -510,3 +510,44 @@ def test_hierarchical_probe_matches_two_stage_reference(ctx, n_extra_keys):
     files.close()
     blocks.close()
     assert n_bw > 0
+
+
+def test_concurrent_callers_share_one_context(ctx):
+    """The probe entry points are thread-safe and re-entrant (query_exec.go:303-357 runs up to
+    MaxQueryConcurrency file workers): 8 host threads x 25 bsg_probe calls with different batches
+    on one ctx / corpus, each checked against the oracle."""
+    import threading
+    rng = random.Random(77)
+    unit_keys = [(rand_keys(rng, 6, 3, 8), rand_keys(rng, 180, 1, 10), rand_keys(rng, 170, 4, 20)) for _ in range(64)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    corpus = bs.Corpus(ctx, desc, words)
+    batches = []
+    for t in range(8):
+        keys, kinds = _mixed_keys(random.Random(1000 + t), unit_keys, 40 + 37 * t, 30 + 11 * t)
+        kinds = np.asarray(kinds, np.uint8)
+        blob, off = N.pack_keys(keys)
+        prog = np.array([(N.OP_LEAF, 0), (N.OP_LEAF, 1), (N.OP_AND, 2), (N.OP_LEAF, len(keys) - 1), (N.OP_OR, 2)], dtype=N.OP_DTYPE)
+        batches.append((keys, kinds, blob, off, prog,
+                        cref.probe_matrix(desc, words, len(unit_keys), blob, off, kinds),
+                        cref.probe_mask(desc, words, len(unit_keys), blob, off, kinds, prog)))
+    errors = []
+
+    def worker(t):
+        keys, kinds, blob, off, prog, want_m, want_mask = batches[t]
+        m = np.zeros_like(want_m)
+        mask = np.zeros_like(want_mask)
+        for _ in range(25):
+            m[:] = 0
+            mask[:] = 0
+            corpus.probe_packed(blob, off, kinds, prog, m, mask)
+            if not (np.array_equal(m, want_m) and np.array_equal(mask, want_mask)):
+                errors.append(t)
+                return
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    corpus.close()
+    assert not errors, errors
