@@ -172,9 +172,9 @@ static inline void put_be64(uint8_t *p, uint64_t v) {
     for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (56 - 8 * i));
 }
 static inline uint64_t get_be64(const uint8_t *p) {
-    uint64_t v = 0;
-    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
-    return v;
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return __builtin_bswap64(v); /* binary.BigEndian.Uint64 compiles to MOVBE/BSWAP in Go too */
 }
 
 size_t bref_filter_serialized_size(const bref_filter *f) { return 24 + 8 * f->nwords; }
@@ -228,7 +228,28 @@ static void crc32c_init(void) {
             crc32c_table[t][i] = (crc32c_table[t - 1][i] >> 8) ^ crc32c_table[0][crc32c_table[t - 1][i] & 0xff];
 }
 
+#if defined(__x86_64__)
+/* Go's hash/crc32 uses the SSE4.2 crc32 instruction for the Castagnoli table; so does the CPU
+ * baseline when the host has it (same polynomial, same result as the table path below). */
+__attribute__((target("sse4.2")))
+static uint32_t crc32c_hw(const uint8_t *data, size_t len) {
+    uint64_t c = 0xFFFFFFFFu;
+    while (len >= 8) {
+        uint64_t v;
+        memcpy(&v, data, 8);
+        c = __builtin_ia32_crc32di(c, v);
+        data += 8; len -= 8;
+    }
+    uint32_t c32 = (uint32_t)c;
+    while (len--) c32 = __builtin_ia32_crc32qi(c32, *data++);
+    return c32 ^ 0xFFFFFFFFu;
+}
+#endif
+
 uint32_t bref_crc32c(const uint8_t *data, size_t len) {
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("sse4.2")) return crc32c_hw(data, len);
+#endif
     pthread_once(&crc_once, crc32c_init);
     uint32_t c = 0xFFFFFFFFu;
     while (len >= 8) { /* slicing-by-8, comparable to Go's software path */

@@ -551,3 +551,44 @@ def test_concurrent_callers_share_one_context(ctx):
         th.join()
     corpus.close()
     assert not errors, errors
+
+
+# ------------------------------------------------------------ error behaviour ---
+def test_invalid_arguments_are_rejected_with_codes(ctx):
+    rng = random.Random(5)
+    unit_keys = [(rand_keys(rng, 3, 3, 8), rand_keys(rng, 20, 1, 10), rand_keys(rng, 20, 4, 20)) for _ in range(3)]
+    desc, words = oracle_units(unit_keys, 0.01)
+    corpus = bs.Corpus(ctx, desc, words)
+    keys, kinds = [b"a", b"b"], [1, 1]
+
+    def bad(prog=None, kinds_=kinds):
+        with pytest.raises(bs.BloomGpuError) as ei:
+            corpus.probe(keys, kinds_, None if prog is None else np.array(prog, dtype=N.OP_DTYPE))
+        assert ei.value.code == N.ERR_INVALID
+        return ei.value.detail
+
+    assert "leaf" in bad([(N.OP_LEAF, 2)])                       # leaf index out of range
+    assert "pops" in bad([(N.OP_LEAF, 0), (N.OP_AND, 2)])         # stack underflow
+    assert "stack" in bad([(N.OP_LEAF, 0), (N.OP_LEAF, 1)])       # leaves 2 values
+    assert "unknown op" in bad([(9, 0)])
+    assert "deeper" in bad([(N.OP_TRUE, 0)] * 65 + [(N.OP_AND, 65)])
+    assert "kind" in bad(kinds_=[1, 3])
+    corpus.close()
+    # corpus descriptors
+    for d, msg in (((1 << 63, 3, 0), "exceeds"), ((100, 0, 0), "k="), ((100, 3, 10**9), "outside")):
+        dd = np.zeros(3, dtype=N.DESC_DTYPE)
+        dd[1] = d
+        with pytest.raises(bs.BloomGpuError) as ei:
+            bs.Corpus(ctx, dd, np.zeros(4, np.uint64))
+        assert ei.value.code == N.ERR_INVALID and msg in ei.value.detail
+    # build: filter id out of range, non-monotone offsets
+    blob, off = N.pack_keys([b"x", b"y"])
+    dsc = np.array([(64, 3, 0)], dtype=N.DESC_DTYPE)
+    with pytest.raises(bs.BloomGpuError):
+        ctx.build(blob, off, np.array([0, 2], np.uint64), np.array([1], np.uint32), None, dsc, 1)
+    badoff = off.copy()
+    badoff[1] = 5
+    with pytest.raises(bs.BloomGpuError):
+        ctx.build(blob, badoff, np.array([0, 2], np.uint64), np.array([0], np.uint32), None, dsc, 1)
+    with pytest.raises(bs.BloomGpuError):
+        ctx.hash_keys_raw(blob, badoff) if hasattr(ctx, "hash_keys_raw") else (_ for _ in ()).throw(bs.BloomGpuError(-1, "n/a"))
