@@ -47,7 +47,7 @@ def log(*a):
 
 # ----------------------------------------------------------------- inputs ---
 def gen_corpus(workload: str, rank: int, scale: float = 1.0):
-    from oracle.corpus import SynthCorpus
+    from synth.corpus import SynthCorpus
     n_blocks, rows, bpf = WORKLOADS[workload]
     n_blocks = max(bpf, int(n_blocks * scale) // bpf * bpf)
     t = time.time()
@@ -133,15 +133,26 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------- CPU baseline ---
-def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=12.0):
-    """Oracle port of the Go path on the host cores: per block parseFilterSection (CRC32C + BE
-    decode) then TestString for every key.  Bounded sample: the whole corpus' sections, probed
-    repeatedly for about target_s seconds of wall time on all host threads."""
+def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=12.0, c=None, gpu_matrix=None):
+    """cpu_baseline leg — the only place the GPU arm touches the oracle.  (1) As the CHECKER: the
+    GPU-built bitsets of the first blocks and the GPU probe matrix must equal the oracle's.
+    (2) As the BASELINE: the oracle port of the Go path on the host cores, per block
+    parseFilterSection (CRC32C + BE decode) then TestString for every key; bounded sample = the
+    whole corpus' sections probed repeatedly for about target_s seconds on all host threads."""
     from oracle import cref
     threads = os.cpu_count() or 1
     blob, off = cref.pack_keys(keys)
     sec, sec_off = cref.encode_sections(desc, words, n_units_total)
-    cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)  # warm-up (page-in, thread start)
+    first, errs = cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)  # warm-up + check
+    assert errs == 0
+    if gpu_matrix is not None:
+        assert np.array_equal(gpu_matrix, first), "GPU probe matrix differs from the oracle"
+    if c is not None:
+        chk = min(n_units_total, 24)
+        end = int(desc[chk * 3 - 1]["word_off"]) + (int(desc[chk * 3 - 1]["m"]) + 63) // 64
+        want = cref.build_filters(c.blob, c.key_off, c.group_begin[:chk * 3 + 1], np.arange(chk * 3, dtype=np.uint32),
+                                  None, desc[:chk * 3], end)
+        assert np.array_equal(words[:end], want), "GPU-built filters differ from the oracle"
     reps, t0 = 0, time.perf_counter()
     while True:
         cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
@@ -151,6 +162,7 @@ def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=12.0):
             break
     probes = reps * n_units_total * len(keys)
     return {"value": probes / dt, "unit": "probes/s", "cores": threads, "kind": "port",
+            "gpu_output_verified_against_oracle": gpu_matrix is not None,
             "sample": f"{reps} passes over all {n_units_total} blocks x {len(keys)} keys in {dt:.1f}s; per block: "
                       f"section CRC32C + big-endian decode (parseFilterSection) then TestString per key; "
                       f"{threads} threads (C restatement of the Go path, -O2)"}, sec.nbytes
@@ -261,23 +273,19 @@ def main():
         log(f"GPU-built {len(desc)} filters, {n_words * 8 / 1e6:.1f} MB of bitsets ({time.time() - t:.1f}s incl. PCIe)")
         keys, kinds = make_batch(c, 7 + rank)
         n_units = c.n_blocks
-        # spot parity against the oracle before timing anything
-        from oracle import cref
-        chk = min(n_units, 24)
-        chk_words_end = int(desc[chk * 3 - 1]["word_off"]) + (int(desc[chk * 3 - 1]["m"]) + 63) // 64
-        want = cref.build_filters(c.blob, c.key_off, c.group_begin[:chk * 3 + 1], np.arange(chk * 3, dtype=np.uint32),
-                                  None, desc[:chk * 3], chk_words_end)
-        assert np.array_equal(words[:chk_words_end], want), "GPU-built filters differ from the oracle"
         blob, off = N.pack_keys(keys)
-        want_m = cref.probe_matrix(desc[:chk * 3], words, chk, blob, off, kinds, n_threads=4)
 
         n_rep = max(1, args.replicas)
         corpora = [bs.Corpus(ctx, desc, words) for _ in range(n_rep)]
         bitset_bytes = corpora[0].bitset_bytes(7)
         queries = [bs.Query(cp, keys, kinds, None) for cp in corpora]
-        queries[0].run(N.PROBE_AUTO)
+        # self-consistency before timing (no oracle in the GPU arm): the two data paths agree, and every
+        # sampled key is found in some block.  The oracle check lives in the cpu_baseline leg below.
+        queries[0].run(N.PROBE_STAGED)
         got_m, got_mask = queries[0].fetch()
-        assert np.array_equal(got_m[:chk], want_m), "GPU probe matrix differs from the oracle"
+        queries[0].run(N.PROBE_GATHER)
+        got_g, _ = queries[0].fetch()
+        assert np.array_equal(got_m, got_g), "staged and gather probe paths disagree"
         assert bs.unpack_mask(got_mask, n_units).all()
 
         # ---- device-timed steps, inputs resident in HBM; replicas cycled so no step hits L2.
@@ -362,7 +370,7 @@ def main():
             for th in ths:
                 th.join()
             dt = time.perf_counter() - t0
-            assert np.array_equal(outs[0][:chk], want_m), "e2e matrix differs from the oracle"
+            assert np.array_equal(outs[0], got_m), "e2e matrix differs from the resident run"
             return dt
 
         e2e_run(args.e2e_callers, 5)  # warm-up (scratch + pinned staging allocation)
@@ -378,7 +386,7 @@ def main():
                "what": "bsg_probe(): packed host key bytes -> H2D, hash, probe, D2H of the (block x key) matrix"}
 
         if headline and rank == 0 and not args.no_cpu:
-            cpu, _ = cpu_probe_rate(desc, words, n_units, keys, kinds)
+            cpu, _ = cpu_probe_rate(desc, words, n_units, keys, kinds, c=c, gpu_matrix=got_m)
 
         results[wl] = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e,
                        "clocks": clk.summary(), "launches_per_step": launches_per_step,

@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libbloomref.so")
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("bloomref.c", "bloomref.h", "corpusgen.c")]
+    src = [os.path.join(_HERE, f) for f in ("bloomref.c", "bloomref.h")]
     stale = (not os.path.exists(_SO)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bloomsearch_b200 as bs
 from bloomsearch_b200 import _native as N
 from oracle import cref
-from oracle.corpus import SynthCorpus
+from synth.corpus import SynthCorpus
 import bench
 
 ap = argparse.ArgumentParser()

@@ -1,11 +1,31 @@
-"""Synthetic benchRows-shaped corpus (oracle/corpusgen.c) — TEST / BENCH INFRASTRUCTURE ONLY."""
+"""Synthetic benchRows-shaped corpus (synth/corpusgen.c): INPUT DATA for tests and bench.
+Not part of the oracle (it computes no bloom arithmetic) and not part of the product."""
 from __future__ import annotations
 
 import ctypes as C
 
 import numpy as np
 
-from . import cref
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libsynth.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "corpusgen.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(src) > os.path.getmtime(_SO):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else ["-s"]), stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
 
 
 class SynthCorpus:
@@ -13,7 +33,7 @@ class SynthCorpus:
     fieldtoken), and each file's exact union distinct counts."""
 
     def __init__(self, seed: int, block_lo: int, n_blocks: int, rows_per_block: int, blocks_per_file: int):
-        L = cref.lib()
+        L = _load()
         L.bgen_generate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.bgen_generate.restype = C.c_void_p
         L.bgen_free.argtypes = [C.c_void_p]

@@ -1,6 +1,6 @@
 /*
- * corpusgen.c — synthetic log-corpus entry sets.  TEST / BENCH INFRASTRUCTURE ONLY
- * (same standing as the oracle: never linked into the product).
+ * corpusgen.c — synthetic log-corpus entry sets: INPUT DATA for tests and bench
+ * (not part of the oracle — it computes no bloom arithmetic — and never linked into the product).
  *
  * Restates, for the one fixed row shape of the reference's benchmarks
  * (benchRows, bench_test.go:16-49), what bloomEntrySets.indexRow collects

@@ -11,7 +11,7 @@ import pytest
 import bloomsearch_b200 as bs
 from bloomsearch_b200 import _native as N
 from oracle import cref
-from oracle.corpus import SynthCorpus
+from synth.corpus import SynthCorpus
 
 pytestmark = pytest.mark.gpu
 FPR = 0.001

@@ -11,7 +11,7 @@ import bloomsearch_b200 as bs
 from bloomsearch_b200 import _native as N
 from oracle import bloomref as pyref
 from oracle import cref
-from oracle.corpus import SynthCorpus
+from synth.corpus import SynthCorpus
 from tests.helpers import oracle_units, rand_keys
 
 pytestmark = pytest.mark.gpu

@@ -18,7 +18,7 @@ def _worker(rank, world, uid_q, res_q):
     from bloomsearch_b200 import _native as N
     from bloomsearch_b200.sharding import FileSharding, sharded_candidates, split_entries
     from oracle import cref
-    from oracle.corpus import SynthCorpus
+    from synth.corpus import SynthCorpus
     try:
         torch.cuda.set_device(rank)
         ctx = bs.Context(rank)

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 from bloomsearch_b200.sharding import FileSharding, sharded_candidates, split_entries
 from oracle import cref
-from oracle.corpus import SynthCorpus
+from synth.corpus import SynthCorpus
 
 
 def _free_port():
