@@ -385,7 +385,7 @@ def main():
                "single_caller": {"value": total_probes * e2e_steps / dt_single, "ms_per_step": dt_single / e2e_steps * 1e3},
                "what": "bsg_probe(): packed host key bytes -> H2D, hash, probe, D2H of the (block x key) matrix"}
 
-        if headline and rank == 0 and not args.no_cpu:
+        if headline and rank == 0 and world == 1 and not args.no_cpu:
             cpu, _ = cpu_probe_rate(desc, words, n_units, keys, kinds, c=c, gpu_matrix=got_m)
 
         results[wl] = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e,
