@@ -197,7 +197,7 @@ def run_reference(args, rank, world):
     sample = (f"{n_units} blocks ({wl} layout, the whole 10M-row corpus) x {len(keys)} keys per step; per block: "
               f"section CRC32C + BE decode (parseFilterSection), then TestString per key; {threads} threads; "
               f"C restatement of the Go path (no Go toolchain in the image)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "bloom probes/sec (block-level)", "value": value, "unit": "probes/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -205,10 +205,34 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "probes/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
+
+
+_JSON_FD = None
+
+
+def _capture_stdout():
+    """Libraries (NCCL prints its version banner to stdout) must not pollute the one-JSON-line
+    contract: fd 1 is pointed at stderr for the whole run and the result is written to the
+    original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -416,7 +440,7 @@ def main():
             "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],
                          "e2e": v["e2e"]} for w, v in results.items() if w != args.workload},
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
