@@ -83,7 +83,6 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int probe_kpt = 1;     // BSG_PROBE_KPT: 2 selects the experimental two-keys-per-thread kernel
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
@@ -140,7 +139,6 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(sections_configure());
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_KPT")) ctx->probe_kpt = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     *out = ctx;
     return BSG_OK;
@@ -1026,7 +1024,6 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             plan.smem_bytes = kProbeSmemPrefixBytes + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(c->n_staged, ctx->sm_count));
             plan.warps = ctx->probe_warps;
-            plan.kpt = ctx->probe_kpt;
             // time for the whole chip to stream one stage per SM at ~6.5 TB/s, capped at 2 us
             {
                 const double ns = static_cast<double>(stage_bytes) * plan.grid / 6500.0;

@@ -82,7 +82,6 @@ struct ProbeStagedPlan {
     int grid;
     int warps;            // 0 = auto
     uint32_t stagger_ns;  // delay between the prologue's stage fills (0 = none)
-    int kpt;              // keys per thread: 1 (default) or 2 (experimental lock-step variant)
 };
 cudaError_t probe_staged_configure(int max_smem_optin);
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,

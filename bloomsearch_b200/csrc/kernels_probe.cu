@@ -247,125 +247,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
     }
 }
 
-// Experimental variant (BSG_PROBE_KPT=2): two keys per thread tested in lock-step with
-// predication instead of early-exit branches — two independent dependency chains per thread
-// (ILP 2) and half the per-unit overhead per key, at the price of running both chains until
-// both probes are decided.
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
-probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
-                     const uint64_t* __restrict__ words, const uint64_t* __restrict__ hashes,
-                     const uint8_t* __restrict__ kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
-                     uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
-    uint8_t* stages = smem + kProbeSmemPrefixBytes;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t T = blockDim.x, n_warps = T >> 5, G = gridDim.x, S = n_stages;
-    if (tid == 0) {
-        for (uint32_t s = 0; s < S; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const uint32_t n_list = n_list_dev ? __ldg(n_list_dev) : n_list_host;
-    const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
-    if (warp == 0 && lane < S && lane < my_count) {
-        const uint32_t li = blockIdx.x + lane * G;
-        const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
-        const uint4 a = __ldg(hp), b = __ldg(hp + 1);
-        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
-                   li + S * G, words, (static_cast<uint64_t>(a.w) << 32) | a.z, b.x, b.y, b.z, kind_mask);
-    }
-    // keys tid (A) and tid + T (B)
-    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    uint32_t fa_off = 0, fb_off = 0;
-    const bool validA = tid < n_keys, validB = tid + T < n_keys;
-    if (validA) {
-        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * (key_base + tid));
-        const ulonglong2 x = __ldg(hp), y = __ldg(hp + 1);
-        a0 = x.x; a1 = x.y; a2 = y.x; a3 = y.y;
-        fa_off = 32u + 32u * __ldg(&kinds[key_base + tid]);
-    }
-    if (validB) {
-        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * (key_base + tid + T));
-        const ulonglong2 x = __ldg(hp), y = __ldg(hp + 1);
-        b0 = x.x; b1 = x.y; b2 = y.x; b3 = y.y;
-        fb_off = 32u + 32u * __ldg(&kinds[key_base + tid + T]);
-    }
-    const bool warpA = warp * 32 < n_keys, warpB = T + warp * 32 < n_keys;
-    uint32_t* outA = matrix32 + ((key_base + warp * 32) >> 5);
-    uint32_t* outB = matrix32 + ((key_base + T + warp * 32) >> 5);
-
-    uint32_t s = 0, ph = 0;
-    const uint8_t* st = stages;
-    for (uint32_t it = 0; it < my_count; ++it) {
-        mbar_wait(&full[s], ph);
-        const uint8_t* data = st + kProbeStageHeaderBytes;
-        // filter parameters (a dead / absent / invalid probe runs on a harmless dummy: m = 1 -> bit 0 of word 0)
-        uint32_t mA = 1, kA = 0, ihA = 0xffffffffu, ilA = 0xffffffffu, mB = 1, kB = 0, ihB = 0xffffffffu, ilB = 0xffffffffu;
-        const uint32_t* wA = reinterpret_cast<const uint32_t*>(data);
-        const uint32_t* wB = wA;
-        bool resA = false, resB = false, liveA = false, liveB = false;
-        if (validA) {
-            const uint4 f = *reinterpret_cast<const uint4*>(st + fa_off);
-            if (f.x == 0) resA = true;  // absent filter cannot disqualify
-            else { mA = f.x; kA = f.y; ihA = f.z; ilA = f.w; liveA = true;
-                   wA = reinterpret_cast<const uint32_t*>(data + *reinterpret_cast<const uint32_t*>(st + fa_off + 16)); }
-        }
-        if (validB) {
-            const uint4 f = *reinterpret_cast<const uint4*>(st + fb_off);
-            if (f.x == 0) resB = true;
-            else { mB = f.x; kB = f.y; ihB = f.z; ilB = f.w; liveB = true;
-                   wB = reinterpret_cast<const uint32_t*>(data + *reinterpret_cast<const uint32_t*>(st + fb_off + 16)); }
-        }
-        uint64_t ia2 = 0, ia3 = 0, ib2 = 0, ib3 = 0;
-        for (uint32_t i = 0; liveA | liveB; i += 4) {
-#define BSG_STEP(J, LA, LB)                                                         \
-            {                                                                        \
-                const uint32_t bitA = mod_m32((LA), mA, ihA, ilA);                    \
-                const uint32_t bitB = mod_m32((LB), mB, ihB, ilB);                    \
-                const bool pA = (wA[bitA >> 5] >> (bitA & 31u)) & 1u;                 \
-                const bool pB = (wB[bitB >> 5] >> (bitB & 31u)) & 1u;                 \
-                if (liveA) { if (!pA) liveA = false; else if (i + (J) + 1 >= kA) { liveA = false; resA = true; } } \
-                if (liveB) { if (!pB) liveB = false; else if (i + (J) + 1 >= kB) { liveB = false; resB = true; } } \
-            }
-            BSG_STEP(0, a0 + ia2, b0 + ib2)
-            BSG_STEP(1, a1 + ia3 + a3, b1 + ib3 + b3)
-            BSG_STEP(2, a0 + ia3 + 2 * a3, b0 + ib3 + 2 * b3)
-            BSG_STEP(3, a1 + ia2 + 3 * a2, b1 + ib2 + 3 * b2)
-#undef BSG_STEP
-            ia2 += 4 * a2; ia3 += 4 * a3; ib2 += 4 * b2; ib3 += 4 * b3;
-        }
-        const uint32_t bitsA = __ballot_sync(0xffffffffu, resA);
-        const uint32_t bitsB = __ballot_sync(0xffffffffu, resB);
-        if (lane == 0) {
-            const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
-            if (warpA) outA[static_cast<size_t>(unit) * row_words32] = bitsA;
-            if (warpB) outB[static_cast<size_t>(unit) * row_words32] = bitsB;
-            const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
-            if (old == n_warps - 1) {
-                done[s] = 0;
-                const uint32_t nxt = it + S;
-                if (nxt < my_count) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
-                    const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
-                    fence_proxy_async();
-                    fill_stage(const_cast<uint8_t*>(st), &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
-                               blockIdx.x + (nxt + S) * G, words, (static_cast<uint64_t>(a.w) << 32) | a.z, b.x, b.y, b.z,
-                               kind_mask);
-                }
-            }
-        }
-        st += stage_bytes;
-        if (++s == S) { s = 0; ph ^= 1u; st = stages; }
-    }
-}
-
 cudaError_t probe_staged_configure(int max_smem_optin) {
-    cudaError_t e0 = cudaFuncSetAttribute(probe_staged2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          max_smem_optin);
-    if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(probe_staged_kernel<1024, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
@@ -381,17 +263,6 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if ((n_list == 0 && !d_n_list) || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
-    if (plan.kpt == 2) {  // experimental: two keys per thread, lock-step predicated tests
-        uint32_t w2 = (n_keys + 63) / 64;
-        if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > w2) w2 = plan.warps;
-        if (w2 < 4) w2 = 4;
-        if (w2 > 32) w2 = 32;
-        if (static_cast<uint64_t>(w2) * 64 < n_keys) return cudaErrorInvalidValue;
-        probe_staged2_kernel<1024><<<dim3(plan.grid), dim3(w2 * 32), plan.smem_bytes, s>>>(
-            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            static_cast<uint32_t>(plan.n_stages), stage_bytes);
-        return cudaGetLastError();
-    }
     // one key per thread; at least 4 warps so a small batch still has some latency hiding
     uint32_t warps = (n_keys + 31) / 32;
     if (plan.warps > 0 && static_cast<uint32_t>(plan.warps) > warps) warps = plan.warps;
