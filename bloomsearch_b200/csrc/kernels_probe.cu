@@ -107,28 +107,43 @@ __device__ __forceinline__ bool test_hashes_g32(uint64_t h0, uint64_t h1, uint64
 }
 
 // TestString with precomputed base hashes on a bitset resident in shared memory, m < 2^30.
-// Compile-time unrolled in groups of four locations (i%4 pattern of location()), early exit
-// on the first clear bit exactly like BloomFilter.Test.
-__device__ __forceinline__ bool test_hashes_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
-                                                uint32_t ih, uint32_t il, uint32_t k,
+// Compile-time unrolled in groups of four locations (i%4 pattern of location()), early exit on
+// the first clear bit exactly like BloomFilter.Test.  The first four locations of a key do not
+// depend on the unit, so they are computed once per key (l0..l3) and cost no adds per unit.
+struct KeyLocs {
+    uint64_t l0, l1, l2, l3;  // location(h, 0..3) = h0, h1+h3, h0+2*h3, h1+3*h2
+    uint64_t h0, h1, h2, h3;
+};
+
+__device__ __forceinline__ bool test_hashes_s32(const KeyLocs& K, uint32_t m, uint32_t ih, uint32_t il, uint32_t k,
                                                 const uint32_t* __restrict__ w32) {
     auto test = [&](uint64_t loc) {
         const uint32_t bit = mod_m32(loc, m, ih, il);
         return (w32[bit >> 5] & (1u << (bit & 31u))) != 0u;
     };
-    uint64_t ih2 = 0, ih3 = 0;  // i*h2, i*h3 at i = multiple of 4
-    uint32_t i = 0;
-    for (; i + 4 <= k; i += 4) {  // full groups: no per-test bound check
-        if (!test(h0 + ih2)) return false;
-        if (!test(h1 + ih3 + h3)) return false;
-        if (!test(h0 + ih3 + 2 * h3)) return false;
-        if (!test(h1 + ih2 + 3 * h2)) return false;
-        ih2 += 4 * h2;
-        ih3 += 4 * h3;
+    if (k >= 4) {  // the common case (default fpr: k = 10/11)
+        if (!test(K.l0)) return false;
+        if (!test(K.l1)) return false;
+        if (!test(K.l2)) return false;
+        if (!test(K.l3)) return false;
+        uint64_t ih2 = 4 * K.h2, ih3 = 4 * K.h3;  // i*h2, i*h3 at i = 4
+        uint32_t i = 4;
+        for (; i + 4 <= k; i += 4) {  // full groups: no per-test bound check
+            if (!test(K.h0 + ih2)) return false;
+            if (!test(K.h1 + ih3 + K.h3)) return false;
+            if (!test(K.h0 + ih3 + 2 * K.h3)) return false;
+            if (!test(K.h1 + ih2 + 3 * K.h2)) return false;
+            ih2 += 4 * K.h2;
+            ih3 += 4 * K.h3;
+        }
+        if (i < k && !test(K.h0 + ih2)) return false;
+        if (i + 1 < k && !test(K.h1 + ih3 + K.h3)) return false;
+        if (i + 2 < k && !test(K.h0 + ih3 + 2 * K.h3)) return false;
+        return true;
     }
-    if (i < k && !test(h0 + ih2)) return false;
-    if (i + 1 < k && !test(h1 + ih3 + h3)) return false;
-    if (i + 2 < k && !test(h0 + ih3 + 2 * h3)) return false;
+    if (k > 0 && !test(K.l0)) return false;
+    if (k > 1 && !test(K.l1)) return false;
+    if (k > 2 && !test(K.l2)) return false;
     return true;
 }
 
@@ -194,13 +209,14 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
 
     // ---- this thread's key ----
     const bool valid = tid < n_keys;
-    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    KeyLocs K = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t f_off = 0;  // byte offset of this key's StageFilter inside a stage row
     if (valid) {
         const uint32_t q = key_base + tid;
         const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
         const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-        h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
+        K.h0 = a.x; K.h1 = a.y; K.h2 = b.x; K.h3 = b.y;
+        K.l0 = K.h0; K.l1 = K.h1 + K.h3; K.l2 = K.h0 + 2 * K.h3; K.l3 = K.h1 + 3 * K.h2;
         f_off = 32u + 32u * __ldg(&kinds[q]);
     }
     const bool warp_has_keys = warp * 32 < n_keys;
@@ -218,7 +234,7 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
                 res = true;  // absent filter cannot disqualify (query_exec.go:137-151)
             } else {
                 const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + f_off + 16);
-                res = test_hashes_s32(h0, h1, h2, h3, f.x, f.z, f.w, f.y,
+                res = test_hashes_s32(K, f.x, f.z, f.w, f.y,
                                       reinterpret_cast<const uint32_t*>(st + kProbeStageHeaderBytes + rel));
             }
         }
@@ -227,8 +243,11 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
         if (lane == 0) {
             const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
             if (warp_has_keys) out_base[static_cast<size_t>(unit) * row_words32] = bits;
-            const uint32_t old = atom_add_acq_rel_shared(&done[s], 1u);
+            // Relaxed counter: this warp's reads of the stage were consumed (they decided `bits`)
+            // before the add can issue; only the refilling thread needs the fences.
+            const uint32_t old = atom_add_relaxed_shared(&done[s], 1u);
             if (old == n_warps - 1) {
+                fence_acq_rel_cta();
                 done[s] = 0;
                 if (TRACE && tr && 2 + 2 * it < trace_slots) tr[2 + 2 * it] = globaltimer_ns();
                 const uint32_t nxt = it + S;
