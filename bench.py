@@ -434,7 +434,9 @@ def main():
                        "bitset_mb_per_gpu": r["bitset_mb"],
                        "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per step "
                              f"({r['replicas'] * r['bitset_mb']:.0f} MB > 126 MB L2): inputs larger than L2",
-                       "sharding": "by file, one shard per GPU, no data-path collective"},
+                       "sharding": "by file, one shard per GPU, no data-path collective",
+                       "timed_launches": f"K probe launches issued from C, round-robin on {args.streams} streams forked "
+                                         "from / joined to the timed stream (independent batches overlap tail-to-head)"},
             "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "clocks": r["clocks"],
             "gpu_launches": r["launches_per_step"] * args.steps,
             "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],

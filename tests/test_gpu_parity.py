@@ -592,3 +592,52 @@ def test_invalid_arguments_are_rejected_with_codes(ctx):
         ctx.build(blob, badoff, np.array([0, 2], np.uint64), np.array([0], np.uint32), None, dsc, 1)
     with pytest.raises(bs.BloomGpuError):
         ctx.hash_keys_raw(blob, badoff) if hasattr(ctx, "hash_keys_raw") else (_ for _ in ()).throw(bs.BloomGpuError(-1, "n/a"))
+
+
+# ------------------------------------------------- committed golden fixtures ---
+def test_gpu_reproduces_committed_golden_fixtures(ctx):
+    """tests/golden/bloom_golden.json (oracle-generated, see make_golden.py) and the public
+    murmur3 vectors, reproduced by the CUDA path alone: hashes, filter words, WriteTo bytes,
+    the encoded section (host codec over GPU-built filters) and its device-side decode."""
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = json.load(open(os.path.join(gdir, "bloom_golden.json")))
+    pub = json.load(open(os.path.join(gdir, "murmur3_x64_128.json")))["vectors"]
+    keys = [e["key"].encode("utf-8") for e in g["base_hashes"]] + [v["data"].encode() for v in pub]
+    h = ctx.hash_keys(keys)
+    for i, e in enumerate(g["base_hashes"]):
+        assert [int(x) for x in h[i]] == [int(x, 16) for x in e["h"]], e["key"]
+    for j, v in enumerate(pub):
+        row = h[len(g["base_hashes"]) + j]
+        assert (int(row[0]), int(row[1])) == (int(v["h1"], 16), int(v["h2"], 16)), v["data"]
+    for e in g["estimate_parameters"]:
+        assert bs.estimate_parameters(e["n"], e["p"]) == (e["m"], e["k"])
+    for e in g["filters"]:
+        entries = [x.encode() for x in e["entries"]]
+        blob, off = N.pack_keys(entries)
+        d = np.array([(e["m"], e["k"], 0)], dtype=N.DESC_DTYPE)
+        nw = (e["m"] + 63) // 64
+        w = ctx.build(blob, off, np.array([0, len(entries)], np.uint64), np.zeros(1, np.uint32), None, d, nw)
+        assert ["%016x" % int(x) for x in w] == e["words"], e["name"]
+        assert bs.BloomFilter(e["m"], e["k"], w).write_to().hex() == e["write_to_hex"], e["name"]
+    s = g["section"]
+    es_f, es_t = bs.BloomEntrySets(), bs.BloomEntrySets()
+    for x in s["field_entries"]:
+        es_f.add_field(x.encode())
+    for x in s["token_entries"]:
+        es_t.add_token(x.encode())
+    ff = es_f.build_filters(ctx, s["fpr"]).FieldBloomFilter
+    tf = es_t.build_filters(ctx, s["fpr"]).TokenBloomFilter
+    raw = bytes([3])
+    for f in (ff, tf):
+        body = f.write_to()
+        raw += len(body).to_bytes(4, "little") + body
+    raw += cref.crc32c(raw).to_bytes(4, "little")  # CRC by the checker; the framing is the product's
+    assert raw.hex() == s["hex"]
+    corpus, status = bs.Corpus.from_sections(ctx, np.frombuffer(bytes.fromhex(s["hex"]), dtype=np.uint8),
+                                             np.array([0, len(s["hex"]) // 2], np.uint64))
+    assert status[0] == 0
+    m, _ = corpus.probe([b"service", b"nope", b"auth", b"zzz"], [0, 0, 1, 1])
+    assert list(bs.unpack_matrix(m, 4)[0]) == [True, False, True, False]
+    corpus.close()
