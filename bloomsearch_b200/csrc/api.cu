@@ -515,6 +515,101 @@ extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_
     return rc;
 }
 
+// Fused field::token build.  Same contract as bsg_build, but entry i of a group
+// is (pair_path[i], pair_token[i]) into one string table and its key is path + "::" + token.
+extern "C" int bsg_build_fieldtokens(bsg_ctx* ctx, const uint8_t* strings, const uint64_t* str_off, uint64_t n_strings,
+                                     const uint32_t* pair_path, const uint32_t* pair_token, uint64_t n_pairs,
+                                     const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_filter,
+                                     const uint32_t* group_filter2, const bsg_filter_desc* desc, uint32_t n_filters,
+                                     uint64_t* out_words, uint64_t n_words) {
+    if (!ctx || !str_off || !desc || !out_words || (n_pairs && (!pair_path || !pair_token)) ||
+        (n_groups && (!group_begin || !group_filter)))
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t nbytes = n_strings ? str_off[n_strings] : 0;
+    if (nbytes && !strings) return fail(BSG_ERR_INVALID, "strings is NULL");
+    {
+        const uint64_t bad = first_bad_offset(str_off, n_strings);
+        if (bad != n_strings) return fail(BSG_ERR_INVALID, "str_off not monotone at %llu", (unsigned long long)bad);
+    }
+    for (uint64_t i = 0; i < n_pairs; ++i)
+        if (pair_path[i] >= n_strings || pair_token[i] >= n_strings)
+            return fail(BSG_ERR_INVALID, "pair %llu: string index out of range", (unsigned long long)i);
+    std::vector<BuildFilter> bf(n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+        if (desc[f].m == 0) return fail(BSG_ERR_INVALID, "filter %u: m == 0", f);
+        int rc = validate_filter(desc[f], n_words, "filter", f);
+        if (rc) return rc;
+        bf[f] = BuildFilter{desc[f].word_off, desc[f].m, reciprocal(desc[f].m), static_cast<uint32_t>(desc[f].k),
+                            static_cast<uint32_t>(words_for(desc[f].m))};
+    }
+    constexpr uint64_t kSplit = 16384;
+    std::vector<uint64_t> gbe;
+    std::vector<uint32_t> gf, gf2;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const uint64_t b = group_begin[g], e = group_begin[g + 1];
+        if (e < b || e > n_pairs) return fail(BSG_ERR_INVALID, "group %u: pair range invalid", g);
+        if (group_filter[g] >= n_filters) return fail(BSG_ERR_INVALID, "group %u: filter id out of range", g);
+        if (group_filter2 && group_filter2[g] != BSG_NO_FILTER && group_filter2[g] >= n_filters)
+            return fail(BSG_ERR_INVALID, "group %u: secondary filter id out of range", g);
+        for (uint64_t s0 = b; s0 < e; s0 += kSplit) {
+            gbe.push_back(s0);
+            gf.push_back(group_filter[g]);
+            if (group_filter2) gf2.push_back(group_filter2[g]);
+        }
+    }
+    gbe.push_back(n_groups ? group_begin[n_groups] : 0);
+    const uint32_t n_sub = static_cast<uint32_t>(gf.size());
+    const uint32_t cap_limit = static_cast<uint32_t>(std::min<int>(ctx->max_smem_optin, 100 * 1024));
+    uint32_t smem_cap = 0;
+    for (uint32_t g = 0; g < n_sub; ++g) {
+        const uint64_t bytes = static_cast<uint64_t>(bf[gf[g]].nwords) * 8;
+        if (bytes <= cap_limit) smem_cap = std::max<uint32_t>(smem_cap, static_cast<uint32_t>((bytes + 15) & ~15ull));
+    }
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    DevBuf<uint8_t> d_str;
+    DevBuf<uint64_t> d_off, d_gb, d_out;
+    DevBuf<uint32_t> d_pp, d_pt, d_gf, d_gf2;
+    DevBuf<BuildFilter> d_bf;
+    int rc = BSG_OK;
+    do {
+        if (d_str.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_strings + 1) != cudaSuccess ||
+            d_pp.alloc(n_pairs) != cudaSuccess || d_pt.alloc(n_pairs) != cudaSuccess ||
+            d_gb.alloc(gbe.size()) != cudaSuccess || d_out.alloc(n_words) != cudaSuccess ||
+            d_gf.alloc(n_sub) != cudaSuccess || d_bf.alloc(n_filters) != cudaSuccess ||
+            (group_filter2 && d_gf2.alloc(n_sub) != cudaSuccess)) { rc = fail(BSG_ERR_NOMEM, "device alloc"); break; }
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+        cudaError_t e = cudaMemsetAsync(d_str.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_out.p, 0, std::max<uint64_t>(n_words, 1) * 8, s);
+        if (e == cudaSuccess) e = upload(ctx, d_str.p, strings, nbytes, s);
+        if (e == cudaSuccess) e = upload(ctx, d_off.p, str_off, (n_strings + 1) * 8, s);
+        if (e == cudaSuccess) e = upload(ctx, d_pp.p, pair_path, n_pairs * 4, s);
+        if (e == cudaSuccess) e = upload(ctx, d_pt.p, pair_token, n_pairs * 4, s);
+        if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gb.p, gbe.data(), gbe.size() * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_sub) e = cudaMemcpyAsync(d_gf.p, gf.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_sub && group_filter2)
+            e = cudaMemcpyAsync(d_gf2.p, gf2.data(), n_sub * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n_filters)
+            e = cudaMemcpyAsync(d_bf.p, bf.data(), n_filters * sizeof(BuildFilter), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess)
+            e = launch_build_ft(d_str.p, d_off.p, d_pp.p, d_pt.p, d_gb.p, n_sub, d_gf.p, group_filter2 ? d_gf2.p : nullptr,
+                                d_bf.p, d_out.p, smem_cap, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess && n_words) {
+            if (n_words * 8 < kStageThreshold) {
+                e = cudaMemcpyAsync(out_words, d_out.p, n_words * 8, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            } else {
+                e = staged_copy(ctx, d_out.p, out_words, n_words * 8, false);
+            }
+        }
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_build_fieldtokens: %s", cudaGetErrorString(e));
+    } while (0);
+    pool_put(ctx, s);
+    return rc;
+}
+
 // ------------------------------------------------------------------ corpus ---
 struct bsg_corpus {
     int device = 0;

@@ -79,10 +79,54 @@ struct WordReader {
     }
 };
 
-// Two-part reader: bytes of `a` (len la) followed by bytes of `b` (len lb),
-// presented as one little-endian word stream.  Used for field + "::" + token
-// hashing without materialising the joined key (tokenizer.go:508-511).
-// (Declared here; used by the fused field-token build path.)
+// Byte-stream murmur: segments of bytes are fed one after another and mixed 16 bytes at a
+// time — used to hash field + "::" + token without materialising the joined key
+// (makeFieldTokenKey, tokenizer.go:508-511; addFieldToken, ingest.go:95-102).
+struct StreamHasher {
+    uint64_t h1 = 0, h2 = 0;   // running murmur state (seed 0)
+    uint64_t w[2] = {0, 0};    // pending (not yet mixed) bytes, little-endian
+    uint32_t nb = 0;           // number of pending bytes, 0..15
+    uint64_t total = 0;        // bytes fed so far
+
+    // append the low n (1..8) bytes of v at byte position nb of the pending 16-byte block
+    __device__ __forceinline__ void feed(uint64_t v, uint32_t n) {
+        v &= low_bytes_mask(n);
+        uint64_t spill = 0;  // bytes that fall beyond the 16-byte block (at most 7)
+        if (nb < 8u) {
+            const uint32_t sh = nb * 8u;  // 0..56
+            w[0] |= v << sh;
+            if (sh) w[1] |= v >> (64u - sh);  // zero when everything fitted: v's high bytes are zero
+        } else {
+            const uint32_t sh = (nb - 8u) * 8u;  // 0..56
+            w[1] |= v << sh;
+            if (sh) spill = v >> (64u - sh);
+        }
+        nb += n;
+        total += n;
+        if (nb >= 16u) {
+            bmix(h1, h2, w[0], w[1]);
+            w[0] = spill;
+            w[1] = 0;
+            nb -= 16u;
+        }
+    }
+    __device__ __forceinline__ void feed_bytes(const uint8_t* p, uint32_t len) {
+        if (len == 0) return;
+        WordReader rd(p);
+        uint32_t left = len;
+        while (left >= 8u) { feed(rd.next(), 8u); left -= 8u; }
+        if (left) feed(rd.next(), left);
+    }
+    // baseHashes of everything fed so far: murmur(data) and murmur(data || 0x01)
+    __device__ __forceinline__ void finish(uint64_t h[4]) const {
+        finalize(h1, h2, w[0], w[1], total, h[0], h[1]);
+        uint64_t k1 = w[0], k2 = w[1];
+        uint64_t g1 = h1, g2 = h2;
+        if (nb < 8u) k1 |= 1ull << (8u * nb); else k2 |= 1ull << (8u * (nb - 8u));
+        if (nb == 15u) { bmix(g1, g2, k1, k2); k1 = 0; k2 = 0; }
+        finalize(g1, g2, k1, k2, total + 1, h[2], h[3]);
+    }
+};
 
 // baseHashes(key): h[0..1] = murmur(key), h[2..3] = murmur(key || 0x01).
 __device__ __forceinline__ void base_hashes(const uint8_t* key, uint32_t len, uint64_t h[4]) {

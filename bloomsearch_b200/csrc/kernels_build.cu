@@ -84,11 +84,86 @@ build_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_
     }
 }
 
+// Fused field::token build (§8 f.2): entry i of a group is the pair (path_of[i], token_of[i]) of
+// indexes into one string table; its key is strings[path] + "::" + strings[token]
+// (makeFieldTokenKey, tokenizer.go:508-511), hashed as a byte stream without materialising it.
+__global__ void __launch_bounds__(256)
+build_ft_kernel(const uint8_t* __restrict__ strings, const uint64_t* __restrict__ str_off,
+                const uint32_t* __restrict__ pair_path, const uint32_t* __restrict__ pair_token,
+                const uint64_t* __restrict__ group_begin, const uint32_t* __restrict__ group_filter,
+                const uint32_t* __restrict__ group_filter2, const BuildFilter* __restrict__ filters,
+                uint64_t* __restrict__ out_words, uint32_t smem_cap_words64) {
+    extern __shared__ __align__(16) uint64_t s_words[];
+    const uint32_t g = blockIdx.x;
+    const BuildFilter f1 = filters[group_filter[g]];
+    const uint32_t f2_id = group_filter2 ? group_filter2[g] : BSG_NO_FILTER;
+    const bool has2 = f2_id != BSG_NO_FILTER;
+    BuildFilter f2 = {0, 1, 0, 0, 0};
+    if (has2) f2 = filters[f2_id];
+    const uint64_t kb = group_begin[g], ke = group_begin[g + 1];
+    const bool staged = f1.nwords <= smem_cap_words64;
+    if (staged) {
+        for (uint32_t w = threadIdx.x; w < f1.nwords; w += blockDim.x) s_words[w] = 0;
+        __syncthreads();
+    }
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(s_words);
+    unsigned long long* g1 = reinterpret_cast<unsigned long long*>(out_words + f1.word_off);
+    unsigned long long* g2 = reinterpret_cast<unsigned long long*>(out_words + f2.word_off);
+    for (uint64_t i = kb + threadIdx.x; i < ke; i += blockDim.x) {
+        const uint32_t pi = __ldg(&pair_path[i]), ti = __ldg(&pair_token[i]);
+        const uint64_t pb = __ldg(&str_off[pi]), pe = __ldg(&str_off[pi + 1]);
+        const uint64_t tb = __ldg(&str_off[ti]), te = __ldg(&str_off[ti + 1]);
+        StreamHasher sh;
+        sh.feed_bytes(strings + pb, static_cast<uint32_t>(pe - pb));
+        sh.feed(0x3a3aull, 2);  // "::"
+        sh.feed_bytes(strings + tb, static_cast<uint32_t>(te - tb));
+        uint64_t h[4];
+        sh.finish(h);
+        if (staged) {
+            scatter_locations(h, f1.m, f1.inv, f1.k, [&](uint64_t bit) {
+                atomicOr(&s32[static_cast<uint32_t>(bit >> 5)], 1u << (static_cast<uint32_t>(bit) & 31u));
+            });
+        } else {
+            scatter_locations(h, f1.m, f1.inv, f1.k, [&](uint64_t bit) {
+                atomicOr(&g1[bit >> 6], 1ull << (static_cast<uint32_t>(bit) & 63u));
+            });
+        }
+        if (has2) {
+            scatter_locations(h, f2.m, f2.inv, f2.k, [&](uint64_t bit) {
+                atomicOr(&g2[bit >> 6], 1ull << (static_cast<uint32_t>(bit) & 63u));
+            });
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < f1.nwords; w += blockDim.x) {
+            const uint64_t v = s_words[w];
+            if (v) atomicOr(&g1[w], static_cast<unsigned long long>(v));
+        }
+    }
+}
+
 static int g_build_max_smem = 48 * 1024;
 
 cudaError_t build_configure(int max_smem_optin) {
     g_build_max_smem = max_smem_optin;
+    cudaError_t e = cudaFuncSetAttribute(build_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+}
+
+cudaError_t launch_build_ft(const uint8_t* d_strings, const uint64_t* d_str_off, const uint32_t* d_pair_path,
+                            const uint32_t* d_pair_token, const uint64_t* d_group_begin, uint32_t n_groups,
+                            const uint32_t* d_group_filter, const uint32_t* d_group_filter2,
+                            const BuildFilter* d_filters, uint64_t* d_out_words, uint32_t smem_cap_bytes,
+                            cudaStream_t s) {
+    if (n_groups == 0) return cudaSuccess;
+    if (smem_cap_bytes > static_cast<uint32_t>(g_build_max_smem)) smem_cap_bytes = g_build_max_smem;
+    smem_cap_bytes &= ~15u;
+    build_ft_kernel<<<n_groups, 256, smem_cap_bytes, s>>>(d_strings, d_str_off, d_pair_path, d_pair_token,
+                                                          d_group_begin, d_group_filter, d_group_filter2, d_filters,
+                                                          d_out_words, smem_cap_bytes / 8);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_build(const uint8_t* d_keys, const uint64_t* d_key_off, const uint64_t* d_group_begin,

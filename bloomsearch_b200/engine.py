@@ -88,6 +88,25 @@ class Context:
                                   N.ptr(out), int(n_words)))
         return out[:int(n_words)]
 
+    def build_fieldtokens(self, strings_blob: np.ndarray, str_off: np.ndarray, pair_path: np.ndarray,
+                          pair_token: np.ndarray, group_begin: np.ndarray, group_filter: np.ndarray,
+                          group_filter2: Optional[np.ndarray], desc: np.ndarray, n_words: int) -> np.ndarray:
+        """bsg_build_fieldtokens: entries are (path, token) index pairs into one string table; the
+        key path + "::" + token is hashed on the device without being materialised."""
+        desc = np.ascontiguousarray(desc, dtype=N.DESC_DTYPE)
+        str_off = np.ascontiguousarray(str_off, dtype=np.uint64)
+        pair_path = np.ascontiguousarray(pair_path, dtype=np.uint32)
+        pair_token = np.ascontiguousarray(pair_token, dtype=np.uint32)
+        group_begin = np.ascontiguousarray(group_begin, dtype=np.uint64)
+        group_filter = np.ascontiguousarray(group_filter, dtype=np.uint32)
+        gf2 = None if group_filter2 is None else np.ascontiguousarray(group_filter2, dtype=np.uint32)
+        out = np.zeros(max(int(n_words), 1), dtype=np.uint64)
+        N.check(N.lib().bsg_build_fieldtokens(self._h, N.ptr(strings_blob), N.ptr(str_off), len(str_off) - 1,
+                                              N.ptr(pair_path), N.ptr(pair_token), len(pair_path), N.ptr(group_begin),
+                                              len(group_filter), N.ptr(group_filter), N.ptr(gf2), N.ptr(desc), len(desc),
+                                              N.ptr(out), int(n_words)))
+        return out[:int(n_words)]
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -120,6 +120,17 @@ int bsg_build(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64
               const uint32_t *group_filter2, const bsg_filter_desc *desc, uint32_t n_filters,
               uint64_t *out_words, uint64_t n_words);
 
+/* Fused field::token build (ingest.go:95-102 addFieldToken + tokenizer.go:508-511): same contract
+ * as bsg_build, but entry i of a group is the pair (pair_path[i], pair_token[i]) of indexes into ONE
+ * string table (strings / str_off, n_strings entries) and its key is
+ * strings[path] + "::" + strings[token], hashed on the device as a byte stream — the host never
+ * materialises (or ships over PCIe) the joined keys. */
+int bsg_build_fieldtokens(bsg_ctx *ctx, const uint8_t *strings, const uint64_t *str_off, uint64_t n_strings,
+                          const uint32_t *pair_path, const uint32_t *pair_token, uint64_t n_pairs,
+                          const uint64_t *group_begin, uint32_t n_groups, const uint32_t *group_filter,
+                          const uint32_t *group_filter2, const bsg_filter_desc *desc, uint32_t n_filters,
+                          uint64_t *out_words, uint64_t n_words);
+
 /* ---- corpus residency ------------------------------------------------------ *
  * A corpus is n_units "units" (data blocks, or files for the file-level stage),
  * each with up to three filters: desc[3*u + kind].  The words are copied to HBM

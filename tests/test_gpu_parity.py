@@ -641,3 +641,42 @@ def test_gpu_reproduces_committed_golden_fixtures(ctx):
     m, _ = corpus.probe([b"service", b"nope", b"auth", b"zzz"], [0, 0, 1, 1])
     assert list(bs.unpack_matrix(m, 4)[0]) == [True, False, True, False]
     corpus.close()
+
+
+# --------------------------------------------- fused field::token build (f.2) ---
+def test_build_fieldtokens_equals_joined_keys(ctx):
+    """bsg_build_fieldtokens(path, token pairs) == bsg_build / oracle on the materialised
+    path + "::" + token keys (makeFieldTokenKey, tokenizer.go:508-511), all length / alignment mixes."""
+    rng = random.Random(91)
+    paths = [b"", b"a", b"level", b"nested.region", b"a.very.long.path.name.with.many.parts", b"x" * 15, b"y" * 16, b"z" * 17]
+    tokens = [b"", b"1", b"info", b"region-7", b"0123456789abcde", b"0123456789abcdef", b"t" * 33] + \
+             [bytes(rng.randrange(256) for _ in range(rng.randint(0, 40))) for _ in range(200)]
+    strings = paths + tokens
+    blob, off = N.pack_keys(strings)
+    groups = []
+    for g in range(5):
+        n = [0, 1, 7, 300, 2000][g]
+        groups.append([(rng.randrange(len(paths)), len(paths) + rng.randrange(len(tokens))) for _ in range(n)])
+    pair_path = np.array([p for g in groups for p, _ in g], dtype=np.uint32)
+    pair_token = np.array([t for g in groups for _, t in g], dtype=np.uint32)
+    gb = np.cumsum([0] + [len(g) for g in groups]).astype(np.uint64)
+    desc, wo = [], 0
+    for g in groups:
+        m, k = bs.estimate_parameters(max(len(set(g)), 1), 0.001)
+        desc.append((m, k, wo))
+        wo += (m + 63) // 64
+    m, k = bs.estimate_parameters(sum(len(g) for g in groups), 0.001)   # a shared secondary (file-level) filter
+    desc.append((m, k, wo))
+    wo += (m + 63) // 64
+    d = np.array(desc, dtype=N.DESC_DTYPE)
+    gf = np.arange(len(groups), dtype=np.uint32)
+    gf2 = np.full(len(groups), len(groups), dtype=np.uint32)
+    got = ctx.build_fieldtokens(blob, off, pair_path, pair_token, gb, gf, gf2, d, wo)
+    joined = [strings[p] + b"::" + strings[t] for g in groups for p, t in g]
+    jb, jo = N.pack_keys(joined)
+    want = cref.build_filters(jb, jo, gb, gf, gf2, d, wo)
+    assert np.array_equal(got, want)
+    assert np.array_equal(ctx.build(jb, jo, gb, gf, gf2, d, wo), want)
+    with pytest.raises(bs.BloomGpuError):
+        ctx.build_fieldtokens(blob, off, np.array([len(strings)], np.uint32), np.array([0], np.uint32),
+                              np.array([0, 1], np.uint64), np.zeros(1, np.uint32), None, d[:1], wo)
