@@ -211,3 +211,54 @@ func (c *Context) Probe(cp *Corpus, keys PackedKeys, kinds []Kind, prog []Op, wa
 	runtime.KeepAlive(keys)
 	return mask[:(cp.Units+63)/64], matrix, check(rc)
 }
+
+// SetParents records, for every unit (block) of cp, the index of its file in the files corpus;
+// ProbeHierarchical then runs both pruning stages of Query (query_exec.go:399-406 and :572-615)
+// in one call, compacting the surviving blocks on the device between them.
+func (c *Context) SetParents(cp *Corpus, parent []uint32, nParentUnits uint64) error {
+	if len(parent) == 0 {
+		return nil
+	}
+	return check(C.bsg_corpus_set_parents(c.h, cp.h, (*C.uint32_t)(unsafe.Pointer(&parent[0])), C.uint64_t(len(parent)),
+		C.uint64_t(nParentUnits)))
+}
+
+func (c *Context) ProbeHierarchical(files, blocks *Corpus, keys PackedKeys, kinds []Kind, prog []Op) (fileMask, blockMask []uint64, err error) {
+	n := uint32(len(keys.Off) - 1)
+	fileMask = make([]uint64, (files.Units+63)/64+1)
+	blockMask = make([]uint64, (blocks.Units+63)/64+1)
+	var pp *C.bsg_expr_op
+	if len(prog) > 0 {
+		pp = (*C.bsg_expr_op)(unsafe.Pointer(&prog[0]))
+	}
+	var kp *C.uint8_t
+	if n > 0 {
+		kp = (*C.uint8_t)(unsafe.Pointer(&kinds[0]))
+	}
+	rc := C.bsg_probe_hierarchical(c.h, files.h, blocks.h, (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0])),
+		(*C.uint64_t)(unsafe.Pointer(&keys.Off[0])), C.uint32_t(n), kp, pp, C.uint32_t(len(prog)),
+		(*C.uint64_t)(unsafe.Pointer(&fileMask[0])), (*C.uint64_t)(unsafe.Pointer(&blockMask[0])))
+	runtime.KeepAlive(keys)
+	return fileMask[:(files.Units+63)/64], blockMask[:(blocks.Units+63)/64], check(rc)
+}
+
+// BuildFieldTokens is bsg_build_fieldtokens: field::token entries as (path, token) index pairs into
+// one string table; the joined key is hashed on the GPU and never materialised (ingest.go:95-102).
+func (c *Context) BuildFieldTokens(strings PackedKeys, pairPath, pairToken []uint32, groupBegin []uint64,
+	groupFilter, groupFilter2 []uint32, desc []FilterDesc, nWords uint64) ([]uint64, error) {
+	out := make([]uint64, nWords+1)
+	if len(groupFilter) == 0 || len(desc) == 0 || len(pairPath) == 0 {
+		return out[:nWords], nil
+	}
+	var gf2 *C.uint32_t
+	if groupFilter2 != nil {
+		gf2 = (*C.uint32_t)(unsafe.Pointer(&groupFilter2[0]))
+	}
+	rc := C.bsg_build_fieldtokens(c.h, (*C.uint8_t)(unsafe.Pointer(&strings.Bytes[0])), (*C.uint64_t)(unsafe.Pointer(&strings.Off[0])),
+		C.uint64_t(len(strings.Off)-1), (*C.uint32_t)(unsafe.Pointer(&pairPath[0])), (*C.uint32_t)(unsafe.Pointer(&pairToken[0])),
+		C.uint64_t(len(pairPath)), (*C.uint64_t)(unsafe.Pointer(&groupBegin[0])), C.uint32_t(len(groupFilter)),
+		(*C.uint32_t)(unsafe.Pointer(&groupFilter[0])), gf2, (*C.bsg_filter_desc)(unsafe.Pointer(&desc[0])),
+		C.uint32_t(len(desc)), (*C.uint64_t)(unsafe.Pointer(&out[0])), C.uint64_t(nWords))
+	runtime.KeepAlive(strings)
+	return out[:nWords], check(rc)
+}
