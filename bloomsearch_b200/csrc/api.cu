@@ -83,7 +83,6 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int probe_steal = 1;   // BSG_PROBE_STEAL=0 disables the dynamically claimed tail (static striding)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
@@ -140,7 +139,6 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(sections_configure());
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_STEAL")) ctx->probe_steal = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     *out = ctx;
     return BSG_OK;
@@ -895,7 +893,6 @@ struct bsg_query {
     StageRow* d_rows = nullptr;
     size_t cap_rows = 0;
     uint32_t* d_n_rows = nullptr;
-    uint32_t* d_steal = nullptr;  // claim counter of the staged kernel's dynamically scheduled tail
     // output shape the pad words were last zeroed for (kernels never write pad words)
     uint64_t zeroed_units = ~0ull;
     uint32_t zeroed_row_words32 = ~0u, zeroed_groups = ~0u;
@@ -927,7 +924,6 @@ extern "C" void bsg_query_free(bsg_query* q) {
     if (q->h_pin) cudaFreeHost(q->h_pin);
     cudaFree(q->d_rows);
     cudaFree(q->d_n_rows);
-    cudaFree(q->d_steal);
     delete q;
 }
 
@@ -1139,12 +1135,11 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
                 rows = q->d_rows;
                 d_n_rows = q->d_n_rows;
             }
-            if (!q->d_steal && ctx->probe_steal) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_steal), 4));
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
                 CUDA_TRY(launch_probe_staged(plan, rows, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
                                              q->kind_mask, q->d_matrix32, q->row_words32, s, ctx->d_trace,
-                                             ctx->trace_slots, d_n_rows, ctx->probe_steal ? q->d_steal : nullptr));
+                                             ctx->trace_slots, d_n_rows));
                 ++launches;
             }
         } else if (c->n_staged) {

@@ -88,8 +88,7 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
                                 uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
                                 uint32_t row_words32, cudaStream_t s, uint64_t* d_trace = nullptr,
-                                uint32_t trace_slots = 0, const uint32_t* d_n_list = nullptr,
-                                uint32_t* d_steal = nullptr);
+                                uint32_t trace_slots = 0, const uint32_t* d_n_list = nullptr);
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
                                 uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s,

@@ -148,27 +148,20 @@ __device__ __forceinline__ bool test_hashes_s32(const KeyLocs& K, uint32_t m, ui
 }
 
 // The staged probe.  All warps of the CTA work on the same resident unit; thread t owns key
-// key_base + t for the whole kernel (hashes + its first four locations in registers) and tests it
-// against every unit this CTA streams through its shared-memory ring.  No producer warp: the warp
-// whose release frees a stage refills it at once (fill_stage), using the next unit's row head
-// that travelled in with the current unit.
-// Unit schedule: CTA b statically owns rows b, b+G, ... for the first floor(n/G) rounds; the
-// remaining n mod G rows are CLAIMED from a global counter by whichever CTAs get there first
-// (steal != nullptr), so CTAs whose first stage arrived late do not also carry an extra unit.
-// A stage whose claim finds no row left is completed with an END marker.
-// (Measured alternatives — per-lane state machines that decouple lanes across units or across
-// several keys per lane, lock-step two-keys-per-thread — executed fewer iterations but more
-// instructions and lost; see DESIGN.md.)
-constexpr uint32_t kEndMarker = 0xffffffffu;
-
+// key_base + t for the whole kernel (hashes in registers) and tests it against every unit this
+// CTA streams through its shared-memory ring.  No producer warp: the warp whose release frees
+// a stage refills it at once (fill_stage), using the next unit's row head that travelled in
+// with the current unit.  (Measured alternatives — per-lane state machines that decouple lanes
+// across units or across several keys per lane — executed fewer iterations but 2.5x more
+// instructions per iteration and lost; see DESIGN.md.)
 template <int MAXT, bool TRACE>
 __global__ void __launch_bounds__(MAXT, 1)
 probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
                     const uint64_t* __restrict__ words,
                     const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ kinds, uint32_t key_base,
                     uint32_t n_keys, uint32_t kind_mask, uint32_t* __restrict__ matrix32, uint32_t row_words32,
-                    uint32_t n_stages, uint32_t stage_bytes, uint32_t stagger_ns, uint32_t* __restrict__ steal,
-                    uint64_t* __restrict__ trace, uint32_t trace_slots) {
+                    uint32_t n_stages, uint32_t stage_bytes, uint32_t stagger_ns, uint64_t* __restrict__ trace,
+                    uint32_t trace_slots) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + kProbeMaxStages * sizeof(uint64_t));
@@ -196,50 +189,22 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
 
     // hierarchical probes compact the surviving units on the device: their count lives there too
     const uint32_t n_list = n_list_dev ? __ldg(n_list_dev) : n_list_host;
-    // rounds every CTA owns statically; rows >= n_static * G are claimed dynamically (or, without
-    // a steal counter, strided like the rest)
-    const uint32_t n_static = steal ? n_list / G
-                                    : (n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0);
-    const uint32_t dyn_base = n_static * G;
+    const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
-    // Fills stage `st` (ring slot s) with this CTA's `it`-th unit, or completes it with the END marker.
-    // Static rounds use the row head passed in (prefetched); dynamic ones claim a row and load its head.
-    auto fill_it = [&](uint8_t* st, uint32_t s, uint32_t it, bool have_head, uint64_t head_wb, uint32_t hn0,
-                       uint32_t hn1, uint32_t hn2) {
-        if (it < n_static) {
-            const uint32_t li = blockIdx.x + it * G;
-            if (!have_head) {
-                const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
-                const uint4 a = __ldg(hp), b = __ldg(hp + 1);
-                head_wb = (static_cast<uint64_t>(a.w) << 32) | a.z;
-                hn0 = b.x; hn1 = b.y; hn2 = b.z;
-            }
-            fill_stage(st, &full[s], stab, li, it + S < n_static, li + S * G, words, head_wb, hn0, hn1, hn2, kind_mask);
-            return;
-        }
-        uint32_t li = kEndMarker;
-        if (steal) {
-            const uint32_t r = dyn_base + atomicAdd(steal, 1u);
-            if (r < n_list) li = r;
-        }
-        if (li == kEndMarker) {  // nothing left: complete the phase with an END marker in the header
-            *reinterpret_cast<uint32_t*>(st) = kEndMarker;
-            mbar_arrive(&full[s]);
-            return;
-        }
+    // ---- prologue: lane l of warp 0 fills stage l with this CTA's l-th unit.  stagger_ns > 0
+    //      delays fill l by l*stagger_ns (experiment knob BSG_PROBE_STAGGER; measured: staggering
+    //      does not help, the default is 0). ----
+    if (warp == 0 && lane < S && lane < my_count) {
+        const uint64_t t_start = globaltimer_ns();
+        const uint32_t li = blockIdx.x + lane * G;
         const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
         const uint4 a = __ldg(hp), b = __ldg(hp + 1);
-        fill_stage(st, &full[s], stab, li, false, 0, words, (static_cast<uint64_t>(a.w) << 32) | a.z, b.x, b.y, b.z,
-                   kind_mask);
-    };
-
-    // ---- prologue: lane l of warp 0 fills stage l.  stagger_ns > 0 delays fill l by l*stagger_ns
-    //      (experiment knob BSG_PROBE_STAGGER; measured: no gain, default 0). ----
-    if (warp == 0 && lane < S) {
-        const uint64_t t_go = globaltimer_ns() + static_cast<uint64_t>(lane) * stagger_ns;
+        const uint64_t word_base = (static_cast<uint64_t>(a.w) << 32) | a.z;
+        const uint64_t t_go = t_start + static_cast<uint64_t>(lane) * stagger_ns;
         while (stagger_ns && globaltimer_ns() < t_go) {
         }
-        fill_it(stages + static_cast<size_t>(lane) * stage_bytes, lane, lane, false, 0, 0, 0, 0);
+        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
+                   li + S * G, words, word_base, b.x, b.y, b.z, kind_mask);
     }
 
     // ---- this thread's key ----
@@ -258,11 +223,9 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
     uint32_t* out_base = matrix32 + ((key_base + warp * 32) >> 5);
 
     uint32_t s = 0, ph = 0;
-    uint8_t* st = stages;
-    for (uint32_t it = 0;; ++it) {
+    const uint8_t* st = stages;
+    for (uint32_t it = 0; it < my_count; ++it) {
         mbar_wait(&full[s], ph);
-        const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
-        if (unit == kEndMarker) break;  // uniform: every warp sees the same stage sequence
         if (TRACE && tr && tid == 0 && 1 + 2 * it < trace_slots) tr[1 + 2 * it] = globaltimer_ns();
         bool res = false;
         if (valid) {
@@ -276,8 +239,9 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
             }
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, res);
-        // ---- release: the last warp out refills this stage with the CTA's unit it + S ----
+        // ---- release: the last warp out refills this stage with unit it + S ----
         if (lane == 0) {
+            const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
             if (warp_has_keys) out_base[static_cast<size_t>(unit) * row_words32] = bits;
             // Relaxed counter: this warp's reads of the stage were consumed (they decided `bits`)
             // before the add can issue; only the refilling thread needs the fences.
@@ -287,11 +251,14 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
                 done[s] = 0;
                 if (TRACE && tr && 2 + 2 * it < trace_slots) tr[2 + 2 * it] = globaltimer_ns();
                 const uint32_t nxt = it + S;
-                const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
-                const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
-                fence_proxy_async();
-                // the prefetched head is valid exactly when this stage was filled with has_next
-                fill_it(st, s, nxt, nxt < n_static, (static_cast<uint64_t>(a.w) << 32) | a.z, b.x, b.y, b.z);
+                if (nxt < my_count) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
+                    const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
+                    const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
+                    fence_proxy_async();
+                    fill_stage(const_cast<uint8_t*>(st), &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
+                               blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask);
+                }
             }
         }
         st += stage_bytes;
@@ -311,12 +278,8 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,
                                 uint32_t key_base, uint32_t n_keys, uint32_t kind_mask, uint32_t* d_matrix32,
                                 uint32_t row_words32, cudaStream_t s, uint64_t* d_trace, uint32_t trace_slots,
-                                const uint32_t* d_n_list, uint32_t* d_steal) {
+                                const uint32_t* d_n_list) {
     if ((n_list == 0 && !d_n_list) || n_keys == 0) return cudaSuccess;
-    if (d_steal) {  // the claim counter starts at 0 for every launch
-        cudaError_t e = cudaMemsetAsync(d_steal, 0, 4, s);
-        if (e != cudaSuccess) return e;
-    }
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
     // one key per thread; at least 4 warps so a small batch still has some latency hiding
@@ -327,11 +290,11 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
     if (d_trace)
         probe_staged_kernel<1024, true><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
             d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_steal, d_trace, trace_slots);
+            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_trace, trace_slots);
     else
         probe_staged_kernel<1024, false><<<dim3(plan.grid), dim3(warps * 32), plan.smem_bytes, s>>>(
             d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, d_steal, nullptr, 0);
+            static_cast<uint32_t>(plan.n_stages), stage_bytes, plan.stagger_ns, nullptr, 0);
     return cudaGetLastError();
 }
 
