@@ -60,7 +60,7 @@ _lib = None
 # every symbol include/bloomgpu.h declares (tests check the .so exports them all)
 ABI_SYMBOLS = [
     "bsg_abi_version", "bsg_strerror", "bsg_last_error", "bsg_create", "bsg_destroy", "bsg_set_stream",
-    "bsg_synchronize", "bsg_device_info", "bsg_estimate", "bsg_hash_keys", "bsg_build", "bsg_build_fieldtokens", "bsg_corpus_load",
+    "bsg_synchronize", "bsg_device_info", "bsg_estimate", "bsg_hash_keys", "bsg_build", "bsg_build_fieldtokens", "bsg_count_distinct", "bsg_corpus_load",
     "bsg_corpus_load_sections", "bsg_corpus_free", "bsg_corpus_units", "bsg_corpus_bitset_bytes",
     "bsg_corpus_unit_desc", "bsg_corpus_set_parents", "bsg_probe_hierarchical", "bsg_probe", "bsg_query_create", "bsg_query_run", "bsg_query_fetch", "bsg_query_free",
     "bsg_query_last_launches", "bsg_timer_begin", "bsg_timer_end", "bsg_comm_unique_id", "bsg_comm_init",
@@ -95,6 +95,7 @@ def lib():
     L.bsg_hash_keys.argtypes = [vp, vp, vp, u64, vp]
     L.bsg_build.argtypes = [vp, vp, vp, u64, vp, u32, vp, vp, vp, u32, vp, u64]
     L.bsg_build_fieldtokens.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, u32, vp, vp, vp, u32, vp, u64]
+    L.bsg_count_distinct.argtypes = [vp, vp, vp, u64, vp, u32, vp, u32, vp, vp]
     L.bsg_corpus_load.argtypes = [vp, vp, u64, vp, u64, i32, C.POINTER(vp)]
     L.bsg_corpus_load_sections.argtypes = [vp, vp, vp, u64, i32, vp, C.POINTER(u64), C.POINTER(vp)]
     L.bsg_corpus_free.argtypes = [vp]

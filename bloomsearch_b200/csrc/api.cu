@@ -610,6 +610,66 @@ extern "C" int bsg_build_fieldtokens(bsg_ctx* ctx, const uint8_t* strings, const
     return rc;
 }
 
+// (f.3) exact distinct counts per group and per parent union — replaces the dedup the Go maps do.
+extern "C" int bsg_count_distinct(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
+                                  const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_parent,
+                                  uint32_t n_parents, uint64_t* out_group_counts, uint64_t* out_parent_counts) {
+    if (!ctx || !key_off || (n_groups && (!group_begin || !out_group_counts)) ||
+        ((group_parent != nullptr) != (out_parent_counts != nullptr)))
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
+    if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
+    {
+        const uint64_t bad = first_bad_offset(key_off, n_keys);
+        if (bad != n_keys) return fail(BSG_ERR_INVALID, "key_off not monotone at %llu", (unsigned long long)bad);
+    }
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (group_begin[g + 1] < group_begin[g] || group_begin[g + 1] > n_keys)
+            return fail(BSG_ERR_INVALID, "group %u: key range invalid", g);
+        if (group_parent && group_parent[g] >= n_parents) return fail(BSG_ERR_INVALID, "group %u: parent out of range", g);
+    }
+    if (n_groups && (group_begin[0] != 0 || group_begin[n_groups] != n_keys))
+        return fail(BSG_ERR_INVALID, "groups must cover all keys");
+    for (uint32_t g = 0; g < n_groups; ++g) out_group_counts[g] = 0;
+    for (uint32_t p = 0; group_parent && p < n_parents; ++p) out_parent_counts[p] = 0;
+    if (n_keys == 0 || n_groups == 0) return BSG_OK;
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    DevBuf<uint8_t> d_keys, d_em;
+    DevBuf<uint64_t> d_off, d_gb;
+    DevBuf<uint32_t> d_gp;
+    DevBuf<unsigned long long> d_gc, d_pc;
+    int rc = BSG_OK;
+    do {
+        if (d_keys.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_keys + 1) != cudaSuccess ||
+            d_gb.alloc(n_groups + 1) != cudaSuccess || d_gc.alloc(n_groups) != cudaSuccess ||
+            d_em.alloc(count_distinct_scratch_bytes(n_keys)) != cudaSuccess ||
+            (group_parent && (d_gp.alloc(n_groups) != cudaSuccess || d_pc.alloc(n_parents) != cudaSuccess))) {
+            rc = fail(BSG_ERR_NOMEM, "device alloc");
+            break;
+        }
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+        cudaError_t e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_gc.p, 0, n_groups * 8, s);
+        if (e == cudaSuccess && group_parent) e = cudaMemsetAsync(d_pc.p, 0, std::max<uint32_t>(n_parents, 1) * 8, s);
+        if (e == cudaSuccess) e = upload(ctx, d_keys.p, keys, nbytes, s);
+        if (e == cudaSuccess) e = upload(ctx, d_off.p, key_off, (n_keys + 1) * 8, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_gb.p, group_begin, (static_cast<size_t>(n_groups) + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && group_parent) e = cudaMemcpyAsync(d_gp.p, group_parent, n_groups * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess)
+            e = launch_count_distinct(d_keys.p, d_off.p, n_keys, d_gb.p, n_groups, group_parent ? d_gp.p : nullptr, d_em.p,
+                                      d_gc.p, group_parent ? d_pc.p : nullptr, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_group_counts, d_gc.p, n_groups * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && group_parent)
+            e = cudaMemcpyAsync(out_parent_counts, d_pc.p, n_parents * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_count_distinct: %s", cudaGetErrorString(e));
+    } while (0);
+    pool_put(ctx, s);
+    return rc;
+}
+
 // ------------------------------------------------------------------ corpus ---
 struct bsg_corpus {
     int device = 0;

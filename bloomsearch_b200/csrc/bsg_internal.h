@@ -114,6 +114,12 @@ cudaError_t launch_build_ft(const uint8_t* d_strings, const uint64_t* d_str_off,
                             const BuildFilter* d_filters, uint64_t* d_out_words, uint32_t smem_cap_bytes,
                             cudaStream_t s);
 
+cudaError_t launch_count_distinct(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,
+                                  const uint64_t* d_group_begin, uint32_t n_groups, const uint32_t* d_group_parent,
+                                  void* d_emissions, unsigned long long* d_group_counts,
+                                  unsigned long long* d_parent_counts, cudaStream_t s);
+size_t count_distinct_scratch_bytes(uint64_t n_keys);
+
 cudaError_t launch_repack(const uint64_t* d_src, const uint64_t* d_src_off, const DevFilter* d_udesc,
                           uint64_t n_filters, uint64_t* d_dst, int big_endian, cudaStream_t s);
 

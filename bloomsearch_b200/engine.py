@@ -107,6 +107,20 @@ class Context:
                                               N.ptr(out), int(n_words)))
         return out[:int(n_words)]
 
+    def count_distinct(self, blob: np.ndarray, key_off: np.ndarray, group_begin: np.ndarray,
+                       group_parent: Optional[np.ndarray] = None, n_parents: int = 0):
+        """bsg_count_distinct: exact distinct-entry counts per group (and per parent union) of emissions
+        that may repeat — the counts bloomEntrySets' maps provide (ingest.go:24-45,105-123)."""
+        key_off = np.ascontiguousarray(key_off, dtype=np.uint64)
+        group_begin = np.ascontiguousarray(group_begin, dtype=np.uint64)
+        n_groups = len(group_begin) - 1
+        gp = None if group_parent is None else np.ascontiguousarray(group_parent, dtype=np.uint32)
+        gc = np.zeros(max(n_groups, 1), dtype=np.uint64)
+        pc = None if gp is None else np.zeros(max(int(n_parents), 1), dtype=np.uint64)
+        N.check(N.lib().bsg_count_distinct(self._h, N.ptr(blob), N.ptr(key_off), len(key_off) - 1, N.ptr(group_begin),
+                                           n_groups, N.ptr(gp), int(n_parents), N.ptr(gc), N.ptr(pc)))
+        return gc[:n_groups], (None if pc is None else pc[:int(n_parents)])
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -242,6 +242,36 @@ func (c *Context) ProbeHierarchical(files, blocks *Corpus, keys PackedKeys, kind
 	return fileMask[:(files.Units+63)/64], blockMask[:(blocks.Units+63)/64], check(rc)
 }
 
+// CountDistinct is bsg_count_distinct: exact distinct counts per group and (if groupParent != nil)
+// per parent union of emissions that may repeat — the counts the maps of bloomEntrySets provide
+// (ingest.go:24-45,105-123), i.e. the n that sizes each filter (ingest.go:139-140).
+func (c *Context) CountDistinct(keys PackedKeys, groupBegin []uint64, groupParent []uint32, nParents int) (groups, parents []uint64, err error) {
+	nGroups := len(groupBegin) - 1
+	groups = make([]uint64, nGroups+1)
+	if nGroups <= 0 {
+		return groups[:0], nil, nil
+	}
+	var gp *C.uint32_t
+	var pc *C.uint64_t
+	if groupParent != nil {
+		parents = make([]uint64, nParents+1)
+		gp = (*C.uint32_t)(unsafe.Pointer(&groupParent[0]))
+		pc = (*C.uint64_t)(unsafe.Pointer(&parents[0]))
+	}
+	var kb *C.uint8_t
+	if len(keys.Bytes) > 0 {
+		kb = (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0]))
+	}
+	rc := C.bsg_count_distinct(c.h, kb, (*C.uint64_t)(unsafe.Pointer(&keys.Off[0])), C.uint64_t(len(keys.Off)-1),
+		(*C.uint64_t)(unsafe.Pointer(&groupBegin[0])), C.uint32_t(nGroups), gp, C.uint32_t(nParents),
+		(*C.uint64_t)(unsafe.Pointer(&groups[0])), pc)
+	runtime.KeepAlive(keys)
+	if parents != nil {
+		parents = parents[:nParents]
+	}
+	return groups[:nGroups], parents, check(rc)
+}
+
 // BuildFieldTokens is bsg_build_fieldtokens: field::token entries as (path, token) index pairs into
 // one string table; the joined key is hashed on the GPU and never materialised (ingest.go:95-102).
 func (c *Context) BuildFieldTokens(strings PackedKeys, pairPath, pairToken []uint32, groupBegin []uint64,

@@ -131,6 +131,16 @@ int bsg_build_fieldtokens(bsg_ctx *ctx, const uint8_t *strings, const uint64_t *
                           const uint32_t *group_filter2, const bsg_filter_desc *desc, uint32_t n_filters,
                           uint64_t *out_words, uint64_t n_words);
 
+/* Exact distinct counts (what the Go maps of bloomEntrySets provide, ingest.go:24-45,105-123):
+ * keys may repeat inside and across groups.  out_group_counts[g] = number of distinct keys of
+ * group g; if group_parent != NULL, out_parent_counts[p] = number of distinct keys of the union
+ * of all groups with group_parent[g] == p (the file-level union count, flush.go:221,253).
+ * These are the n of NewWithEstimates(max(n,1), fpr) (ingest.go:139-140).  Two keys count as
+ * equal when their 256 bits of base hashes agree. */
+int bsg_count_distinct(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64_t n_keys,
+                       const uint64_t *group_begin, uint32_t n_groups, const uint32_t *group_parent,
+                       uint32_t n_parents, uint64_t *out_group_counts, uint64_t *out_parent_counts);
+
 /* ---- corpus residency ------------------------------------------------------ *
  * A corpus is n_units "units" (data blocks, or files for the file-level stage),
  * each with up to three filters: desc[3*u + kind].  The words are copied to HBM

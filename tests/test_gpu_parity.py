@@ -680,3 +680,71 @@ def test_build_fieldtokens_equals_joined_keys(ctx):
     with pytest.raises(bs.BloomGpuError):
         ctx.build_fieldtokens(blob, off, np.array([len(strings)], np.uint32), np.array([0], np.uint32),
                               np.array([0, 1], np.uint64), np.zeros(1, np.uint32), None, d[:1], wo)
+
+
+# --------------------------------------------- exact distinct counts (f.3) ---
+def _emissions(rng, n_groups, vocab, sizes):
+    groups = [[vocab[rng.randrange(len(vocab))] for _ in range(sizes[g % len(sizes)])] for g in range(n_groups)]
+    keys = [k for g in groups for k in g]
+    gb = np.cumsum([0] + [len(g) for g in groups]).astype(np.uint64)
+    return groups, keys, gb
+
+
+def test_count_distinct_matches_host_sets(ctx):
+    """bsg_count_distinct == len(set(...)) per group and per parent union — the counts the Go maps of
+    bloomEntrySets hold (ingest.go:24-45 dedup, :105-123 unionInto/counts)."""
+    rng = random.Random(1234)
+    vocab = [b"", b"a", b"b", b"level", b"level\x00", b"service::api"] + \
+            [bytes(rng.randrange(256) for _ in range(rng.randint(0, 48))) for _ in range(700)]
+    groups, keys, gb = _emissions(rng, 23, vocab, [0, 1, 2, 31, 32, 33, 500, 4000])
+    parent = np.array([g % 5 for g in range(len(groups))], dtype=np.uint32)
+    blob, off = N.pack_keys(keys)
+    gc, pc = ctx.count_distinct(blob, off, gb, parent, 6)       # parent 5 has no groups
+    assert gc.tolist() == [len(set(g)) for g in groups]
+    want_p = [len(set(k for g, p in zip(groups, parent) if p == q for k in g)) for q in range(6)]
+    assert pc.tolist() == want_p and pc[5] == 0
+    gc2, pc2 = ctx.count_distinct(blob, off, gb)
+    assert gc2.tolist() == gc.tolist() and pc2 is None
+    # no keys at all / only empty groups
+    e_blob, e_off = N.pack_keys([])
+    gc3, _ = ctx.count_distinct(e_blob, e_off, np.zeros(4, np.uint64))
+    assert gc3.tolist() == [0, 0, 0]
+    with pytest.raises(bs.BloomGpuError):
+        ctx.count_distinct(blob, off, gb, np.full(len(groups), 9, np.uint32), 6)
+    with pytest.raises(bs.BloomGpuError):
+        ctx.count_distinct(blob, off, gb[:-1])                   # groups do not cover the keys
+
+
+def test_counted_emissions_build_equals_deduped_sets(ctx):
+    """Ingest without host maps: raw emissions (with repeats) -> device distinct counts -> sizes ->
+    bsg_build over the raw emissions is bit-identical to buildFilters over the deduplicated sets
+    (insertion is an idempotent OR; ingest.go:127-145), block filters and the file union filter."""
+    rng = random.Random(77)
+    vocab = [b"tok%d" % i for i in range(3000)]
+    groups, keys, gb = _emissions(rng, 12, vocab, [50, 900, 2500, 1])
+    blob, off = N.pack_keys(keys)
+    parent = np.zeros(len(groups), dtype=np.uint32)
+    gc, pc = ctx.count_distinct(blob, off, gb, parent, 1)
+    desc, wo = [], 0
+    for n in list(gc) + [pc[0]]:
+        m, k = bs.estimate_parameters(max(int(n), 1), 0.001)
+        desc.append((m, k, wo))
+        wo += (m + 63) // 64
+    d = np.array(desc, dtype=N.DESC_DTYPE)
+    gf = np.arange(len(groups), dtype=np.uint32)
+    gf2 = np.full(len(groups), len(groups), dtype=np.uint32)
+    got = ctx.build(blob, off, gb, gf, gf2, d, wo)
+    dedup = [sorted(set(g)) for g in groups]
+    dk = [k for g in dedup for k in g]
+    db, do = N.pack_keys(dk)
+    dgb = np.cumsum([0] + [len(g) for g in dedup]).astype(np.uint64)
+    # the oracle sizes from its own set sizes: same descriptors must come out
+    d_want = []
+    wo2 = 0
+    for n in [len(g) for g in dedup] + [len(set(keys))]:
+        m, k = pyref.estimate_parameters(max(n, 1), 0.001)
+        d_want.append((m, k, wo2))
+        wo2 += (m + 63) // 64
+    assert d_want == desc
+    want = cref.build_filters(db, do, dgb, gf, gf2, d, wo)
+    assert np.array_equal(got, want)
