@@ -38,6 +38,9 @@ N_KEYS = 1000
 # `ncu --set full` captures (profiles/): 2b 70.52 MB + 0.44 MB, 2a 74.92 MB + 1.24 MB
 TRAFFIC_NCU = {"2b": 70.96e6, "2a": 76.16e6}
 L2_BYTES = 126 * 1024 * 1024
+# the staged probe kernel the library launches (BSG_PROBE_VARIANT: 0 = one phase, 1/2 = two phases)
+PROBE_KERNEL = {"0": "probe_staged_kernel", "1": "probe_staged2_kernel<16,2>", "2": "probe_staged2_kernel<8,4>"}[
+    os.environ.get("BSG_PROBE_VARIANT", "1")]
 
 
 def log(*a):
@@ -367,7 +370,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = algo_bytes / (k_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": TRAFFIC_NCU.get(wl), "kernel": "probe_staged_kernel", "kernel_ms": k_ms,
+                    "traffic": TRAFFIC_NCU.get(wl), "kernel": PROBE_KERNEL, "kernel_ms": k_ms,
                     "kernel_ms_single_stream": ms_single, "frac_single_stream": algo_bytes / (ms_single / 1e3) / 1e9 / peak,
                     "launch_streams": args.streams,
                     "algorithmic_bytes_per_launch": algo_bytes,

@@ -83,6 +83,7 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
+    int probe_variant = 1; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1/2 = probe_staged2 (two phases)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
@@ -140,6 +141,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
+    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(2, std::max(0, atoi(w)));
     *out = ctx;
     return BSG_OK;
 }
@@ -763,8 +765,9 @@ int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
 int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter_desc* desc, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
     // staged vs gather: a unit is staged when at least 3 stages of its size fit
-    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - kProbeSmemPrefixBytes;
-    const uint64_t unit_limit = budget / 3 - kProbeStageHeaderBytes;
+    // (sized for the two-phase kernel's larger stage header so either staged kernel can run)
+    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - kProbe2SmemPrefixBytes;
+    const uint64_t unit_limit = budget / 3 - kProbeStage2HeaderBytes;
     std::vector<uint32_t> staged, gather;
     std::vector<StageRow> stab;
     uint32_t cap = 0;
@@ -1169,14 +1172,17 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         }
         if (use_staged) {
             ProbeStagedPlan plan;
-            const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - kProbeSmemPrefixBytes;
+            plan.variant = ctx->d_trace ? 0 : ctx->probe_variant;  // the timeline lives in the one-phase kernel
+            const uint64_t prefix = plan.variant ? kProbe2SmemPrefixBytes : kProbeSmemPrefixBytes;
+            const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - prefix;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);
-            const uint64_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
+            const uint64_t stage_bytes =
+                (plan.variant ? kProbeStage2HeaderBytes : kProbeStageHeaderBytes) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
             if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
             plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, budget / stage_bytes));
             if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: stage does not fit shared memory");
-            plan.smem_bytes = kProbeSmemPrefixBytes + plan.n_stages * stage_bytes;
+            plan.smem_bytes = prefix + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(c->n_staged, ctx->sm_count));
             plan.warps = ctx->probe_warps;
             // time for the whole chip to stream one stage per SM at ~6.5 TB/s, capped at 2 us

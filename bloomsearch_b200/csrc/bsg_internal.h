@@ -70,6 +70,10 @@ constexpr int kProbeMaxStages = 16;
 constexpr int kProbeSmemPrefixBytes = 256;     // 16 mbarriers (128 B) + 16 done counters (64 B) + pad
 constexpr int kProbeStageHeaderBytes = 160;    // StageRow (128 B) + next unit's head (32 B)
 constexpr uint32_t kProbeMaxKeysPerPass = 1024;  // one key per thread, up to 32 warps per CTA
+// two-phase staged kernel (probe_staged2): stage header = StageRow + next head + result row (128 B)
+// + survivor count (16 B) + survivor queue (1024 x u16); prefix = full + aready mbarriers + done counters
+constexpr int kProbeStage2HeaderBytes = 160 + 128 + 16 + 2048;
+constexpr int kProbe2SmemPrefixBytes = 384;
 
 // ---- launch wrappers (defined in the kernels_*.cu files) -------------------
 cudaError_t launch_hash_keys(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,
@@ -82,6 +86,7 @@ struct ProbeStagedPlan {
     int grid;
     int warps;            // 0 = auto
     uint32_t stagger_ns;  // delay between the prologue's stage fills (0 = none)
+    int variant;          // 0 = probe_staged (one phase), 1 = probe_staged2<16,2>, 2 = probe_staged2<8,4>
 };
 cudaError_t probe_staged_configure(int max_smem_optin);
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,

@@ -64,14 +64,15 @@ __device__ __forceinline__ bool test_hashes(const uint64_t h0, const uint64_t h1
 __device__ __forceinline__ void fill_stage(uint8_t* st, uint64_t* full_bar, const StageRow* __restrict__ stab,
                                            uint32_t li, bool has_next, uint32_t li_next,
                                            const uint64_t* __restrict__ words, uint64_t word_base, uint32_t nw0,
-                                           uint32_t nw1, uint32_t nw2, uint32_t kind_mask) {
+                                           uint32_t nw1, uint32_t nw2, uint32_t kind_mask,
+                                           uint32_t hdr_bytes = kProbeStageHeaderBytes) {
     const uint32_t b0 = (kind_mask & 1u) ? nw0 * 8u : 0u;
     const uint32_t b1 = (kind_mask & 2u) ? nw1 * 8u : 0u;
     const uint32_t b2 = (kind_mask & 4u) ? nw2 * 8u : 0u;
     mbar_arrive_expect_tx(full_bar, kStageRowBytes + (has_next ? kStageHeadBytes : 0u) + b0 + b1 + b2);
     bulk_g2s(st, &stab[li], kStageRowBytes, full_bar);
     if (has_next) bulk_g2s(st + kStageRowBytes, &stab[li_next], kStageHeadBytes, full_bar);
-    uint8_t* data = st + kProbeStageHeaderBytes;
+    uint8_t* data = st + hdr_bytes;
     const uint64_t* src = words + word_base;
     if (kind_mask == 7u) {
         if (b0 + b1 + b2) bulk_g2s(data, src, b0 + b1 + b2, full_bar);
@@ -266,9 +267,248 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
     }
 }
 
+
+// ------------------------------------------------- staged path, two phases ---
+// probe_staged2: the same ring of bulk-copied units, but TestString is split in two phases so
+// that the early exit does not idle lanes (in probe_staged a warp runs until its slowest lane
+// is done: ~6.3 of k = 10 tests for 32 absent keys whose mean is 2 -> a third of the lanes work).
+//
+//   phase A  (warps 0..NA-1, KPT keys per thread, only location 0 and 1 of each key kept in
+//            registers): both tests of every key, no branch between them (ILP 2*KPT).  A key that
+//            fails is final (bit 0).  A key whose filter is absent or has k <= 2 is final (bit 1).
+//            Every other passing key is a *survivor*: its index is appended to the stage's queue
+//            (one shared-memory atomicAdd per warp per unit).  For keys absent from a unit a
+//            quarter survives.
+//   phase B  (warps NA..31): wait for the A warps of that unit (mbarrier), then test locations
+//            2..k-1 of the queued survivors, 32 survivors per warp pass (dense lanes), early exit
+//            per lane; a survivor that passes everything ORs its bit into the unit's result row in
+//            shared memory.  The last B warp out writes the row to HBM with one coalesced store,
+//            resets the stage and refills it (same last-arriver refill as probe_staged).
+//
+// Same bits as probe_staged (TestString is an AND over the k locations; the order in which clear
+// bits are discovered does not matter).
+constexpr uint32_t kStage2RowBitsOff = kProbeStageHeaderBytes;             // 32 x u32 result row
+constexpr uint32_t kStage2CntOff = kStage2RowBitsOff + 128;                // u32 survivors in queue
+constexpr uint32_t kStage2QueueOff = kStage2CntOff + 16;                   // 1024 x u16 key indexes
+static_assert(kStage2QueueOff + 2 * kProbeMaxKeysPerPass == kProbeStage2HeaderBytes, "stage2 header layout");
+static_assert(kProbeStage2HeaderBytes % 16 == 0, "bulk copies need 16-byte aligned destinations");
+
+__device__ __forceinline__ uint32_t ld_volatile_shared_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// locations 2..k-1 of a survivor (k > 2); same unrolling as test_hashes_s32
+__device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
+                                              uint32_t ih, uint32_t il, uint32_t k,
+                                              const uint32_t* __restrict__ w32) {
+    auto test = [&](uint64_t loc) {
+        const uint32_t bit = mod_m32(loc, m, ih, il);
+        return (w32[bit >> 5] & (1u << (bit & 31u))) != 0u;
+    };
+    if (!test(h0 + 2 * h3)) return false;
+    if (k > 3 && !test(h1 + 3 * h2)) return false;
+    uint64_t ih2 = 4 * h2, ih3 = 4 * h3;
+    uint32_t i = 4;
+    for (; i + 4 <= k; i += 4) {
+        if (!test(h0 + ih2)) return false;
+        if (!test(h1 + ih3 + h3)) return false;
+        if (!test(h0 + ih3 + 2 * h3)) return false;
+        if (!test(h1 + ih2 + 3 * h2)) return false;
+        ih2 += 4 * h2;
+        ih3 += 4 * h3;
+    }
+    if (i < k && !test(h0 + ih2)) return false;
+    if (i + 1 < k && !test(h1 + ih3 + h3)) return false;
+    if (i + 2 < k && !test(h0 + ih3 + 2 * h3)) return false;
+    return true;
+}
+
+template <int NA, int KPT>
+__global__ void __launch_bounds__(1024, 1)
+probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
+                     const uint64_t* __restrict__ words, const uint64_t* __restrict__ hashes,
+                     const uint8_t* __restrict__ kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
+                     uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes) {
+    static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
+    constexpr uint32_t NB = 32 - NA;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* aready = full + kProbeMaxStages;
+    uint32_t* done = reinterpret_cast<uint32_t*>(aready + kProbeMaxStages);
+    uint8_t* stages = smem + kProbe2SmemPrefixBytes;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31;
+    const uint32_t warp = tid >> 5;
+    const uint32_t G = gridDim.x;
+    const uint32_t S = n_stages;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&aready[s], NA);
+            done[s] = 0;
+            *reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(s) * stage_bytes + kStage2CntOff) = 0;
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t n_list = n_list_dev ? __ldg(n_list_dev) : n_list_host;
+    const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
+
+    if (warp == 0 && lane < S && lane < my_count) {  // prologue: lane l fills stage l
+        const uint32_t li = blockIdx.x + lane * G;
+        const uint4* hp = reinterpret_cast<const uint4*>(&stab[li]);
+        const uint4 a = __ldg(hp), b = __ldg(hp + 1);
+        const uint64_t word_base = (static_cast<uint64_t>(a.w) << 32) | a.z;
+        fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
+                   li + S * G, words, word_base, b.x, b.y, b.z, kind_mask, kProbeStage2HeaderBytes);
+    }
+
+    uint32_t s = 0, ph = 0;
+    uint8_t* st = stages;
+    if (warp < NA) {
+        // ------------------------------------------------------------ phase A ---
+        uint64_t l0[KPT], l1[KPT];
+        uint32_t f_off[KPT];  // byte offset of the key's StageFilter in the stage row; 0 = no key
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            const uint32_t ql = (warp * KPT + j) * 32 + lane;
+            l0[j] = 0; l1[j] = 0; f_off[j] = 0;
+            if (ql < n_keys) {
+                const uint32_t q = key_base + ql;
+                const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+                const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+                l0[j] = a.x;
+                l1[j] = a.y + b.y;
+                f_off[j] = 32u + 32u * __ldg(&kinds[q]);
+            }
+        }
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        for (uint32_t it = 0; it < my_count; ++it) {
+            mbar_wait(&full[s], ph);
+            uint32_t fin_bits[KPT], surv_bits[KPT];
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                bool fin = false, surv = false;
+                if (f_off[j]) {
+                    const uint4 f = *reinterpret_cast<const uint4*>(st + f_off[j]);  // m, k, ih, il
+                    if (f.x == 0) {
+                        fin = true;  // absent filter cannot disqualify (query_exec.go:137-151)
+                    } else {
+                        const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + f_off[j] + 16);
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel);
+                        const uint32_t b0 = mod_m32(l0[j], f.x, f.z, f.w);
+                        const uint32_t b1 = mod_m32(l1[j], f.x, f.z, f.w);
+                        const uint32_t w0 = w32[b0 >> 5], w1 = w32[b1 >> 5];
+                        const bool p0 = ((w0 >> (b0 & 31u)) & 1u) | (f.y == 0u);
+                        const bool p1 = ((w1 >> (b1 & 31u)) & 1u) | (f.y <= 1u);
+                        const bool pass = p0 & p1;
+                        fin = pass & (f.y <= 2u);
+                        surv = pass & (f.y > 2u);
+                    }
+                }
+                fin_bits[j] = __ballot_sync(0xffffffffu, fin);
+                surv_bits[j] = __ballot_sync(0xffffffffu, surv);
+            }
+            uint32_t total = 0;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) total += __popc(surv_bits[j]);
+            uint32_t base = 0;
+            if (lane == 0) {
+                uint4* row = reinterpret_cast<uint4*>(st + kStage2RowBitsOff) + (warp * KPT) / 4;
+                if constexpr (KPT == 4) {
+                    *row = make_uint4(fin_bits[0], fin_bits[1], fin_bits[2], fin_bits[3]);
+                } else {
+                    uint32_t* r32 = reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + warp * KPT;
+#pragma unroll
+                    for (int j = 0; j < KPT; ++j) r32[j] = fin_bits[j];
+                }
+                if (total) base = atomicAdd(reinterpret_cast<uint32_t*>(st + kStage2CntOff), total);
+            }
+            if (total) {
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint16_t* queue = reinterpret_cast<uint16_t*>(st + kStage2QueueOff);
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) {
+                    if ((surv_bits[j] >> lane) & 1u)
+                        queue[base + __popc(surv_bits[j] & lt_mask)] = static_cast<uint16_t>((warp * KPT + j) * 32 + lane);
+                    base += __popc(surv_bits[j]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aready[s]);  // release: row words + queue entries of this warp
+            st += stage_bytes;
+            if (++s == S) { s = 0; ph ^= 1u; st = stages; }
+        }
+    } else {
+        // ------------------------------------------------------------ phase B ---
+        const uint32_t wb = warp - NA;
+        const uint32_t out_words = (n_keys + 31) >> 5;
+        uint32_t* out_base = matrix32 + (key_base >> 5);
+        for (uint32_t it = 0; it < my_count; ++it) {
+            mbar_wait(&full[s], ph);    // the bulk copy's bytes (async proxy) are visible
+            mbar_wait(&aready[s], ph);  // every A warp has published its row words and survivors
+            const uint32_t n = ld_volatile_shared_u32(st + kStage2CntOff);
+            const uint32_t n_chunks = (n + 31) >> 5;
+            const uint16_t* queue = reinterpret_cast<const uint16_t*>(st + kStage2QueueOff);
+            // rotate the first chunk over the B warps from unit to unit
+            for (uint32_t c = (wb + NB - (it % NB)) % NB; c < n_chunks; c += NB) {
+                const uint32_t idx = c * 32 + lane;
+                if (idx < n) {
+                    const uint32_t ql = queue[idx];
+                    const uint32_t q = key_base + ql;
+                    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
+                    const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+                    const uint32_t fo = 32u + 32u * __ldg(&kinds[q]);
+                    const uint4 f = *reinterpret_cast<const uint4*>(st + fo);
+                    const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + fo + 16);
+                    if (test_tail_s32(a.x, a.y, b.x, b.y, f.x, f.z, f.w, f.y,
+                                      reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel)))
+                        atomicOr(reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + (ql >> 5), 1u << (ql & 31u));
+                }
+            }
+            __syncwarp();
+            uint32_t last = 0;
+            if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == NB - 1;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {  // every warp is done with this stage: emit the row, reset, refill
+                const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
+                if (lane < out_words)
+                    out_base[static_cast<size_t>(unit) * row_words32 + lane] =
+                        ld_volatile_shared_u32(st + kStage2RowBitsOff + 4 * lane);
+                __syncwarp();
+                if (lane == 0) {
+                    done[s] = 0;
+                    *reinterpret_cast<uint32_t*>(st + kStage2CntOff) = 0;
+                    const uint32_t nxt = it + S;
+                    if (nxt < my_count) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
+                        const uint4 b = *reinterpret_cast<const uint4*>(st + kStageRowBytes + 16);
+                        const uint64_t nwb = (static_cast<uint64_t>(a.w) << 32) | a.z;
+                        fence_proxy_async();
+                        fill_stage(st, &full[s], stab, blockIdx.x + nxt * G, nxt + S < my_count,
+                                   blockIdx.x + (nxt + S) * G, words, nwb, b.x, b.y, b.z, kind_mask,
+                                   kProbeStage2HeaderBytes);
+                    }
+                }
+            }
+            st += stage_bytes;
+            if (++s == S) { s = 0; ph ^= 1u; st = stages; }
+        }
+    }
+}
+
 cudaError_t probe_staged_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(probe_staged_kernel<1024, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(probe_staged2_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(probe_staged2_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(probe_staged_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 max_smem_optin);
@@ -281,6 +521,18 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
                                 const uint32_t* d_n_list) {
     if ((n_list == 0 && !d_n_list) || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
+    if (plan.variant != 0 && !d_trace) {  // two-phase kernel: always 32 warps (NA phase-A + 32-NA phase-B)
+        const uint32_t sb = kProbeStage2HeaderBytes + plan.stage_data_bytes;
+        if (plan.variant == 2)
+            probe_staged2_kernel<8, 4><<<dim3(plan.grid), dim3(1024), plan.smem_bytes, s>>>(
+                d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32,
+                row_words32, static_cast<uint32_t>(plan.n_stages), sb);
+        else
+            probe_staged2_kernel<16, 2><<<dim3(plan.grid), dim3(1024), plan.smem_bytes, s>>>(
+                d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32,
+                row_words32, static_cast<uint32_t>(plan.n_stages), sb);
+        return cudaGetLastError();
+    }
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
     // one key per thread; at least 4 warps so a small batch still has some latency hiding
     uint32_t warps = (n_keys + 31) / 32;

@@ -748,3 +748,69 @@ def test_counted_emissions_build_equals_deduped_sets(ctx):
     assert d_want == desc
     want = cref.build_filters(db, do, dgb, gf, gf2, d, wo)
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------- staged kernels: every variant, forced refills ---
+def _units_with_fprs(unit_keys, fprs, absent=()):
+    """Like helpers.oracle_units but with one fpr per unit (k from 1 to 30)."""
+    desc = np.zeros(len(unit_keys) * 3, dtype=cref.DESC_DTYPE)
+    chunks, off = [], 0
+    for u, kinds_ in enumerate(unit_keys):
+        for kind, ks in enumerate(kinds_):
+            if (u, kind) in absent:
+                continue
+            f = cref.Filter.build_sized(ks, fprs[u % len(fprs)])
+            w = f.words()
+            desc[u * 3 + kind] = (f.m, f.k, off)
+            chunks.append(w)
+            off += len(w)
+    return desc, np.concatenate(chunks)
+
+
+@pytest.mark.parametrize("variant,stages", [(0, 0), (0, 2), (1, 0), (1, 2), (1, 1), (2, 0), (2, 3)])
+def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, monkeypatch):
+    """probe_staged (one phase) and probe_staged2 (phase A: locations 0-1 of every key, phase B:
+    locations 2..k-1 of the compacted survivors) must give the oracle's matrix for k = 1, 2, 3
+    (no phase-B work), k = 30, absent filters, keys present in every unit (survivor queue full),
+    1024-key passes + a ragged second pass, and rings of 1-3 stages so every CTA refills."""
+    from tests.conftest import _has_gpu
+    if not _has_gpu():
+        pytest.skip("no CUDA device in this process")
+    monkeypatch.setenv("BSG_PROBE_VARIANT", str(variant))
+    if stages:
+        monkeypatch.setenv("BSG_PROBE_STAGES", str(stages))
+    rng = random.Random(4242 + variant)
+    shared_tok = rand_keys(rng, 700, 2, 14)       # present in every unit
+    shared_ft = rand_keys(rng, 500, 6, 24)
+    n_units = 700                                  # > 148 CTAs x 3 stages: refills even without the knob... (x16 not)
+    unit_keys = []
+    for u in range(n_units):
+        unit_keys.append((rand_keys(rng, 6, 3, 9), shared_tok + rand_keys(rng, 40 + u % 50, 15, 20),
+                          shared_ft + rand_keys(rng, 30 + u % 40, 25, 32)))
+    fprs = [0.6, 0.3, 0.2, 0.05, 0.001, 1e-9]
+    absent = {(5, 1), (6, 2), (7, 0), (8, 0), (8, 1), (8, 2), (n_units - 1, 1)}
+    desc, words = _units_with_fprs(unit_keys, fprs, absent)
+    assert sorted({int(k) for k in desc["k"] if k}) [:3] == [1, 2, 3] and int(desc["k"].max()) == 30
+    keys = shared_tok + shared_ft[:324]            # 1024 keys that pass everywhere: queue = 1024 survivors
+    kinds = [1] * len(shared_tok) + [2] * 324
+    extra, extra_kinds = _mixed_keys(rng, unit_keys[:50], 300, 401)
+    keys, kinds = keys + extra, kinds + extra_kinds
+    assert len(keys) == 1725
+    blob, off = N.pack_keys(keys)
+    kinds = np.asarray(kinds, dtype=np.uint8)
+    want = cref.probe_matrix(desc, words, n_units, blob, off, kinds)
+    c2 = bs.Context(0)
+    try:
+        corpus = bs.Corpus(c2, desc, words)
+        for _ in range(2):                         # twice: stage state must be clean at kernel exit
+            q = bs.Query(corpus, keys, kinds, None)
+            q.run(N.PROBE_STAGED)
+            got, _ = q.fetch()
+            q.close()
+            assert np.array_equal(got, want), f"variant {variant} stages {stages}"
+        # first 1024 keys pass in every unit that has the filter (no false negatives)
+        bits = bs.unpack_matrix(want, len(keys))
+        assert bits[:, :1024].all()
+        corpus.close()
+    finally:
+        c2.close()
