@@ -141,7 +141,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(2, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(8, std::max(0, atoi(w)));
     *out = ctx;
     return BSG_OK;
 }
@@ -1172,7 +1172,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         }
         if (use_staged) {
             ProbeStagedPlan plan;
-            plan.variant = ctx->d_trace ? 0 : ctx->probe_variant;  // the timeline lives in the one-phase kernel
+            plan.variant = ctx->probe_variant;
             const uint64_t prefix = plan.variant ? kProbe2SmemPrefixBytes : kProbeSmemPrefixBytes;
             const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - prefix;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);

@@ -273,14 +273,14 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
 // that the early exit does not idle lanes (in probe_staged a warp runs until its slowest lane
 // is done: ~6.3 of k = 10 tests for 32 absent keys whose mean is 2 -> a third of the lanes work).
 //
-//   phase A  (warps 0..NA-1, KPT keys per thread, only location 0 and 1 of each key kept in
-//            registers): both tests of every key, no branch between them (ILP 2*KPT).  A key that
-//            fails is final (bit 0).  A key whose filter is absent or has k <= 2 is final (bit 1).
-//            Every other passing key is a *survivor*: its index is appended to the stage's queue
-//            (one shared-memory atomicAdd per warp per unit).  For keys absent from a unit a
-//            quarter survives.
-//   phase B  (warps NA..31): wait for the A warps of that unit (mbarrier), then test locations
-//            2..k-1 of the queued survivors, 32 survivors per warp pass (dense lanes), early exit
+//   phase A  (warps 0..NA-1, KPT keys per thread, only locations 0..NT-1 of each key kept in
+//            registers): the first NT tests of every key, no branch between them (ILP NT*KPT).
+//            A key that fails is final (bit 0).  A key whose filter is absent or has k <= NT is
+//            final (bit 1).  Every other passing key is a *survivor*: its index is appended to the
+//            stage's queue (one shared-memory atomicAdd per warp per unit).  Of the keys absent
+//            from a unit 2^-NT survive.
+//   phase B  (warps NA..NA+NB-1): wait for the A warps of that unit (mbarrier), then test locations
+//            NT..k-1 of the queued survivors, 32 survivors per warp pass (dense lanes), early exit
 //            per lane; a survivor that passes everything ORs its bit into the unit's result row in
 //            shared memory.  The last B warp out writes the row to HBM with one coalesced store,
 //            resets the stage and refills it (same last-arriver refill as probe_staged).
@@ -299,16 +299,20 @@ __device__ __forceinline__ uint32_t ld_volatile_shared_u32(const void* p) {
     return v;
 }
 
-// locations 2..k-1 of a survivor (k > 2); same unrolling as test_hashes_s32
+// locations START..k-1 of a survivor (k > START, START in 1..4); same unrolling as test_hashes_s32
+template <int START>
 __device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
                                               uint32_t ih, uint32_t il, uint32_t k,
                                               const uint32_t* __restrict__ w32) {
+    static_assert(START >= 1 && START <= 4, "phase A runs 1..4 tests");
     auto test = [&](uint64_t loc) {
         const uint32_t bit = mod_m32(loc, m, ih, il);
         return (w32[bit >> 5] & (1u << (bit & 31u))) != 0u;
     };
-    if (!test(h0 + 2 * h3)) return false;
-    if (k > 3 && !test(h1 + 3 * h2)) return false;
+    // i = START is always needed (k > START); the others up to 3 depend on k
+    if (START <= 1 && !test(h1 + h3)) return false;
+    if (START <= 2 && (START == 2 || k > 2) && !test(h0 + 2 * h3)) return false;
+    if (START <= 3 && (START == 3 || k > 3) && !test(h1 + 3 * h2)) return false;
     uint64_t ih2 = 4 * h2, ih3 = 4 * h3;
     uint32_t i = 4;
     for (; i + 4 <= k; i += 4) {
@@ -325,14 +329,19 @@ __device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t
     return true;
 }
 
-template <int NA, int KPT>
-__global__ void __launch_bounds__(1024, 1)
+template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
+__global__ void __launch_bounds__((NA + NB) * 32, 1)
 probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
                      const uint64_t* __restrict__ words, const uint64_t* __restrict__ hashes,
                      const uint8_t* __restrict__ kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
-                     uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes) {
+                     uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes,
+                     uint64_t* __restrict__ trace, uint32_t trace_slots) {
     static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
-    constexpr uint32_t NB = 32 - NA;
+    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0, "shape");
+    // B warps work in teams of T; team g serves units g, g+NTEAMS, ...  The host guarantees
+    // n_stages % NTEAMS == 0: a team then revisits only its own stages, so it can never wait for a
+    // fill two phases ahead of a stage's mbarrier (parity waits alias beyond one phase).
+    constexpr uint32_t NTEAMS = NB / T;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* aready = full + kProbeMaxStages;
@@ -344,6 +353,10 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     const uint32_t warp = tid >> 5;
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
+    // optional timeline (profiling only), per CTA: [0] start; per unit it: [1+4it] unit resident (A warp 0),
+    // [2+4it] A warp 0 done, [3+4it] all A warps done (seen by the first B warp), [4+4it] released
+    uint64_t* tr = (TRACE && trace) ? trace + static_cast<size_t>(blockIdx.x) * trace_slots : nullptr;
+    if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
 
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) {
@@ -372,24 +385,28 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     uint8_t* st = stages;
     if (warp < NA) {
         // ------------------------------------------------------------ phase A ---
-        uint64_t l0[KPT], l1[KPT];
-        uint32_t f_off[KPT];  // byte offset of the key's StageFilter in the stage row; 0 = no key
+        uint64_t loc[KPT][NT];  // location(h, 0..NT-1) = h0, h1+h3, h0+2*h3, h1+3*h2
+        uint32_t f_off[KPT];    // byte offset of the key's StageFilter in the stage row; 0 = no key
 #pragma unroll
         for (int j = 0; j < KPT; ++j) {
             const uint32_t ql = (warp * KPT + j) * 32 + lane;
-            l0[j] = 0; l1[j] = 0; f_off[j] = 0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) loc[j][t] = 0;
+            f_off[j] = 0;
             if (ql < n_keys) {
                 const uint32_t q = key_base + ql;
                 const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
                 const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
-                l0[j] = a.x;
-                l1[j] = a.y + b.y;
+                const uint64_t l4[4] = {a.x, a.y + b.y, a.x + 2 * b.y, a.y + 3 * b.x};
+#pragma unroll
+                for (int t = 0; t < NT; ++t) loc[j][t] = l4[t];
                 f_off[j] = 32u + 32u * __ldg(&kinds[q]);
             }
         }
         const uint32_t lt_mask = (1u << lane) - 1u;
         for (uint32_t it = 0; it < my_count; ++it) {
             mbar_wait(&full[s], ph);
+            if (TRACE && tr && tid == 0 && 1 + 4 * it < trace_slots) tr[1 + 4 * it] = globaltimer_ns();
             uint32_t fin_bits[KPT], surv_bits[KPT];
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
@@ -401,14 +418,17 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                     } else {
                         const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + f_off[j] + 16);
                         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel);
-                        const uint32_t b0 = mod_m32(l0[j], f.x, f.z, f.w);
-                        const uint32_t b1 = mod_m32(l1[j], f.x, f.z, f.w);
-                        const uint32_t w0 = w32[b0 >> 5], w1 = w32[b1 >> 5];
-                        const bool p0 = ((w0 >> (b0 & 31u)) & 1u) | (f.y == 0u);
-                        const bool p1 = ((w1 >> (b1 & 31u)) & 1u) | (f.y <= 1u);
-                        const bool pass = p0 & p1;
-                        fin = pass & (f.y <= 2u);
-                        surv = pass & (f.y > 2u);
+                        uint32_t bit[NT], wv[NT];
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f.x, f.z, f.w);
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) wv[t] = w32[bit[t] >> 5];
+                        bool pass = true;
+#pragma unroll
+                        for (int t = 0; t < NT; ++t)  // location t exists only when t < k
+                            pass &= static_cast<bool>(((wv[t] >> (bit[t] & 31u)) & 1u) | (f.y <= static_cast<uint32_t>(t)));
+                        fin = pass & (f.y <= static_cast<uint32_t>(NT));
+                        surv = pass & (f.y > static_cast<uint32_t>(NT));
                     }
                 }
                 fin_bits[j] = __ballot_sync(0xffffffffu, fin);
@@ -419,16 +439,12 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             for (int j = 0; j < KPT; ++j) total += __popc(surv_bits[j]);
             uint32_t base = 0;
             if (lane == 0) {
-                uint4* row = reinterpret_cast<uint4*>(st + kStage2RowBitsOff) + (warp * KPT) / 4;
-                if constexpr (KPT == 4) {
-                    *row = make_uint4(fin_bits[0], fin_bits[1], fin_bits[2], fin_bits[3]);
-                } else {
-                    uint32_t* r32 = reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + warp * KPT;
+                uint32_t* r32 = reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + warp * KPT;
 #pragma unroll
-                    for (int j = 0; j < KPT; ++j) r32[j] = fin_bits[j];
-                }
+                for (int j = 0; j < KPT; ++j) r32[j] = fin_bits[j];
                 if (total) base = atomicAdd(reinterpret_cast<uint32_t*>(st + kStage2CntOff), total);
             }
+            __syncwarp();  // reconverge before the shuffle (else it takes the divergent slow path)
             if (total) {
                 base = __shfl_sync(0xffffffffu, base, 0);
                 uint16_t* queue = reinterpret_cast<uint16_t*>(st + kStage2QueueOff);
@@ -441,22 +457,28 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&aready[s]);  // release: row words + queue entries of this warp
+            if (TRACE && tr && tid == 0 && 2 + 4 * it < trace_slots) tr[2 + 4 * it] = globaltimer_ns();
             st += stage_bytes;
             if (++s == S) { s = 0; ph ^= 1u; st = stages; }
         }
     } else {
         // ------------------------------------------------------------ phase B ---
         const uint32_t wb = warp - NA;
+        const uint32_t team = wb / T, member = wb % T;
         const uint32_t out_words = (n_keys + 31) >> 5;
         uint32_t* out_base = matrix32 + (key_base >> 5);
-        for (uint32_t it = 0; it < my_count; ++it) {
+        s = team;
+        while (s >= S) { s -= S; ph ^= 1u; }
+        for (uint32_t it = team; it < my_count; it += NTEAMS) {
+            st = stages + static_cast<size_t>(s) * stage_bytes;
             mbar_wait(&full[s], ph);    // the bulk copy's bytes (async proxy) are visible
             mbar_wait(&aready[s], ph);  // every A warp has published its row words and survivors
+            if (TRACE && tr && member == 0 && lane == 0 && 3 + 4 * it < trace_slots) tr[3 + 4 * it] = globaltimer_ns();
             const uint32_t n = ld_volatile_shared_u32(st + kStage2CntOff);
             const uint32_t n_chunks = (n + 31) >> 5;
             const uint16_t* queue = reinterpret_cast<const uint16_t*>(st + kStage2QueueOff);
-            // rotate the first chunk over the B warps from unit to unit
-            for (uint32_t c = (wb + NB - (it % NB)) % NB; c < n_chunks; c += NB) {
+            // rotate the first chunk over the team's warps from unit to unit (even load per warp)
+            for (uint32_t c = (member + T - ((it / NTEAMS) % T)) % T; c < n_chunks; c += T) {
                 const uint32_t idx = c * 32 + lane;
                 if (idx < n) {
                     const uint32_t ql = queue[idx];
@@ -466,22 +488,24 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                     const uint32_t fo = 32u + 32u * __ldg(&kinds[q]);
                     const uint4 f = *reinterpret_cast<const uint4*>(st + fo);
                     const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + fo + 16);
-                    if (test_tail_s32(a.x, a.y, b.x, b.y, f.x, f.z, f.w, f.y,
-                                      reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel)))
+                    if (test_tail_s32<NT>(a.x, a.y, b.x, b.y, f.x, f.z, f.w, f.y,
+                                          reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel)))
                         atomicOr(reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + (ql >> 5), 1u << (ql & 31u));
                 }
             }
             __syncwarp();
             uint32_t last = 0;
-            if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == NB - 1;
+            if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == T - 1;
+            __syncwarp();  // reconverge before the shuffle
             last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {  // every warp is done with this stage: emit the row, reset, refill
+            if (last) {  // every warp of the team is done with this stage: emit the row, reset, refill
                 const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
                 if (lane < out_words)
                     out_base[static_cast<size_t>(unit) * row_words32 + lane] =
                         ld_volatile_shared_u32(st + kStage2RowBitsOff + 4 * lane);
                 __syncwarp();
                 if (lane == 0) {
+                    if (TRACE && tr && 4 + 4 * it < trace_slots) tr[4 + 4 * it] = globaltimer_ns();
                     done[s] = 0;
                     *reinterpret_cast<uint32_t*>(st + kStage2CntOff) = 0;
                     const uint32_t nxt = it + S;
@@ -495,21 +519,65 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                                    kProbeStage2HeaderBytes);
                     }
                 }
+                __syncwarp();
             }
-            st += stage_bytes;
-            if (++s == S) { s = 0; ph ^= 1u; st = stages; }
+            s += NTEAMS;
+            while (s >= S) { s -= S; ph ^= 1u; }
         }
     }
 }
+
+// The shapes kept for measurement (BSG_PROBE_VARIANT): <A warps, keys per A thread, A tests, B warps, B team size>
+template <int NA, int KPT, int NT, int NB, int T>
+static cudaError_t staged2_configure(int max_smem_optin) {
+    cudaError_t e = cudaFuncSetAttribute(probe_staged2_kernel<NA, KPT, NT, NB, T, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(probe_staged2_kernel<NA, KPT, NT, NB, T, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    if constexpr (T != NB) return staged2_configure<NA, KPT, NT, NB, NB>(max_smem_optin);
+    return cudaSuccess;
+}
+template <int NA, int KPT, int NT, int NB, int T>
+static void staged2_launch(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
+                           const uint32_t* d_n_list, const uint64_t* d_words, const uint64_t* d_hashes,
+                           const uint8_t* d_kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
+                           uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s, uint64_t* d_trace,
+                           uint32_t trace_slots) {
+    const uint32_t sb = kProbeStage2HeaderBytes + plan.stage_data_bytes;
+    constexpr uint32_t NTEAMS = NB / T;
+    uint32_t n_stages = static_cast<uint32_t>(plan.n_stages);
+    if constexpr (NTEAMS > 1) {
+        if (n_stages < NTEAMS) {  // ring too short for teams (large units): one team of all B warps
+            staged2_launch<NA, KPT, NT, NB, NB>(plan, d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base,
+                                                n_keys, kind_mask, d_matrix32, row_words32, s, d_trace, trace_slots);
+            return;
+        }
+        n_stages -= n_stages % NTEAMS;  // a team must own its stages (see the kernel)
+    }
+    if (d_trace)
+        probe_staged2_kernel<NA, KPT, NT, NB, T, true><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
+            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            n_stages, sb, d_trace, trace_slots);
+    else
+        probe_staged2_kernel<NA, KPT, NT, NB, T, false><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
+            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
+            n_stages, sb, nullptr, 0);
+}
+#define BSG_STAGED2_SHAPES(X)                                                                              \
+    X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4) \
+    X(6, 8, 4, 3, 24, 4) X(7, 16, 2, 3, 16, 8) X(8, 16, 2, 4, 16, 16)
 
 cudaError_t probe_staged_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(probe_staged_kernel<1024, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(probe_staged2_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+#define X(id, na, kpt, nt, nb, t) \
+    e = staged2_configure<na, kpt, nt, nb, t>(max_smem_optin); \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(probe_staged2_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (e != cudaSuccess) return e;
+    BSG_STAGED2_SHAPES(X)
+#undef X
     return cudaFuncSetAttribute(probe_staged_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 max_smem_optin);
 }
@@ -521,17 +589,15 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
                                 const uint32_t* d_n_list) {
     if ((n_list == 0 && !d_n_list) || n_keys == 0) return cudaSuccess;
     if (n_keys > kProbeMaxKeysPerPass) return cudaErrorInvalidValue;
-    if (plan.variant != 0 && !d_trace) {  // two-phase kernel: always 32 warps (NA phase-A + 32-NA phase-B)
-        const uint32_t sb = kProbeStage2HeaderBytes + plan.stage_data_bytes;
-        if (plan.variant == 2)
-            probe_staged2_kernel<8, 4><<<dim3(plan.grid), dim3(1024), plan.smem_bytes, s>>>(
-                d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32,
-                row_words32, static_cast<uint32_t>(plan.n_stages), sb);
-        else
-            probe_staged2_kernel<16, 2><<<dim3(plan.grid), dim3(1024), plan.smem_bytes, s>>>(
-                d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32,
-                row_words32, static_cast<uint32_t>(plan.n_stages), sb);
-        return cudaGetLastError();
+    switch (plan.variant) {  // two-phase kernel shapes
+#define X(id, na, kpt, nt, nb, t) \
+        case id: \
+            staged2_launch<na, kpt, nt, nb, t>(plan, d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, \
+                                            n_keys, kind_mask, d_matrix32, row_words32, s, d_trace, trace_slots); \
+            return cudaGetLastError();
+        BSG_STAGED2_SHAPES(X)
+#undef X
+        default: break;
     }
     const uint32_t stage_bytes = kProbeStageHeaderBytes + plan.stage_data_bytes;
     // one key per thread; at least 4 warps so a small batch still has some latency hiding

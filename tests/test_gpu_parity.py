@@ -767,11 +767,16 @@ def _units_with_fprs(unit_keys, fprs, absent=()):
     return desc, np.concatenate(chunks)
 
 
-@pytest.mark.parametrize("variant,stages", [(0, 0), (0, 2), (1, 0), (1, 2), (1, 1), (2, 0), (2, 3)])
-def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, monkeypatch):
-    """probe_staged (one phase) and probe_staged2 (phase A: locations 0-1 of every key, phase B:
-    locations 2..k-1 of the compacted survivors) must give the oracle's matrix for k = 1, 2, 3
-    (no phase-B work), k = 30, absent filters, keys present in every unit (survivor queue full),
+@pytest.mark.parametrize("variant,stages,n_units", [
+    (0, 0, 700), (0, 2, 700), (1, 0, 700), (1, 2, 700), (1, 1, 700), (2, 0, 700), (2, 3, 700),
+    # shapes whose B warps work in teams: rings that are a multiple of the team count (teams on, with
+    # refills), rings that are not (rounded down / one-team fallback)
+    (3, 0, 700), (3, 4, 700), (3, 1, 700), (3, 3, 700), (3, 7, 1300), (4, 0, 700), (4, 8, 2600), (4, 2, 700),
+    (5, 4, 700), (5, 3, 700), (6, 0, 700), (6, 6, 1900), (6, 1, 700), (7, 2, 700), (7, 5, 900), (8, 0, 700), (8, 2, 700)])
+def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, n_units, monkeypatch):
+    """probe_staged (one phase) and every shape of probe_staged2 (phase A: locations 0..NT-1 of every
+    key, phase B: locations NT..k-1 of the compacted survivors) must give the oracle's matrix for
+    k = 1..5 (k <= NT: no phase-B work), k = 30, absent filters, keys present in every unit (survivor queue full),
     1024-key passes + a ragged second pass, and rings of 1-3 stages so every CTA refills."""
     from tests.conftest import _has_gpu
     if not _has_gpu():
@@ -782,18 +787,17 @@ def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, mon
     rng = random.Random(4242 + variant)
     shared_tok = rand_keys(rng, 700, 2, 14)       # present in every unit
     shared_ft = rand_keys(rng, 500, 6, 24)
-    n_units = 700                                  # > 148 CTAs x 3 stages: refills even without the knob... (x16 not)
     unit_keys = []
     for u in range(n_units):
         unit_keys.append((rand_keys(rng, 6, 3, 9), shared_tok + rand_keys(rng, 40 + u % 50, 15, 20),
                           shared_ft + rand_keys(rng, 30 + u % 40, 25, 32)))
-    fprs = [0.6, 0.3, 0.2, 0.05, 0.001, 1e-9]
+    fprs = [0.6, 0.3, 0.2, 0.1, 0.05, 0.001, 1e-9]
     absent = {(5, 1), (6, 2), (7, 0), (8, 0), (8, 1), (8, 2), (n_units - 1, 1)}
     desc, words = _units_with_fprs(unit_keys, fprs, absent)
-    assert sorted({int(k) for k in desc["k"] if k}) [:3] == [1, 2, 3] and int(desc["k"].max()) == 30
+    assert sorted({int(k) for k in desc["k"] if k})[:5] == [1, 2, 3, 4, 5] and int(desc["k"].max()) == 30
     keys = shared_tok + shared_ft[:324]            # 1024 keys that pass everywhere: queue = 1024 survivors
     kinds = [1] * len(shared_tok) + [2] * 324
-    extra, extra_kinds = _mixed_keys(rng, unit_keys[:50], 300, 401)
+    extra, extra_kinds = _mixed_keys(rng, unit_keys[:50], 300, 401)  # present in few units + absent
     keys, kinds = keys + extra, kinds + extra_kinds
     assert len(keys) == 1725
     blob, off = N.pack_keys(keys)
@@ -807,7 +811,7 @@ def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, mon
             q.run(N.PROBE_STAGED)
             got, _ = q.fetch()
             q.close()
-            assert np.array_equal(got, want), f"variant {variant} stages {stages}"
+            assert np.array_equal(got, want), f"variant {variant} stages {stages} units {n_units}"
         # first 1024 keys pass in every unit that has the filter (no false negatives)
         bits = bs.unpack_matrix(want, len(keys))
         assert bits[:, :1024].all()
