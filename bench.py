@@ -39,9 +39,8 @@ N_KEYS = 1000
 TRAFFIC_NCU = {"2b": 70.96e6, "2a": 76.16e6}
 L2_BYTES = 126 * 1024 * 1024
 # the staged probe kernel the library launches (BSG_PROBE_VARIANT: 0 = one phase, 1/2 = two phases)
-_SHAPES = {"1": "16,2,2,16,16", "2": "16,2,3,16,16", "3": "16,2,3,16,4", "4": "16,2,3,16,2", "5": "16,2,4,16,4",
-           "6": "8,4,3,24,4", "7": "16,2,3,16,8", "8": "16,2,4,16,16"}
-_V = os.environ.get("BSG_PROBE_VARIANT", "1")
+_SHAPES = {"1": "16,2,2,16,16", "2": "16,2,3,16,16", "3": "16,2,3,16,4", "4": "16,2,3,16,2", "5": "16,2,4,16,4"}
+_V = os.environ.get("BSG_PROBE_VARIANT", "3")
 PROBE_KERNEL = "probe_staged_kernel" if _V == "0" else f"probe_staged2_kernel<{_SHAPES[_V]}>"
 
 

@@ -83,7 +83,7 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int probe_variant = 1; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1/2 = probe_staged2 (two phases)
+    int probe_variant = 3; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2 (two phases)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
@@ -141,7 +141,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(8, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
     *out = ctx;
     return BSG_OK;
 }

@@ -86,7 +86,7 @@ struct ProbeStagedPlan {
     int grid;
     int warps;            // 0 = auto
     uint32_t stagger_ns;  // delay between the prologue's stage fills (0 = none)
-    int variant;          // 0 = probe_staged (one phase), 1 = probe_staged2<16,2>, 2 = probe_staged2<8,4>
+    int variant;          // 0 = probe_staged (one phase), 1..5 = probe_staged2 shapes (kernels_probe.cu)
 };
 cudaError_t probe_staged_configure(int max_smem_optin);
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,

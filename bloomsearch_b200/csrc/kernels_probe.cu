@@ -299,33 +299,38 @@ __device__ __forceinline__ uint32_t ld_volatile_shared_u32(const void* p) {
     return v;
 }
 
-// locations START..k-1 of a survivor (k > START, START in 1..4); same unrolling as test_hashes_s32
+// locations START..k-1 of a survivor (k > START, START in 1..4), in groups of up to four locations:
+// the tests of a group are independent (no branch between them -> ILP 4, the dependent chain of a
+// test is ~14 instructions + one shared-memory load), the early exit sits between groups.  A warp
+// runs until its slowest lane is done anyway, so testing a whole group costs no extra issue slots
+// but a quarter of the latency.  location(i): i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2.
+// A location index >= k is computed but masked out (its bit index is < m, the load is in bounds).
 template <int START>
 __device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
                                               uint32_t ih, uint32_t il, uint32_t k,
                                               const uint32_t* __restrict__ w32) {
     static_assert(START >= 1 && START <= 4, "phase A runs 1..4 tests");
-    auto test = [&](uint64_t loc) {
+    auto probe = [&](uint64_t loc) -> uint32_t {
         const uint32_t bit = mod_m32(loc, m, ih, il);
-        return (w32[bit >> 5] & (1u << (bit & 31u))) != 0u;
+        return (w32[bit >> 5] >> (bit & 31u)) & 1u;
     };
-    // i = START is always needed (k > START); the others up to 3 depend on k
-    if (START <= 1 && !test(h1 + h3)) return false;
-    if (START <= 2 && (START == 2 || k > 2) && !test(h0 + 2 * h3)) return false;
-    if (START <= 3 && (START == 3 || k > 3) && !test(h1 + 3 * h2)) return false;
-    uint64_t ih2 = 4 * h2, ih3 = 4 * h3;
-    uint32_t i = 4;
-    for (; i + 4 <= k; i += 4) {
-        if (!test(h0 + ih2)) return false;
-        if (!test(h1 + ih3 + h3)) return false;
-        if (!test(h0 + ih3 + 2 * h3)) return false;
-        if (!test(h1 + ih2 + 3 * h2)) return false;
+    if (START < 4) {  // first group: locations START..3
+        uint32_t ok = 1u;
+        if (START <= 1) ok &= probe(h1 + h3);
+        if (START <= 2) ok &= probe(h0 + 2 * h3) | static_cast<uint32_t>(k <= 2u);
+        if (START <= 3) ok &= probe(h1 + 3 * h2) | static_cast<uint32_t>(k <= 3u);
+        if (!ok) return false;
+    }
+    uint64_t ih2 = 4 * h2, ih3 = 4 * h3;  // i*h2, i*h3 at i = 4, 8, ...
+    for (uint32_t i = 4; i < k; i += 4) {
+        uint32_t ok = probe(h0 + ih2);
+        ok &= probe(h1 + ih3 + h3) | static_cast<uint32_t>(i + 1 >= k);
+        ok &= probe(h0 + ih3 + 2 * h3) | static_cast<uint32_t>(i + 2 >= k);
+        ok &= probe(h1 + ih2 + 3 * h2) | static_cast<uint32_t>(i + 3 >= k);
+        if (!ok) return false;
         ih2 += 4 * h2;
         ih3 += 4 * h3;
     }
-    if (i < k && !test(h0 + ih2)) return false;
-    if (i + 1 < k && !test(h1 + ih3 + h3)) return false;
-    if (i + 2 < k && !test(h0 + ih3 + 2 * h3)) return false;
     return true;
 }
 
@@ -353,8 +358,9 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     const uint32_t warp = tid >> 5;
     const uint32_t G = gridDim.x;
     const uint32_t S = n_stages;
-    // optional timeline (profiling only), per CTA: [0] start; per unit it: [1+4it] unit resident (A warp 0),
-    // [2+4it] A warp 0 done, [3+4it] all A warps done (seen by the first B warp), [4+4it] released
+    // optional timeline (profiling only), per CTA: [0] start; per unit it: [1+8it] unit resident (A warp 0),
+    // [2+8it] A warp 0 done, [3+8it] all A warps done (seen by the first B warp), [4+8it] released,
+    // [5+8it] chunk 0: survivor hashes loaded, [6+8it] chunk 0 tested, [7+8it] B warp 0 arrived on the counter
     uint64_t* tr = (TRACE && trace) ? trace + static_cast<size_t>(blockIdx.x) * trace_slots : nullptr;
     if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
 
@@ -406,7 +412,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
         const uint32_t lt_mask = (1u << lane) - 1u;
         for (uint32_t it = 0; it < my_count; ++it) {
             mbar_wait(&full[s], ph);
-            if (TRACE && tr && tid == 0 && 1 + 4 * it < trace_slots) tr[1 + 4 * it] = globaltimer_ns();
+            if (TRACE && tr && tid == 0 && 1 + 8 * it < trace_slots) tr[1 + 8 * it] = globaltimer_ns();
             uint32_t fin_bits[KPT], surv_bits[KPT];
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
@@ -457,7 +463,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&aready[s]);  // release: row words + queue entries of this warp
-            if (TRACE && tr && tid == 0 && 2 + 4 * it < trace_slots) tr[2 + 4 * it] = globaltimer_ns();
+            if (TRACE && tr && tid == 0 && 2 + 8 * it < trace_slots) tr[2 + 8 * it] = globaltimer_ns();
             st += stage_bytes;
             if (++s == S) { s = 0; ph ^= 1u; st = stages; }
         }
@@ -473,7 +479,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             st = stages + static_cast<size_t>(s) * stage_bytes;
             mbar_wait(&full[s], ph);    // the bulk copy's bytes (async proxy) are visible
             mbar_wait(&aready[s], ph);  // every A warp has published its row words and survivors
-            if (TRACE && tr && member == 0 && lane == 0 && 3 + 4 * it < trace_slots) tr[3 + 4 * it] = globaltimer_ns();
+            if (TRACE && tr && member == 0 && lane == 0 && 3 + 8 * it < trace_slots) tr[3 + 8 * it] = globaltimer_ns();
             const uint32_t n = ld_volatile_shared_u32(st + kStage2CntOff);
             const uint32_t n_chunks = (n + 31) >> 5;
             const uint16_t* queue = reinterpret_cast<const uint16_t*>(st + kStage2QueueOff);
@@ -486,17 +492,22 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                     const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
                     const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
                     const uint32_t fo = 32u + 32u * __ldg(&kinds[q]);
+                    if (TRACE && tr && c == 0 && lane == 0 && 5 + 8 * it < trace_slots)
+                        tr[5 + 8 * it] = globaltimer_ns() + ((a.x ^ b.y ^ fo) == 0x123456789abcull);  // hashes arrived
                     const uint4 f = *reinterpret_cast<const uint4*>(st + fo);
                     const uint32_t rel = *reinterpret_cast<const uint32_t*>(st + fo + 16);
                     if (test_tail_s32<NT>(a.x, a.y, b.x, b.y, f.x, f.z, f.w, f.y,
                                           reinterpret_cast<const uint32_t*>(st + kProbeStage2HeaderBytes + rel)))
                         atomicOr(reinterpret_cast<uint32_t*>(st + kStage2RowBitsOff) + (ql >> 5), 1u << (ql & 31u));
                 }
+                __syncwarp();
+                if (TRACE && tr && c == 0 && lane == 0 && 6 + 8 * it < trace_slots) tr[6 + 8 * it] = globaltimer_ns();  // chunk 0 tested
             }
             __syncwarp();
             uint32_t last = 0;
             if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == T - 1;
             __syncwarp();  // reconverge before the shuffle
+            if (TRACE && tr && member == 0 && lane == 0 && 7 + 8 * it < trace_slots) tr[7 + 8 * it] = globaltimer_ns();
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {  // every warp of the team is done with this stage: emit the row, reset, refill
                 const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
@@ -505,7 +516,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                         ld_volatile_shared_u32(st + kStage2RowBitsOff + 4 * lane);
                 __syncwarp();
                 if (lane == 0) {
-                    if (TRACE && tr && 4 + 4 * it < trace_slots) tr[4 + 4 * it] = globaltimer_ns();
+                    if (TRACE && tr && 4 + 8 * it < trace_slots) tr[4 + 8 * it] = globaltimer_ns();
                     done[s] = 0;
                     *reinterpret_cast<uint32_t*>(st + kStage2CntOff) = 0;
                     const uint32_t nxt = it + S;
@@ -527,7 +538,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     }
 }
 
-// The shapes kept for measurement (BSG_PROBE_VARIANT): <A warps, keys per A thread, A tests, B warps, B team size>
+// The shapes kept for measurement (BSG_PROBE_VARIANT): <A warps, keys per A thread, A tests, B warps, B team size>;
+// 3 is the default (api.cu), the others are kept for the parity test and for measurement
 template <int NA, int KPT, int NT, int NB, int T>
 static cudaError_t staged2_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(probe_staged2_kernel<NA, KPT, NT, NB, T, false>,
@@ -565,9 +577,8 @@ static void staged2_launch(const ProbeStagedPlan& plan, const StageRow* d_stab, 
             d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
             n_stages, sb, nullptr, 0);
 }
-#define BSG_STAGED2_SHAPES(X)                                                                              \
-    X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4) \
-    X(6, 8, 4, 3, 24, 4) X(7, 16, 2, 3, 16, 8) X(8, 16, 2, 4, 16, 16)
+#define BSG_STAGED2_SHAPES(X)                                                                          \
+    X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4)
 
 cudaError_t probe_staged_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(probe_staged_kernel<1024, false>,

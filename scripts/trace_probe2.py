@@ -21,7 +21,8 @@ for i in range(8):
     qs[i % 4].run(N.PROBE_AUTO | N.RUN_MATRIX_ONLY)
 ctx.synchronize()
 L = N.lib()
-slots = 4 * 80 + 1 if wl == "2a" else 65
+W = 8
+slots = W * 80 + 1 if wl == "2a" else W * 16 + 1
 L.bsg_debug_trace_enable.argtypes = [C.c_void_p, C.c_uint32]
 L.bsg_debug_trace_read.argtypes = [C.c_void_p, C.c_void_p]
 N.check(L.bsg_debug_trace_enable(ctx.handle, slots))
@@ -35,17 +36,19 @@ rel = (out.astype(np.int64) - int(t0)) / 1e3
 rel[out == 0] = np.nan
 np.set_printoptions(precision=2, suppress=True, linewidth=220)
 print("workload", wl, "variant", os.environ.get("BSG_PROBE_VARIANT", "1"), "start spread us", np.nanmin(rel[:, 0]), np.nanmax(rel[:, 0]))
-n_it = min((slots - 1) // 4, 10)
-names = ["resident", "A0 done ", "A done  ", "released"]
-for cta in (0, 1, 73, 147):
+n_it = min((slots - 1) // W, 10)
+names = ["resident", "A0 done ", "A done  ", "released", "c0 hashes", "c0 tested", "B0 arrived"]
+for cta in (0, 73):
     for j, nm in enumerate(names):
-        print("cta", cta, nm, rel[cta, 1 + j:1 + j + 4 * n_it:4])
+        print("cta", cta, nm, rel[cta, 1 + j:1 + j + W * n_it:W])
 ends = np.nanmax(rel, axis=1)
 print("end per CTA: min %.1f median %.1f max %.1f us" % (np.nanmin(ends), np.nanmedian(ends), np.nanmax(ends)))
 for j, nm in enumerate(names):
-    print("mean", nm, "per it:", np.nanmean(rel[:, 1 + j:1 + j + 4 * n_it:4], axis=0))
-d_a = rel[:, 3::4] - rel[:, 1::4]
-d_b = rel[:, 4::4] - rel[:, 3::4]
-d_p = np.diff(rel[:, 1::4], axis=1)
+    print("mean", nm, "per it:", np.nanmean(rel[:, 1 + j:1 + j + W * n_it:W], axis=0))
+d_a = rel[:, 3::W] - rel[:, 1::W]
+d_b = rel[:, 4::W] - rel[:, 3::W]
+d_p = np.diff(rel[:, 1::W], axis=1)
+print("chunk 0: A done -> hashes loaded %.2f us; hashes -> tested %.2f us; B warp 0: A done -> arrived %.2f us"
+      % (np.nanmean(rel[:, 5::W] - rel[:, 3::W]), np.nanmean(rel[:, 6::W] - rel[:, 5::W]), np.nanmean(rel[:, 7::W] - rel[:, 3::W])))
 print("mean A latency (resident -> all A done) %.2f us; B latency (A done -> released) %.2f us; period %.2f us"
       % (np.nanmean(d_a), np.nanmean(d_b), np.nanmean(d_p)))

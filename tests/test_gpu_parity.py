@@ -772,7 +772,7 @@ def _units_with_fprs(unit_keys, fprs, absent=()):
     # shapes whose B warps work in teams: rings that are a multiple of the team count (teams on, with
     # refills), rings that are not (rounded down / one-team fallback)
     (3, 0, 700), (3, 4, 700), (3, 1, 700), (3, 3, 700), (3, 7, 1300), (4, 0, 700), (4, 8, 2600), (4, 2, 700),
-    (5, 4, 700), (5, 3, 700), (6, 0, 700), (6, 6, 1900), (6, 1, 700), (7, 2, 700), (7, 5, 900), (8, 0, 700), (8, 2, 700)])
+    (5, 0, 700), (5, 4, 700), (5, 3, 700)])
 def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, n_units, monkeypatch):
     """probe_staged (one phase) and every shape of probe_staged2 (phase A: locations 0..NT-1 of every
     key, phase B: locations NT..k-1 of the compacted survivors) must give the oracle's matrix for
