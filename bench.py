@@ -35,8 +35,8 @@ WORKLOADS = {
 FPR = 0.001
 N_KEYS = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum per probe_staged launch from the committed
-# `ncu --set full` captures (profiles/): 2b 70.52 MB + 0.44 MB, 2a 74.92 MB + 1.24 MB
-TRAFFIC_NCU = {"2b": 70.96e6, "2a": 76.16e6}
+# `ncu --set full` captures (profiles/r01_ncu_full_*_staged2_raw.csv): 2b 70.52 MB + 0.86 MB, 2a 74.93 MB + 1.55 MB
+TRAFFIC_NCU = {"2b": 71.38e6, "2a": 76.48e6}
 L2_BYTES = 126 * 1024 * 1024
 # the staged probe kernel the library launches (BSG_PROBE_VARIANT: 0 = one phase, 1/2 = two phases)
 _SHAPES = {"1": "16,2,2,16,16", "2": "16,2,3,16,16", "3": "16,2,3,16,4", "4": "16,2,3,16,2", "5": "16,2,4,16,4"}

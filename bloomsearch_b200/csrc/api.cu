@@ -84,6 +84,7 @@ struct bsg_ctx {
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
     int probe_variant = 3; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2 (two phases)
+    int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
 
@@ -142,6 +143,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
     return BSG_OK;
 }
@@ -1173,6 +1175,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         if (use_staged) {
             ProbeStagedPlan plan;
             plan.variant = ctx->probe_variant;
+            plan.relax_sleep_ns = static_cast<uint32_t>(ctx->relax_sleep_ns);
             const uint64_t prefix = plan.variant ? kProbe2SmemPrefixBytes : kProbeSmemPrefixBytes;
             const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - prefix;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);

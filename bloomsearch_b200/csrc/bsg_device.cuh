@@ -241,6 +241,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Wait of a warp that expects to wait long (phase-B warps waiting for phase A): try_wait with a
+// suspend-time hint, and a short sleep between polls, so the poll loop does not eat the issue slots
+// of the warps it is waiting for (measured: 16 % of all issued instructions were this loop).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns, uint32_t sleep_ns) {
+    uint32_t ok = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (ok) break;
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); size and both
 // addresses must be multiples of 16 bytes.  Completion is signalled on `bar`.
 __device__ __forceinline__ uint64_t globaltimer_ns() {

@@ -340,7 +340,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                      const uint64_t* __restrict__ words, const uint64_t* __restrict__ hashes,
                      const uint8_t* __restrict__ kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
                      uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes,
-                     uint64_t* __restrict__ trace, uint32_t trace_slots) {
+                     uint32_t relax_sleep_ns, uint64_t* __restrict__ trace, uint32_t trace_slots) {
     static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
     static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0, "shape");
     // B warps work in teams of T; team g serves units g, g+NTEAMS, ...  The host guarantees
@@ -478,7 +478,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
         for (uint32_t it = team; it < my_count; it += NTEAMS) {
             st = stages + static_cast<size_t>(s) * stage_bytes;
             mbar_wait(&full[s], ph);    // the bulk copy's bytes (async proxy) are visible
-            mbar_wait(&aready[s], ph);  // every A warp has published its row words and survivors
+            // every A warp has published its row words and survivors (usually the long wait of a B warp)
+            mbar_wait_relaxed(&aready[s], ph, 1000u, relax_sleep_ns);
             if (TRACE && tr && member == 0 && lane == 0 && 3 + 8 * it < trace_slots) tr[3 + 8 * it] = globaltimer_ns();
             const uint32_t n = ld_volatile_shared_u32(st + kStage2CntOff);
             const uint32_t n_chunks = (n + 31) >> 5;
@@ -571,11 +572,11 @@ static void staged2_launch(const ProbeStagedPlan& plan, const StageRow* d_stab, 
     if (d_trace)
         probe_staged2_kernel<NA, KPT, NT, NB, T, true><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
             d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            n_stages, sb, d_trace, trace_slots);
+            n_stages, sb, plan.relax_sleep_ns, d_trace, trace_slots);
     else
         probe_staged2_kernel<NA, KPT, NT, NB, T, false><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
             d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            n_stages, sb, nullptr, 0);
+            n_stages, sb, plan.relax_sleep_ns, nullptr, 0);
 }
 #define BSG_STAGED2_SHAPES(X)                                                                          \
     X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4)
