@@ -374,6 +374,7 @@ def main():
                     "traffic": TRAFFIC_NCU.get(wl), "kernel": PROBE_KERNEL, "kernel_ms": k_ms,
                     "kernel_ms_single_stream": ms_single, "frac_single_stream": algo_bytes / (ms_single / 1e3) / 1e9 / peak,
                     "launch_streams": args.streams,
+                    "programmatic_dependent_launch": os.environ.get("BSG_PROBE_PDL", "1") != "0",
                     "algorithmic_bytes_per_launch": algo_bytes,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
 

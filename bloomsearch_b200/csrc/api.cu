@@ -84,6 +84,7 @@ struct bsg_ctx {
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
     int probe_variant = 3; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2 (two phases)
+    int pdl = 1;           // BSG_PROBE_PDL: programmatic dependent launch of the two-phase probe kernel
     int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
 };
@@ -143,6 +144,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
     return BSG_OK;
@@ -954,6 +956,15 @@ struct bsg_query {
     // results come down into it, then are memcpy'd to the caller's (pageable) buffers
     uint8_t* h_pin = nullptr;
     size_t cap_pin = 0;
+    // device mirror of the pinned input block [keys + pad][offsets][kinds][program]: the bsg_probe
+    // path uploads a batch with ONE async copy; k_* are the pointers the kernels read (they alias
+    // d_in on that path, the separately owned buffers on the bsg_query_create path)
+    uint8_t* d_in = nullptr;
+    size_t cap_in = 0;
+    const uint8_t* k_keys = nullptr;
+    const uint64_t* k_key_off = nullptr;
+    const uint8_t* k_kinds = nullptr;
+    const bsg_expr_op* k_prog = nullptr;
     // hierarchical probes: stage rows of the units whose parent survived + their count
     StageRow* d_rows = nullptr;
     size_t cap_rows = 0;
@@ -987,6 +998,7 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_matrix32);
     cudaFree(q->d_mask32);
     if (q->h_pin) cudaFreeHost(q->h_pin);
+    cudaFree(q->d_in);
     cudaFree(q->d_rows);
     cudaFree(q->d_n_rows);
     delete q;
@@ -1057,11 +1069,13 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
     const uint64_t matrix_words32 = std::max<uint64_t>(q->n_units * q->row_words32, 1);
     const uint64_t mask_words32 = std::max<uint64_t>(2 * ((q->n_units + 63) / 64), 1);
     const size_t cap_matrix_before = q->cap_matrix, cap_mask_before = q->cap_mask;
-    CUDA_TRY(ensure_cap(q->d_keys, q->cap_keys, nbytes + kKeyPad));
-    CUDA_TRY(ensure_cap(q->d_key_off, q->cap_key_off, (static_cast<uint64_t>(n_keys) + 1) * 8));
-    CUDA_TRY(ensure_cap(q->d_kinds, q->cap_kinds, std::max<uint32_t>(n_keys, 1)));
+    if (!use_pinned) {
+        CUDA_TRY(ensure_cap(q->d_keys, q->cap_keys, nbytes + kKeyPad));
+        CUDA_TRY(ensure_cap(q->d_key_off, q->cap_key_off, (static_cast<uint64_t>(n_keys) + 1) * 8));
+        CUDA_TRY(ensure_cap(q->d_kinds, q->cap_kinds, std::max<uint32_t>(n_keys, 1)));
+        CUDA_TRY(ensure_cap(q->d_prog, q->cap_prog, std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
+    }
     CUDA_TRY(ensure_cap(q->d_hashes, q->cap_hashes, std::max<uint64_t>(n_keys, 1) * 32));
-    CUDA_TRY(ensure_cap(q->d_prog, q->cap_prog, std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
     CUDA_TRY(ensure_cap(q->d_matrix32, q->cap_matrix, matrix_words32 * 4));
     CUDA_TRY(ensure_cap(q->d_mask32, q->cap_mask, mask_words32 * 4));
     // The kernels overwrite every word that carries a key / unit; pad words are never written, so
@@ -1077,16 +1091,13 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         q->zeroed_row_words32 = q->row_words32;
         q->zeroed_groups = groups;
     }
-    const uint8_t* src_keys = keys;
-    const uint64_t* src_off = key_off;
-    const uint8_t* src_kinds = key_kind;
-    const bsg_expr_op* src_prog = prog;
     if (use_pinned) {
-        // one pinned block: [keys + pad][offsets][kinds][program]
+        // one pinned block [keys + pad][offsets][kinds][program], mirrored on the device: ONE async copy
         const size_t o_off = (nbytes + kKeyPad + 15) & ~size_t(15);
         const size_t o_kind = o_off + (static_cast<size_t>(n_keys) + 1) * 8;
         const size_t o_prog = (o_kind + n_keys + 15) & ~size_t(15);
-        const size_t need = o_prog + static_cast<size_t>(prog_len) * sizeof(bsg_expr_op) + 16;
+        const size_t used = o_prog + static_cast<size_t>(prog_len) * sizeof(bsg_expr_op);
+        const size_t need = used + 16;
         if (need > q->cap_pin) {
             if (q->h_pin) cudaFreeHost(q->h_pin);
             q->h_pin = nullptr;
@@ -1094,28 +1105,33 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
             CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&q->h_pin), need * 2, cudaHostAllocDefault));
             q->cap_pin = need * 2;
         }
+        CUDA_TRY(ensure_cap(q->d_in, q->cap_in, need));
         if (nbytes) memcpy(q->h_pin, keys, nbytes);
-        memset(q->h_pin + nbytes, 0, kKeyPad);
+        memset(q->h_pin + nbytes, 0, o_off - nbytes);
         if (n_keys) {
             memcpy(q->h_pin + o_off, key_off, (static_cast<size_t>(n_keys) + 1) * 8);
             memcpy(q->h_pin + o_kind, key_kind, n_keys);
         }
         if (prog_len) memcpy(q->h_pin + o_prog, prog, prog_len * sizeof(bsg_expr_op));
-        src_keys = q->h_pin;
-        src_off = reinterpret_cast<const uint64_t*>(q->h_pin + o_off);
-        src_kinds = q->h_pin + o_kind;
-        src_prog = reinterpret_cast<const bsg_expr_op*>(q->h_pin + o_prog);
-        CUDA_TRY(cudaMemcpyAsync(q->d_keys, src_keys, nbytes + kKeyPad, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(q->d_in, q->h_pin, used, cudaMemcpyHostToDevice, s));
+        q->k_keys = q->d_in;
+        q->k_key_off = reinterpret_cast<const uint64_t*>(q->d_in + o_off);
+        q->k_kinds = q->d_in + o_kind;
+        q->k_prog = reinterpret_cast<const bsg_expr_op*>(q->d_in + o_prog);
     } else {
         CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
-        if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, src_keys, nbytes, cudaMemcpyHostToDevice, s));
+        if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
+        if (n_keys) {
+            CUDA_TRY(cudaMemcpyAsync(q->d_key_off, key_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
+        }
+        if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+        q->k_keys = q->d_keys;
+        q->k_key_off = q->d_key_off;
+        q->k_kinds = q->d_kinds;
+        q->k_prog = q->d_prog;
     }
-    if (n_keys) {
-        CUDA_TRY(cudaMemcpyAsync(q->d_key_off, src_off, (static_cast<uint64_t>(n_keys) + 1) * 8, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(q->d_kinds, src_kinds, n_keys, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(launch_hash_keys(q->d_keys, q->d_key_off, n_keys, q->d_hashes, s));
-    }
-    if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, src_prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+    if (n_keys) CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, n_keys, q->d_hashes, s));
     return BSG_OK;
 }
 
@@ -1176,6 +1192,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             ProbeStagedPlan plan;
             plan.variant = ctx->probe_variant;
             plan.relax_sleep_ns = static_cast<uint32_t>(ctx->relax_sleep_ns);
+            plan.pdl = ctx->pdl;
             const uint64_t prefix = plan.variant ? kProbe2SmemPrefixBytes : kProbeSmemPrefixBytes;
             const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - prefix;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);
@@ -1206,27 +1223,27 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             }
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
-                CUDA_TRY(launch_probe_staged(plan, rows, c->n_staged, c->d_words, q->d_hashes, q->d_kinds, kb, nk,
+                CUDA_TRY(launch_probe_staged(plan, rows, c->n_staged, c->d_words, q->d_hashes, q->k_kinds, kb, nk,
                                              q->kind_mask, q->d_matrix32, q->row_words32, s, ctx->d_trace,
                                              ctx->trace_slots, d_n_rows));
                 ++launches;
             }
         } else if (c->n_staged) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_staged_list, c->n_staged, q->d_hashes,
-                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         q->k_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
                                          d_parent_mask32));
             ++launches;
         }
         if (c->n_gather) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_gather_list, c->n_gather, q->d_hashes,
-                                         q->d_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         q->k_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
                                          d_parent_mask32));
             ++launches;
         }
     }
     if (c->n_units && !matrix_only) {
         if (q->prog_len) {
-            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->d_prog, q->prog_len, q->d_mask32, s,
+            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->k_prog, q->prog_len, q->d_mask32, s,
                                       d_parent, d_parent_mask32));
         } else if (d_parent) {
             CUDA_TRY(launch_parent_mask(q->d_mask32, c->n_units, d_parent, d_parent_mask32, s));

@@ -10,6 +10,7 @@ namespace bsg {
 __global__ void __launch_bounds__(256)
 hash_keys_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off, uint64_t n_keys,
                  uint64_t* __restrict__ hashes) {
+    griddep_launch_dependents();  // PDL: the probe kernel of this batch may start filling its ring now
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_keys) return;
     const uint64_t b = __ldg(&key_off[i]), e = __ldg(&key_off[i + 1]);

@@ -375,6 +375,10 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     }
     __syncthreads();
 
+    // PDL: the ring's first fills read only the immutable corpus, so they may overlap the tail of the
+    // previous kernel in the stream (the hash kernel of this batch, or the previous batch's probe);
+    // everything the predecessor wrote (hashes, the compacted unit list) is touched after the wait.
+    if (n_list_dev) griddep_wait();
     const uint32_t n_list = n_list_dev ? __ldg(n_list_dev) : n_list_host;
     const uint32_t my_count = n_list > blockIdx.x ? (n_list - blockIdx.x + G - 1) / G : 0;
 
@@ -386,6 +390,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
         fill_stage(stages + static_cast<size_t>(lane) * stage_bytes, &full[lane], stab, li, lane + S < my_count,
                    li + S * G, words, word_base, b.x, b.y, b.z, kind_mask, kProbeStage2HeaderBytes);
     }
+    griddep_launch_dependents();
+    if (!n_list_dev) griddep_wait();
 
     uint32_t s = 0, ph = 0;
     uint8_t* st = stages;
@@ -569,14 +575,26 @@ static void staged2_launch(const ProbeStagedPlan& plan, const StageRow* d_stab, 
         }
         n_stages -= n_stages % NTEAMS;  // a team must own its stages (see the kernel)
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3((NA + NB) * 32);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = plan.pdl ? 1 : 0;
+    uint64_t* tr = d_trace;
+    uint32_t ts = d_trace ? trace_slots : 0;
     if (d_trace)
-        probe_staged2_kernel<NA, KPT, NT, NB, T, true><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
-            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            n_stages, sb, plan.relax_sleep_ns, d_trace, trace_slots);
+        cudaLaunchKernelEx(&cfg, probe_staged2_kernel<NA, KPT, NT, NB, T, true>, d_stab, n_list, d_n_list, d_words, d_hashes,
+                           d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32, n_stages, sb,
+                           plan.relax_sleep_ns, tr, ts);
     else
-        probe_staged2_kernel<NA, KPT, NT, NB, T, false><<<dim3(plan.grid), dim3((NA + NB) * 32), plan.smem_bytes, s>>>(
-            d_stab, n_list, d_n_list, d_words, d_hashes, d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32,
-            n_stages, sb, plan.relax_sleep_ns, nullptr, 0);
+        cudaLaunchKernelEx(&cfg, probe_staged2_kernel<NA, KPT, NT, NB, T, false>, d_stab, n_list, d_n_list, d_words, d_hashes,
+                           d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32, n_stages, sb,
+                           plan.relax_sleep_ns, tr, ts);
 }
 #define BSG_STAGED2_SHAPES(X)                                                                          \
     X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4)
