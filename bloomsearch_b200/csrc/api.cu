@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -84,6 +86,10 @@ struct bsg_ctx {
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
     int probe_variant = 3; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2 (two phases)
+    // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
+    int timing = 0;
+    std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
+    int zero_copy = 1;     // BSG_PROBE_ZEROCOPY: bsg_probe() matrix rows written straight to pinned host memory
     int pdl = 1;           // BSG_PROBE_PDL: programmatic dependent launch of the two-phase probe kernel
     int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
     int stagger_pct = -1;  // BSG_PROBE_STAGGER: % of the one-stage-per-SM stream time between prologue fills
@@ -145,6 +151,8 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
     if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
+    if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
+    if (const char* w = getenv("BSG_PROBE_ZEROCOPY")) ctx->zero_copy = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
     return BSG_OK;
@@ -152,6 +160,12 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
 
 extern "C" void bsg_destroy(bsg_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->timing && ctx->t_calls) {
+        const double n = static_cast<double>(ctx->t_calls.load()) * 1e3;
+        fprintf(stderr, "[bsg] bsg_probe host phases over %llu calls (us/call): prepare+enqueue H2D/hash %.1f, enqueue probe %.1f, "
+                        "enqueue D2H + wait %.1f, copy out %.1f\n", (unsigned long long)ctx->t_calls.load(),
+                ctx->t_prepare / n, ctx->t_run / n, ctx->t_wait / n, ctx->t_copyout / n);
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
@@ -965,6 +979,15 @@ struct bsg_query {
     const uint64_t* k_key_off = nullptr;
     const uint8_t* k_kinds = nullptr;
     const bsg_expr_op* k_prog = nullptr;
+    // where the probe kernels write the (unit x key) matrix: d_matrix32, or — bsg_probe() without a
+    // mask — the pinned host block h_out (zero copy: rows cross PCIe as posted writes while the
+    // kernel runs, no D2H copy operation after it)
+    uint32_t* k_matrix = nullptr;
+    uint32_t* h_out = nullptr;
+    uint32_t* h_out_dev = nullptr;
+    size_t cap_out = 0;
+    uint64_t out_units = ~0ull;
+    uint32_t out_row_words32 = ~0u, out_groups = ~0u;
     // hierarchical probes: stage rows of the units whose parent survived + their count
     StageRow* d_rows = nullptr;
     size_t cap_rows = 0;
@@ -998,6 +1021,7 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_matrix32);
     cudaFree(q->d_mask32);
     if (q->h_pin) cudaFreeHost(q->h_pin);
+    if (q->h_out) cudaFreeHost(q->h_out);
     cudaFree(q->d_in);
     cudaFree(q->d_rows);
     cudaFree(q->d_n_rows);
@@ -1132,6 +1156,30 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         q->k_prog = q->d_prog;
     }
     if (n_keys) CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, n_keys, q->d_hashes, s));
+    q->k_matrix = q->d_matrix32;
+    return BSG_OK;
+}
+
+// bsg_probe() without a mask: let the probe kernels write the matrix straight into pinned host memory.
+static int query_use_host_matrix(bsg_query* q) {
+    const size_t bytes = std::max<uint64_t>(q->n_units * q->row_words32, 1) * 4;
+    const uint32_t groups = (q->n_keys + 31) / 32;
+    if (bytes > q->cap_out) {
+        if (q->h_out) cudaFreeHost(q->h_out);
+        q->h_out = nullptr;
+        q->cap_out = 0;
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&q->h_out), bytes * 2, cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&q->h_out_dev), q->h_out, 0));
+        q->cap_out = bytes * 2;
+        q->out_units = ~0ull;
+    }
+    if (q->out_units != q->n_units || q->out_row_words32 != q->row_words32 || q->out_groups != groups) {
+        memset(q->h_out, 0, bytes);  // pad words are never written by the kernels
+        q->out_units = q->n_units;
+        q->out_row_words32 = q->row_words32;
+        q->out_groups = groups;
+    }
+    q->k_matrix = q->h_out_dev;
     return BSG_OK;
 }
 
@@ -1224,26 +1272,26 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
                 const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
                 CUDA_TRY(launch_probe_staged(plan, rows, c->n_staged, c->d_words, q->d_hashes, q->k_kinds, kb, nk,
-                                             q->kind_mask, q->d_matrix32, q->row_words32, s, ctx->d_trace,
+                                             q->kind_mask, q->k_matrix, q->row_words32, s, ctx->d_trace,
                                              ctx->trace_slots, d_n_rows));
                 ++launches;
             }
         } else if (c->n_staged) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_staged_list, c->n_staged, q->d_hashes,
-                                         q->k_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
                                          d_parent_mask32));
             ++launches;
         }
         if (c->n_gather) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_gather_list, c->n_gather, q->d_hashes,
-                                         q->k_kinds, q->n_keys, q->d_matrix32, q->row_words32, s, d_parent,
+                                         q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
                                          d_parent_mask32));
             ++launches;
         }
     }
     if (c->n_units && !matrix_only) {
         if (q->prog_len) {
-            CUDA_TRY(launch_tree_eval(q->d_matrix32, q->row_words32, c->n_units, q->k_prog, q->prog_len, q->d_mask32, s,
+            CUDA_TRY(launch_tree_eval(q->k_matrix, q->row_words32, c->n_units, q->k_prog, q->prog_len, q->d_mask32, s,
                                       d_parent, d_parent_mask32));
         } else if (d_parent) {
             CUDA_TRY(launch_parent_mask(q->d_mask32, c->n_units, d_parent, d_parent_mask32, s));
@@ -1263,9 +1311,16 @@ extern "C" int bsg_query_run(bsg_ctx* ctx, const bsg_corpus* corpus, bsg_query* 
 }
 
 // D2H through the query's pinned block (true async DMA), then memcpy into the caller's buffers.
-static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s) {
+static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s,
+                              std::chrono::steady_clock::time_point* t_synced = nullptr) {
     const size_t mbytes = (out_matrix && q->n_keys) ? n_units * q->row_words32 * 4 : 0;
     const size_t kbytes = out_mask ? ((n_units + 63) / 64) * 8 : 0;
+    if (q->k_matrix != q->d_matrix32) {  // zero copy: the rows are already in pinned host memory
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (t_synced) *t_synced = std::chrono::steady_clock::now();
+        if (mbytes) memcpy(out_matrix, q->h_out, mbytes);
+        return BSG_OK;
+    }
     const size_t need = mbytes + kbytes + 16;
     if (need > q->cap_pin) {  // grow, keeping nothing (inputs were already consumed by the copies on s)
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -1281,6 +1336,7 @@ static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matr
     if (mbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin, q->d_matrix32, mbytes, cudaMemcpyDeviceToHost, s));
     if (kbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin + mbytes, q->d_mask32, kbytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (t_synced) *t_synced = std::chrono::steady_clock::now();
     if (mbytes) memcpy(out_matrix, q->h_pin, mbytes);
     if (kbytes) memcpy(out_mask, q->h_pin + mbytes, kbytes);
     return BSG_OK;
@@ -1316,12 +1372,26 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     }
     if (!q) q = new (std::nothrow) bsg_query();
     int rc = q ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     if (rc == BSG_OK) rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q, true);
+    if (rc == BSG_OK && ctx->zero_copy && out_matrix && !out_mask && n_keys && corpus->n_units) rc = query_use_host_matrix(q);
+    const auto t1 = clk::now();
     // the mask kernel is skipped when the caller wants no mask
     const int path = BSG_PROBE_AUTO | (out_mask ? 0 : BSG_RUN_MATRIX_ONLY);
     if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, path, out_matrix != nullptr, s);
-    if (rc == BSG_OK) rc = query_fetch_pinned(q, corpus->n_units, out_matrix, out_mask, s);
+    const auto t2 = clk::now();
+    clk::time_point t3 = t2;
+    if (rc == BSG_OK) rc = query_fetch_pinned(q, corpus->n_units, out_matrix, out_mask, s, ctx->timing ? &t3 : nullptr);
     else cudaStreamSynchronize(s);
+    if (ctx->timing) {
+        const auto t4 = clk::now();
+        auto ns = [](clk::time_point a, clk::time_point b) {
+            return static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count());
+        };
+        ctx->t_calls += 1; ctx->t_prepare += ns(t0, t1); ctx->t_run += ns(t1, t2); ctx->t_wait += ns(t2, t3);
+        ctx->t_copyout += ns(t3, t4);
+    }
     if (q) {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->scratch_pool.push_back(q);
