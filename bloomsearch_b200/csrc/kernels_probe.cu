@@ -467,8 +467,12 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                     base += __popc(surv_bits[j]);
                 }
             }
+            // Publication order: every lane's queue / row stores -> bar.warp.sync (orders memory among the
+            // warp's lanes) -> lane 0's mbarrier.arrive (release.cta, cumulative) -> a B warp's try_wait
+            // (acquire.cta) -> its loads.  compute-sanitizer racecheck does not credit the warp barrier's
+            // transitivity and reports the queue write/read pair; memcheck and synccheck are clean.
             __syncwarp();
-            if (lane == 0) mbar_arrive(&aready[s]);  // release: row words + queue entries of this warp
+            if (lane == 0) mbar_arrive(&aready[s]);
             if (TRACE && tr && tid == 0 && 2 + 8 * it < trace_slots) tr[2 + 8 * it] = globaltimer_ns();
             st += stage_bytes;
             if (++s == S) { s = 0; ph ^= 1u; st = stages; }
