@@ -412,7 +412,7 @@ def main():
                "d2h_bytes_per_step": int(n_units * m_words * 8),
                "callers": args.e2e_callers, "ms_per_step_per_caller": dt_multi / e2e_steps * 1e3,
                "single_caller": {"value": total_probes * e2e_steps / dt_single, "ms_per_step": dt_single / e2e_steps * 1e3},
-               "what": "bsg_probe(): packed host key bytes -> one H2D copy, hash, probe; the (block x key) matrix rows are "
+               "what": "bsg_probe(): packed host key bytes -> one H2D copy, one kernel (hashing fused into the probe); the (block x key) matrix rows are "
                        "written by the probe kernel straight into pinned host memory (device->host over PCIe inside "
                        "the call), then copied to the caller's buffer"}
 

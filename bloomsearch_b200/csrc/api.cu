@@ -89,6 +89,7 @@ struct bsg_ctx {
     // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
+    int fuse_hash = 1;     // BSG_PROBE_FUSE_HASH: bsg_probe() hashes inside the staged probe kernel when it can
     int zero_copy = 1;     // BSG_PROBE_ZEROCOPY: bsg_probe() matrix rows written straight to pinned host memory
     int pdl = 1;           // BSG_PROBE_PDL: programmatic dependent launch of the two-phase probe kernel
     int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
@@ -152,6 +153,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
+    if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_ZEROCOPY")) ctx->zero_copy = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
@@ -982,6 +984,11 @@ struct bsg_query {
     // where the probe kernels write the (unit x key) matrix: d_matrix32, or — bsg_probe() without a
     // mask — the pinned host block h_out (zero copy: rows cross PCIe as posted writes while the
     // kernel runs, no D2H copy operation after it)
+    // bsg_probe path: hashing is deferred to the run; a staged-only run hashes inside the probe kernel
+    // (per-CTA scratch table), any other run launches hash_keys_kernel first
+    bool hashed = false;
+    uint64_t* d_hash_scratch = nullptr;
+    size_t cap_hash_scratch = 0;
     uint32_t* k_matrix = nullptr;
     uint32_t* h_out = nullptr;
     uint32_t* h_out_dev = nullptr;
@@ -1023,6 +1030,7 @@ extern "C" void bsg_query_free(bsg_query* q) {
     if (q->h_pin) cudaFreeHost(q->h_pin);
     if (q->h_out) cudaFreeHost(q->h_out);
     cudaFree(q->d_in);
+    cudaFree(q->d_hash_scratch);
     cudaFree(q->d_rows);
     cudaFree(q->d_n_rows);
     delete q;
@@ -1155,7 +1163,11 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         q->k_kinds = q->d_kinds;
         q->k_prog = q->d_prog;
     }
-    if (n_keys) CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, n_keys, q->d_hashes, s));
+    q->hashed = false;
+    if (n_keys && !(use_pinned && ctx->fuse_hash)) {
+        CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, n_keys, q->d_hashes, s));
+        q->hashed = true;
+    }
     q->k_matrix = q->d_matrix32;
     return BSG_OK;
 }
@@ -1236,11 +1248,22 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             const uint64_t gather_bytes = static_cast<uint64_t>(c->n_staged) * q->n_keys * (4 * 32 + 32);
             use_staged = staged_bytes <= gather_bytes;
         }
+        // deferred hashing (bsg_probe path): fused into the two-phase staged kernel when that kernel is
+        // the only consumer of the hashes, else a hash_keys_kernel launch now
+        const bool fuse = !q->hashed && use_staged && c->n_gather == 0 && ctx->probe_variant != 0;
+        if (!q->hashed && !fuse) {
+            CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, q->n_keys, q->d_hashes, s));
+            q->hashed = true;
+            ++launches;
+        }
         if (use_staged) {
             ProbeStagedPlan plan;
             plan.variant = ctx->probe_variant;
             plan.relax_sleep_ns = static_cast<uint32_t>(ctx->relax_sleep_ns);
             plan.pdl = ctx->pdl;
+            plan.fuse_keys = nullptr;
+            plan.fuse_key_off = nullptr;
+            plan.fuse_scratch = nullptr;
             const uint64_t prefix = plan.variant ? kProbe2SmemPrefixBytes : kProbeSmemPrefixBytes;
             const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - prefix;
             plan.stage_data_bytes = std::max<uint32_t>(c->stage_cap_bytes, 16);
@@ -1258,6 +1281,13 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
                 const double ns = static_cast<double>(stage_bytes) * plan.grid / 6500.0;
                 plan.stagger_ns = ctx->stagger_pct < 0 ? 0u
                                                        : static_cast<uint32_t>(std::min(2000.0, ns * ctx->stagger_pct / 100.0));
+            }
+            if (fuse) {
+                CUDA_TRY(ensure_cap(q->d_hash_scratch, q->cap_hash_scratch,
+                                    static_cast<size_t>(plan.grid) * kProbeMaxKeysPerPass * 32));
+                plan.fuse_keys = q->k_keys;
+                plan.fuse_key_off = q->k_key_off;
+                plan.fuse_scratch = q->d_hash_scratch;
             }
             const StageRow* rows = c->d_stab;
             const uint32_t* d_n_rows = nullptr;

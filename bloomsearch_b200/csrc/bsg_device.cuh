@@ -265,6 +265,13 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Coherent 16-byte global load (never the read-only .nc path): for data that the running kernel
+// itself may have written earlier (the fused hash table of probe_staged2).
+__device__ __forceinline__ ulonglong2 ld_global_u64x2(const void* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
 // Programmatic dependent launch (PDL): a kernel launched with programmatic stream serialization may
 // start while its predecessor in the stream is still draining; it must not touch anything the
 // predecessor wrote before griddep_wait() returns.  Both are no-ops for a normal launch.

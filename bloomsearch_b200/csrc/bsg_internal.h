@@ -86,6 +86,11 @@ struct ProbeStagedPlan {
     int grid;
     int warps;            // 0 = auto
     uint32_t stagger_ns;  // delay between the prologue's stage fills (0 = none)
+    // fused hashing (two-phase kernel only): packed key bytes / offsets on the device and a scratch of
+    // grid x 1024 x 32 B; nullptr = the hashes come from hash_keys_kernel
+    const uint8_t* fuse_keys;
+    const uint64_t* fuse_key_off;
+    uint64_t* fuse_scratch;
     int pdl;              // launch with programmatic stream serialization (overlap with the predecessor's tail)
     uint32_t relax_sleep_ns;  // sleep between polls of a phase-B warp waiting for phase A (0 = none)
     int variant;          // 0 = probe_staged (one phase), 1..5 = probe_staged2 shapes (kernels_probe.cu)

@@ -340,7 +340,9 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                      const uint64_t* __restrict__ words, const uint64_t* __restrict__ hashes,
                      const uint8_t* __restrict__ kinds, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
                      uint32_t* __restrict__ matrix32, uint32_t row_words32, uint32_t n_stages, uint32_t stage_bytes,
-                     uint32_t relax_sleep_ns, uint64_t* __restrict__ trace, uint32_t trace_slots) {
+                     uint32_t relax_sleep_ns, uint64_t* __restrict__ trace, uint32_t trace_slots,
+                     const uint8_t* __restrict__ key_bytes, const uint64_t* __restrict__ key_off,
+                     uint64_t* hash_scratch) {
     static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
     static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0, "shape");
     // B warps work in teams of T; team g serves units g, g+NTEAMS, ...  The host guarantees
@@ -393,6 +395,27 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     griddep_launch_dependents();
     if (!n_list_dev) griddep_wait();
 
+    // Fused hashing (bsg_probe path): no separate hash kernel — while the ring's first fills are in
+    // flight every CTA hashes this pass's keys itself (one key per thread, baseHashes as in
+    // kernels_hash.cu) into its own 32 KB slice of a scratch table; phase B reads survivors' hashes
+    // from that slice.  The table is written by this kernel: it is read with coherent loads only.
+    const uint64_t* htab = hashes;
+    uint32_t hbase = 0;
+    if (hash_scratch) {
+        uint64_t* tab = hash_scratch + static_cast<size_t>(blockIdx.x) * kProbeMaxKeysPerPass * 4;
+        for (uint32_t t = tid; t < n_keys; t += blockDim.x) {
+            const uint64_t b = __ldg(&key_off[key_base + t]), e = __ldg(&key_off[key_base + t + 1]);
+            uint64_t h[4];
+            base_hashes(key_bytes + b, static_cast<uint32_t>(e - b), h);
+            ulonglong2* out = reinterpret_cast<ulonglong2*>(tab + 4ull * t);
+            out[0] = make_ulonglong2(h[0], h[1]);
+            out[1] = make_ulonglong2(h[2], h[3]);
+        }
+        __syncthreads();
+        htab = tab;
+        hbase = key_base;
+    }
+
     uint32_t s = 0, ph = 0;
     uint8_t* st = stages;
     if (warp < NA) {
@@ -407,8 +430,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             f_off[j] = 0;
             if (ql < n_keys) {
                 const uint32_t q = key_base + ql;
-                const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-                const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+                const uint64_t* hp = htab + 4ull * (q - hbase);
+                const ulonglong2 a = ld_global_u64x2(hp), b = ld_global_u64x2(hp + 2);
                 const uint64_t l4[4] = {a.x, a.y + b.y, a.x + 2 * b.y, a.y + 3 * b.x};
 #pragma unroll
                 for (int t = 0; t < NT; ++t) loc[j][t] = l4[t];
@@ -500,8 +523,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                 if (idx < n) {
                     const uint32_t ql = queue[idx];
                     const uint32_t q = key_base + ql;
-                    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * q);
-                    const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+                    const uint64_t* hp = htab + 4ull * (q - hbase);
+                    const ulonglong2 a = ld_global_u64x2(hp), b = ld_global_u64x2(hp + 2);
                     const uint32_t fo = 32u + 32u * __ldg(&kinds[q]);
                     if (TRACE && tr && c == 0 && lane == 0 && 5 + 8 * it < trace_slots)
                         tr[5 + 8 * it] = globaltimer_ns() + ((a.x ^ b.y ^ fo) == 0x123456789abcull);  // hashes arrived
@@ -594,11 +617,11 @@ static void staged2_launch(const ProbeStagedPlan& plan, const StageRow* d_stab, 
     if (d_trace)
         cudaLaunchKernelEx(&cfg, probe_staged2_kernel<NA, KPT, NT, NB, T, true>, d_stab, n_list, d_n_list, d_words, d_hashes,
                            d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32, n_stages, sb,
-                           plan.relax_sleep_ns, tr, ts);
+                           plan.relax_sleep_ns, tr, ts, plan.fuse_keys, plan.fuse_key_off, plan.fuse_scratch);
     else
         cudaLaunchKernelEx(&cfg, probe_staged2_kernel<NA, KPT, NT, NB, T, false>, d_stab, n_list, d_n_list, d_words, d_hashes,
                            d_kinds, key_base, n_keys, kind_mask, d_matrix32, row_words32, n_stages, sb,
-                           plan.relax_sleep_ns, tr, ts);
+                           plan.relax_sleep_ns, tr, ts, plan.fuse_keys, plan.fuse_key_off, plan.fuse_scratch);
 }
 #define BSG_STAGED2_SHAPES(X)                                                                          \
     X(1, 16, 2, 2, 16, 16) X(2, 16, 2, 3, 16, 16) X(3, 16, 2, 3, 16, 4) X(4, 16, 2, 3, 16, 2) X(5, 16, 2, 4, 16, 4)
