@@ -9,14 +9,14 @@
 // word order and keys are hashed once per batch (kernels_hash.cu).
 //
 // Two data paths produce identical bits:
-//   probe_staged  — large batches: each unit's bitsets are bulk-copied (TMA 1-D,
-//                   cp.async.bulk + mbarrier) into a multi-stage shared-memory
-//                   ring by a producer warp while consumer warps test their keys
-//                   against the previous stages.  Every bitset byte crosses HBM
-//                   once per batch: the HBM-roofline regime of SURVEY.md §8(d).
-//   probe_gather  — small batches or filters too large to stage: one lane per
-//                   (unit,key), bit words gathered straight from L2/HBM (the
-//                   sparse 8*k bytes/probe bound).
+//   staged  — large batches: each unit's bitsets are bulk-copied (TMA 1-D, cp.async.bulk +
+//             mbarrier) into a multi-stage shared-memory ring; the warp that frees a stage
+//             refills it.  Every bitset byte crosses HBM once per batch: the HBM-roofline
+//             regime of SURVEY.md §8(d).  probe_staged2_kernel (default) splits TestString
+//             into a branch-free first phase over all keys and a second phase over the
+//             compacted survivors; probe_staged_kernel is its one-phase predecessor.
+//   gather  — small batches or filters too large to stage: one lane per (unit,key), bit
+//             words gathered straight from L2/HBM (the sparse 8*k bytes/probe bound).
 // tree_eval turns the (unit x key) bit matrix into the candidate mask with the
 // query's AND/OR tree (query_exec.go:89-125) in postfix form.
 #include "bsg_device.cuh"
