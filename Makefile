@@ -11,5 +11,5 @@ bench: build
 golden:
 	$(PY) tests/golden/make_golden.py
 clean:
-	$(MAKE) -C bloomsearch_b200/csrc clean; $(MAKE) -C oracle clean; $(MAKE) -C synth clean
+	$(MAKE) -C bloomsearch_b200/csrc clean; $(MAKE) -C oracle clean; $(MAKE) -C synth clean; $(MAKE) -C tools clean
 .PHONY: build test-cpu test-gpu bench golden clean
