@@ -460,6 +460,47 @@ def test_bsg_probe_scratch_reuse_across_shapes(ctx):
     corpus.close()
 
 
+def test_bsg_probe_matrix_only_rows_in_host_memory_odd_keys(ctx):
+    """bsg_probe() without a mask: one upload, hashing fused into the staged kernel, matrix rows
+    written by the kernel straight into pinned host memory.  Shapes change on the same scratch
+    (pad words of a row must stay zero), keys include the empty key, keys with NUL bytes and a
+    5 000-byte key; a corpus with one filter too large to stage falls back to the hash kernel."""
+    rng = random.Random(77)
+    odd = [b"", b"\x00", b"\x00\x00tail", bytes(rng.randrange(256) for _ in range(5000)), b"a" * 15, b"b" * 16, b"c" * 17]
+    unit_keys = [(rand_keys(rng, 5, 3, 8), odd + rand_keys(rng, 120, 1, 10), rand_keys(rng, 130, 4, 20)) for _ in range(333)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    corpus = bs.Corpus(ctx, desc, words)
+    pool, pool_kinds = _mixed_keys(rng, unit_keys[:40], 900, 1300)
+    pool = odd + pool
+    pool_kinds = [1] * len(odd) + pool_kinds
+    for n in (1000, 65, 1, 1025, 64, 2049, 33):
+        keys, kinds = pool[:n], np.asarray(pool_kinds[:n], np.uint8)
+        blob, off = N.pack_keys(keys)
+        want = cref.probe_matrix(desc, words, len(unit_keys), blob, off, kinds)
+        got = np.full((len(unit_keys), (n + 63) // 64), 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+        corpus.probe_packed(blob, off, kinds, None, got, None)
+        assert np.array_equal(got, want), n
+    bits = bs.unpack_matrix(want, 33)
+    assert bits[:, :len(odd)].all()   # the odd keys are present in every unit
+    corpus.close()
+    # one unit whose token filter cannot be staged -> gather list is not empty -> separate hash kernel
+    big = [b"tok-%d" % i for i in range(400_000)]
+    f_big = cref.Filter.build_sized(big, 0.001)
+    d2 = np.zeros(len(desc) + 3, dtype=cref.DESC_DTYPE)
+    d2[:len(desc)] = desc
+    d2[len(desc) + 1] = (f_big.m, f_big.k, len(words))
+    w2 = np.concatenate([words, f_big.words()])
+    c2 = bs.Corpus(ctx, d2, w2)
+    keys = [b"tok-7", b"nope"] + pool[:100]
+    kinds = np.asarray([1, 1] + pool_kinds[:100], np.uint8)
+    blob, off = N.pack_keys(keys)
+    want = cref.probe_matrix(d2, w2, len(d2) // 3, blob, off, kinds)
+    got = np.zeros((len(d2) // 3, 2), dtype=np.uint64)
+    c2.probe_packed(blob, off, kinds, None, got, None)
+    assert np.array_equal(got, want)
+    c2.close()
+
+
 # ------------------------------------------------------ hierarchical probe ---
 @pytest.mark.parametrize("n_extra_keys", [0, 60])
 def test_hierarchical_probe_matches_two_stage_reference(ctx, n_extra_keys):
