@@ -80,3 +80,26 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "bloomref" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_go_shim_and_cpp_host_bind_only_declared_entry_points():
+    """The cgo shim (go/bloomgpu, source only: no Go toolchain here) and the C++ host layer must call
+    nothing but what include/bloomgpu.h declares, and the shim must cover the whole hot path
+    (build, fused field::token build, distinct counts, corpus loads, probe, hierarchical probe)."""
+    declared = set(_declared_symbols())
+    types = {"bsg_ctx", "bsg_corpus", "bsg_query", "bsg_expr_op", "bsg_filter_desc"}
+    go_calls = set()
+    for fn in os.listdir(os.path.join(ROOT, "go", "bloomgpu")):
+        if fn.endswith(".go"):
+            go_calls |= set(re.findall(r"\bC\.(bsg_[a-z_0-9]+)", open(os.path.join(ROOT, "go", "bloomgpu", fn)).read()))
+    go_funcs = go_calls - types
+    assert go_funcs and go_funcs <= declared, sorted(go_funcs - declared)
+    for need in ("bsg_create", "bsg_destroy", "bsg_build", "bsg_build_fieldtokens", "bsg_count_distinct",
+                 "bsg_corpus_load", "bsg_corpus_load_sections", "bsg_probe", "bsg_probe_hierarchical", "bsg_last_error"):
+        assert need in go_funcs, need
+    host_dir = os.path.join(ROOT, "bloomsearch_b200", "host")
+    cpp_calls = set()
+    for fn in os.listdir(host_dir):
+        if fn.endswith((".cpp", ".hpp")):
+            cpp_calls |= set(re.findall(r"\b(bsg_[a-z_0-9]+)\s*\(", open(os.path.join(host_dir, fn)).read()))
+    assert cpp_calls and cpp_calls <= declared, sorted(cpp_calls - declared)
