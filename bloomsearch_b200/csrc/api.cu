@@ -1405,7 +1405,12 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
     if (rc == BSG_OK) rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, prog, prog_len, s, q, true);
-    if (rc == BSG_OK && ctx->zero_copy && out_matrix && !out_mask && n_keys && corpus->n_units) rc = query_use_host_matrix(q);
+    // zero copy pays while the rows trickle out under the kernel's own runtime; a matrix of many MB would
+    // instead hold the SMs at PCIe speed, so large outputs keep the copy-engine path (D2H after the kernel)
+    constexpr uint64_t kZeroCopyMaxBytes = 8ull << 20;
+    if (rc == BSG_OK && ctx->zero_copy && out_matrix && !out_mask && n_keys && corpus->n_units &&
+        corpus->n_units * q->row_words32 * 4ull <= kZeroCopyMaxBytes)
+        rc = query_use_host_matrix(q);
     const auto t1 = clk::now();
     // the mask kernel is skipped when the caller wants no mask
     const int path = BSG_PROBE_AUTO | (out_mask ? 0 : BSG_RUN_MATRIX_ONLY);
