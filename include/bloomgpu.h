@@ -177,7 +177,11 @@ int bsg_corpus_unit_desc(const bsg_corpus *corpus, uint64_t unit, bsg_filter_des
  *                 (query_exec.go:81-83)
  *   out_mask      nullable; ceil(n_units/64) uint64 words, bit u = unit u survives
  * FieldToken keys are passed already joined as field + "::" + token
- * (tokenizer.go:508-511); bytes are used verbatim (no normalisation). */
+ * (tokenizer.go:508-511); bytes are used verbatim (no normalisation).
+ * Thread-safe and re-entrant (one pooled stream + scratch per call); the caller's buffers are plain
+ * host memory and are not retained.  Per call: one host-to-device copy of the packed batch, one
+ * kernel when the corpus is staged (hashing is fused into the probe), and — matrix without mask, up
+ * to 8 MB — the rows arrive in pinned host memory while the kernel runs (no copy back). */
 int bsg_probe(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys, const uint64_t *key_off,
               uint32_t n_keys, const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
               uint64_t *out_matrix, uint64_t *out_mask);
