@@ -85,7 +85,11 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int probe_variant = 3; // BSG_PROBE_VARIANT: 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2 (two phases)
+    int probe_variant = 6; // BSG_PROBE_VARIANT: 6 = probe_tiles (default); 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2
+    int tiles_shape = 0;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
+    int tile_bytes = 32 * 1024;  // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
+    int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
+    int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
     // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
@@ -145,12 +149,17 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(probe_staged_configure(ctx->max_smem_optin));
+    CUDA_TRY(probe_tiles_configure(ctx->max_smem_optin));
     CUDA_TRY(build_configure(ctx->max_smem_optin));
     CUDA_TRY(sections_configure());
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(5, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(6, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_TILES_SHAPE")) ctx->tiles_shape = std::min(probe_tiles_n_shapes() - 1, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_TILE_BYTES")) ctx->tile_bytes = std::max(1024, atoi(w));
+    if (const char* w = getenv("BSG_TILE_UNITS")) ctx->tile_units = std::min<int>(kTileMaxUnits, std::max(1, atoi(w)));
+    if (const char* w = getenv("BSG_TILE_MODE")) ctx->tile_mode = std::min(2, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
     if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
@@ -710,6 +719,17 @@ struct bsg_corpus {
     uint64_t kind_bytes[3] = {0, 0, 0};         // Σ 8*ceil(m/64) per kind
     uint64_t staged_kind_bytes[3] = {0, 0, 0};  // same, staged units only (padded words)
     std::vector<bsg_filter_desc> h_desc;        // caller's (m,k) with word_off in the device layout
+    // tile ring (probe_tiles_kernel): records, which units they cover, and the rest (gather list)
+    TileRec* d_tiles = nullptr;
+    uint32_t t_items = 0;          // items = tiles (UNIT mode) or staged units (KIND mode, 2 tiles each)
+    uint32_t t_parts = 1;
+    uint32_t t_units_cap = 1;      // most units in one tile (stage header size)
+    uint32_t t_data_cap = 0;       // largest tile data, 128-byte multiple
+    uint32_t t_staged = 0;         // units covered by tiles
+    uint32_t* d_t_staged_list = nullptr;  // nullptr when every unit is tiled
+    uint32_t* d_t_gather_list = nullptr;
+    uint32_t t_gather = 0;
+    uint64_t t_staged_kind_bytes[3] = {0, 0, 0};
 };
 
 extern "C" void bsg_corpus_free(bsg_corpus* c) {
@@ -721,6 +741,9 @@ extern "C" void bsg_corpus_free(bsg_corpus* c) {
     cudaFree(c->d_staged_list);
     cudaFree(c->d_gather_list);
     cudaFree(c->d_parent);
+    cudaFree(c->d_tiles);
+    cudaFree(c->d_t_staged_list);
+    cudaFree(c->d_t_gather_list);
     delete c;
 }
 
@@ -779,6 +802,152 @@ int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
         cur += unit_words;
     }
     L.total_words = cur;
+    return BSG_OK;
+}
+
+// Cuts the corpus into tiles for probe_tiles_kernel (bsg_internal.h): decides UNIT vs KIND mode, groups
+// small units, and lists the units no tile can hold (they take the gather kernel).
+int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
+    const uint64_t n_units = c->n_units;
+    // conservative ring budget: the largest fixed part any compiled shape needs for a full pass of keys
+    int nb_max = 0;
+    for (int i = 0; i < probe_tiles_n_shapes(); ++i) nb_max = std::max(nb_max, probe_tiles_b_warps(i));
+    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - tiles_fixed_smem(nb_max, kProbeMaxKeysPerPass);
+    const uint64_t unit_limit = budget / 4 - tile_header_bytes(kTileMaxUnits);  // UNIT mode: a ring of >= 4 stages
+    const uint64_t part_limit = budget / 2 - tile_header_bytes(1);              // KIND mode: >= 2 stages
+    auto part_bytes = [&](uint64_t u, int part) -> uint64_t {
+        const UnitTab& t = L.utab[u];
+        return part == 0 ? (static_cast<uint64_t>(t.nw[0]) + t.nw[1]) * 8 : static_cast<uint64_t>(t.nw[2]) * 8;
+    };
+    auto filters_ok = [&](uint64_t u) {
+        for (int k = 0; k < 3; ++k) {
+            const DevFilter& d = L.udesc[u * 3 + k];
+            if (d.m && (d.m >= (1ull << 30) || d.k > 0xffffu)) return false;
+        }
+        return true;
+    };
+    uint64_t bytes_unit = 0, bytes_kind_only = 0;
+    std::vector<uint8_t> cls(n_units, 0);  // 1 = fits UNIT mode, 2 = fits KIND mode only, 0 = neither
+    for (uint64_t u = 0; u < n_units; ++u) {
+        if (!filters_ok(u)) continue;
+        const uint64_t b = static_cast<uint64_t>(L.utab[u].total) * 8;
+        if (b <= unit_limit) { cls[u] = 1; bytes_unit += b; }
+        else if (std::max(part_bytes(u, 0), part_bytes(u, 1)) <= part_limit) { cls[u] = 2; bytes_kind_only += b; }
+    }
+    bool kind_mode = bytes_kind_only * 10 > bytes_unit + bytes_kind_only;
+    if (ctx->tile_mode == 1) kind_mode = false;
+    if (ctx->tile_mode == 2) kind_mode = true;
+    std::vector<TileRec> recs;
+    std::vector<uint32_t> staged, gather;
+    uint32_t units_cap = 1;
+    uint64_t data_cap = 0;
+    auto tile_filter = [&](uint64_t u, int k, uint64_t rel_bytes) {
+        const DevFilter& d = L.udesc[u * 3 + k];
+        if (d.m == 0) return TileFilter{0, 0, 0, 0};
+        return TileFilter{static_cast<uint32_t>(d.m), static_cast<uint32_t>(d.inv >> 32), static_cast<uint32_t>(d.inv),
+                          (d.k << 16) | static_cast<uint32_t>(rel_bytes >> 4)};
+    };
+    auto small_k = [&](uint64_t u, int k) { const DevFilter& d = L.udesc[u * 3 + k]; return d.m && d.k < 4; };
+    if (kind_mode) {
+        for (uint64_t u = 0; u < n_units; ++u) {
+            if (cls[u] == 0) { gather.push_back(static_cast<uint32_t>(u)); continue; }
+            staged.push_back(static_cast<uint32_t>(u));
+            const UnitTab& t = L.utab[u];
+            for (int part = 0; part < 2; ++part) {
+                TileRec r;
+                memset(&r, 0, sizeof(r));
+                r.n_units = 1;
+                r.part_kinds = part == 0 ? 3u : 4u;
+                r.flags = part == 0 ? kTileFirstPart : kTileLastPart;
+                r.unit[0] = static_cast<uint32_t>(u);
+                r.fill.rec_bytes = kTileRecFixedBytes + 48;
+                if (part == 0) {
+                    r.fill.word_base = t.word_base;
+                    r.fill.data_bytes = (t.nw[0] + t.nw[1]) * 8u;
+                    r.fill.nb16[0][0] = static_cast<uint16_t>(t.nw[0] / 2);
+                    r.fill.nb16[0][1] = static_cast<uint16_t>(t.nw[1] / 2);
+                    r.f[0][0] = tile_filter(u, 0, 0);
+                    r.f[0][1] = tile_filter(u, 1, static_cast<uint64_t>(t.nw[0]) * 8);
+                    if (small_k(u, 0) || small_k(u, 1)) r.flags |= kTileSmallK;
+                } else {
+                    r.fill.word_base = t.word_base + t.nw[0] + t.nw[1];
+                    r.fill.data_bytes = t.nw[2] * 8u;
+                    r.fill.nb16[0][2] = static_cast<uint16_t>(t.nw[2] / 2);
+                    r.f[0][2] = tile_filter(u, 2, 0);
+                    if (small_k(u, 2)) r.flags |= kTileSmallK;
+                }
+                data_cap = std::max<uint64_t>(data_cap, r.fill.data_bytes);
+                recs.push_back(r);
+            }
+        }
+    } else {
+        const uint32_t group_max = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
+        const uint64_t target = static_cast<uint64_t>(ctx->tile_bytes);
+        TileRec r;
+        memset(&r, 0, sizeof(r));
+        uint64_t cur_bytes = 0, next_word = 0;
+        bool open = false;
+        auto close_tile = [&]() {
+            if (!open) return;
+            r.fill.rec_bytes = kTileRecFixedBytes + 48 * r.n_units;
+            r.fill.data_bytes = static_cast<uint32_t>(cur_bytes);
+            units_cap = std::max(units_cap, r.n_units);
+            data_cap = std::max(data_cap, cur_bytes);
+            recs.push_back(r);
+            open = false;
+        };
+        for (uint64_t u = 0; u < n_units; ++u) {
+            if (cls[u] != 1) { gather.push_back(static_cast<uint32_t>(u)); continue; }
+            staged.push_back(static_cast<uint32_t>(u));
+            const UnitTab& t = L.utab[u];
+            const uint64_t b = static_cast<uint64_t>(t.total) * 8;
+            // a tile is one contiguous range of the words array: close it at gaps (gather units in between)
+            if (open && (r.n_units >= group_max || cur_bytes + b > std::min(target, unit_limit) || t.word_base != next_word))
+                close_tile();
+            if (!open) {
+                memset(&r, 0, sizeof(r));
+                r.part_kinds = 7u;
+                r.flags = kTileFirstPart | kTileLastPart;
+                r.fill.word_base = t.word_base;
+                cur_bytes = 0;
+                open = true;
+            }
+            const uint32_t j = r.n_units++;
+            r.unit[j] = static_cast<uint32_t>(u);
+            uint64_t rel = cur_bytes;
+            for (int k = 0; k < 3; ++k) {
+                r.f[j][k] = tile_filter(u, k, rel);
+                r.fill.nb16[j][k] = static_cast<uint16_t>(t.nw[k] / 2);
+                rel += static_cast<uint64_t>(t.nw[k]) * 8;
+                if (small_k(u, k)) r.flags |= kTileSmallK;
+            }
+            cur_bytes += b;
+            next_word = t.word_base + t.total;
+        }
+        close_tile();
+    }
+    c->t_parts = kind_mode ? 2u : 1u;
+    c->t_items = static_cast<uint32_t>(recs.size() / c->t_parts);
+    c->t_units_cap = units_cap;
+    c->t_data_cap = static_cast<uint32_t>((std::max<uint64_t>(data_cap, 16) + 127) & ~127ull);
+    c->t_staged = static_cast<uint32_t>(staged.size());
+    c->t_gather = static_cast<uint32_t>(gather.size());
+    for (uint32_t u : staged)
+        for (int k = 0; k < 3; ++k)
+            if (L.udesc[static_cast<uint64_t>(u) * 3 + k].m) c->t_staged_kind_bytes[k] += static_cast<uint64_t>(L.utab[u].nw[k]) * 8;
+    if (!recs.empty()) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_tiles), recs.size() * sizeof(TileRec)));
+        CUDA_TRY(cudaMemcpyAsync(c->d_tiles, recs.data(), recs.size() * sizeof(TileRec), cudaMemcpyHostToDevice, s));
+    }
+    if (!gather.empty()) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_t_gather_list), gather.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(c->d_t_gather_list, gather.data(), gather.size() * 4, cudaMemcpyHostToDevice, s));
+        if (!staged.empty()) {
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_t_staged_list), staged.size() * 4));
+            CUDA_TRY(cudaMemcpyAsync(c->d_t_staged_list, staged.data(), staged.size() * 4, cudaMemcpyHostToDevice, s));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));  // the host vectors die with this scope
     return BSG_OK;
 }
 
@@ -841,7 +1010,7 @@ int finish_corpus(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, const bsg_filter
         }
         CUDA_TRY(cudaStreamSynchronize(s));  // vectors die with this scope
     }
-    return BSG_OK;
+    return build_tiles(ctx, c, L, s);
 }
 
 }  // namespace
@@ -981,6 +1150,13 @@ struct bsg_query {
     const uint64_t* k_key_off = nullptr;
     const uint8_t* k_kinds = nullptr;
     const bsg_expr_op* k_prog = nullptr;
+    // probe_tiles: keys sorted by kind per 1024-key pass; slot -> caller index within the pass | kind << 14
+    const uint16_t* k_slot = nullptr;
+    uint16_t* d_slot = nullptr;
+    size_t cap_slot = 0;
+    std::vector<uint16_t> h_slot;
+    TileRec* d_tiles_c = nullptr;  // hierarchical probes: the compacted tile records
+    size_t cap_tiles_c = 0;
     // where the probe kernels write the (unit x key) matrix: d_matrix32, or — bsg_probe() without a
     // mask — the pinned host block h_out (zero copy: rows cross PCIe as posted writes while the
     // kernel runs, no D2H copy operation after it)
@@ -1033,6 +1209,8 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_hash_scratch);
     cudaFree(q->d_rows);
     cudaFree(q->d_n_rows);
+    cudaFree(q->d_slot);
+    cudaFree(q->d_tiles_c);
     delete q;
 }
 
@@ -1092,6 +1270,18 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         int rc = validate_program(prog, prog_len, n_keys);
         if (rc) return rc;
     }
+    // probe_tiles: stable counting sort of every 1024-key pass by kind
+    q->h_slot.resize(std::max<uint32_t>(n_keys, 1));
+    for (uint32_t kb = 0; kb < n_keys; kb += kProbeMaxKeysPerPass) {
+        const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, n_keys - kb);
+        uint32_t cnt[3] = {0, 0, 0};
+        for (uint32_t i = 0; i < nk; ++i) ++cnt[key_kind[kb + i]];
+        uint32_t at[3] = {0, cnt[0], cnt[0] + cnt[1]};
+        for (uint32_t i = 0; i < nk; ++i) {
+            const uint32_t kd = key_kind[kb + i];
+            q->h_slot[kb + at[kd]++] = static_cast<uint16_t>(i | (kd << 14));
+        }
+    }
     q->device = ctx->device;
     q->n_keys = n_keys;
     q->prog_len = prog_len;
@@ -1106,6 +1296,7 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         CUDA_TRY(ensure_cap(q->d_key_off, q->cap_key_off, (static_cast<uint64_t>(n_keys) + 1) * 8));
         CUDA_TRY(ensure_cap(q->d_kinds, q->cap_kinds, std::max<uint32_t>(n_keys, 1)));
         CUDA_TRY(ensure_cap(q->d_prog, q->cap_prog, std::max<uint32_t>(prog_len, 1) * sizeof(bsg_expr_op)));
+        CUDA_TRY(ensure_cap(q->d_slot, q->cap_slot, std::max<uint32_t>(n_keys, 1) * sizeof(uint16_t)));
     }
     CUDA_TRY(ensure_cap(q->d_hashes, q->cap_hashes, std::max<uint64_t>(n_keys, 1) * 32));
     CUDA_TRY(ensure_cap(q->d_matrix32, q->cap_matrix, matrix_words32 * 4));
@@ -1128,7 +1319,8 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         const size_t o_off = (nbytes + kKeyPad + 15) & ~size_t(15);
         const size_t o_kind = o_off + (static_cast<size_t>(n_keys) + 1) * 8;
         const size_t o_prog = (o_kind + n_keys + 15) & ~size_t(15);
-        const size_t used = o_prog + static_cast<size_t>(prog_len) * sizeof(bsg_expr_op);
+        const size_t o_slot = (o_prog + static_cast<size_t>(prog_len) * sizeof(bsg_expr_op) + 15) & ~size_t(15);
+        const size_t used = o_slot + static_cast<size_t>(n_keys) * sizeof(uint16_t);
         const size_t need = used + 16;
         if (need > q->cap_pin) {
             if (q->h_pin) cudaFreeHost(q->h_pin);
@@ -1145,11 +1337,13 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
             memcpy(q->h_pin + o_kind, key_kind, n_keys);
         }
         if (prog_len) memcpy(q->h_pin + o_prog, prog, prog_len * sizeof(bsg_expr_op));
+        if (n_keys) memcpy(q->h_pin + o_slot, q->h_slot.data(), n_keys * sizeof(uint16_t));
         CUDA_TRY(cudaMemcpyAsync(q->d_in, q->h_pin, used, cudaMemcpyHostToDevice, s));
         q->k_keys = q->d_in;
         q->k_key_off = reinterpret_cast<const uint64_t*>(q->d_in + o_off);
         q->k_kinds = q->d_in + o_kind;
         q->k_prog = reinterpret_cast<const bsg_expr_op*>(q->d_in + o_prog);
+        q->k_slot = reinterpret_cast<const uint16_t*>(q->d_in + o_slot);
     } else {
         CUDA_TRY(cudaMemsetAsync(q->d_keys + nbytes, 0, kKeyPad, s));
         if (nbytes) CUDA_TRY(cudaMemcpyAsync(q->d_keys, keys, nbytes, cudaMemcpyHostToDevice, s));
@@ -1158,6 +1352,8 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
             CUDA_TRY(cudaMemcpyAsync(q->d_kinds, key_kind, n_keys, cudaMemcpyHostToDevice, s));
         }
         if (prog_len) CUDA_TRY(cudaMemcpyAsync(q->d_prog, prog, prog_len * sizeof(bsg_expr_op), cudaMemcpyHostToDevice, s));
+        if (n_keys) CUDA_TRY(cudaMemcpyAsync(q->d_slot, q->h_slot.data(), n_keys * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        q->k_slot = q->d_slot;
         q->k_keys = q->d_keys;
         q->k_key_off = q->d_key_off;
         q->k_kinds = q->d_kinds;
@@ -1235,7 +1431,77 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
     if (path != BSG_PROBE_AUTO && path != BSG_PROBE_STAGED && path != BSG_PROBE_GATHER)
         return fail(BSG_ERR_INVALID, "unknown path %d", path);
     int launches = 0;
-    if (q->n_keys && c->n_units) {
+    if (q->n_keys && c->n_units && ctx->probe_variant == 6) {
+        // ---- tile ring (probe_tiles_kernel) for the units a tile can hold, gather kernel for the rest ----
+        bool use_staged = c->t_staged > 0;
+        if (path == BSG_PROBE_GATHER) use_staged = false;
+        if (path == BSG_PROBE_AUTO && use_staged) {
+            // staged traffic = every byte of the touched kinds; gather traffic ~ one 32 B sector per
+            // tested location (~3 on average for an absent key, k for a present one) + the descriptor.
+            uint64_t staged_bytes = 0;
+            for (int k = 0; k < 3; ++k)
+                if (q->kind_mask & (1u << k)) staged_bytes += c->t_staged_kind_bytes[k];
+            const uint64_t gather_bytes = static_cast<uint64_t>(c->t_staged) * q->n_keys * (4 * 32 + 32);
+            use_staged = staged_bytes <= gather_bytes;
+        }
+        // deferred hashing (bsg_probe path): every CTA of the tile kernel hashes the batch into its own shared
+        // memory when that kernel is the only consumer of the hashes, else a hash_keys_kernel launch now
+        const bool fuse = !q->hashed && use_staged && c->t_gather == 0;
+        if (!q->hashed && !fuse) {
+            CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, q->n_keys, q->d_hashes, s));
+            q->hashed = true;
+            ++launches;
+        }
+        if (use_staged) {
+            ProbeTilesPlan plan;
+            plan.shape = ctx->tiles_shape;
+            plan.pdl = ctx->pdl;
+            plan.parts = c->t_parts;
+            plan.units_cap = c->t_units_cap;
+            plan.stage_data_bytes = c->t_data_cap;
+            plan.fuse_keys = fuse ? q->k_keys : nullptr;
+            plan.fuse_key_off = fuse ? q->k_key_off : nullptr;
+            const uint32_t fixed = tiles_fixed_smem(probe_tiles_b_warps(plan.shape),
+                                                    std::min<uint32_t>(q->n_keys, kProbeMaxKeysPerPass));
+            const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
+            int max_stages = kProbeMaxStages;
+            if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
+            plan.n_stages = static_cast<int>(
+                std::min<uint64_t>(max_stages, (static_cast<uint64_t>(ctx->max_smem_optin) - fixed) / stage_bytes));
+            if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: tile does not fit shared memory");
+            plan.smem_bytes = fixed + plan.n_stages * stage_bytes;
+            plan.grid = static_cast<int>(std::min<uint64_t>(c->t_items, ctx->sm_count));
+            const TileRec* tiles = c->d_tiles;
+            const uint32_t* d_n_items = nullptr;
+            if (d_parent) {  // keep the tiles with a unit whose parent survived (compacted on the device)
+                CUDA_TRY(ensure_cap(q->d_tiles_c, q->cap_tiles_c,
+                                    static_cast<size_t>(c->t_items) * c->t_parts * sizeof(TileRec)));
+                if (!q->d_n_rows) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q->d_n_rows), 4));
+                CUDA_TRY(launch_compact_tiles(c->d_tiles, c->t_items, c->t_parts, d_parent, d_parent_mask32, q->d_tiles_c,
+                                              q->d_n_rows, s));
+                ++launches;
+                tiles = q->d_tiles_c;
+                d_n_items = q->d_n_rows;
+            }
+            for (uint32_t kb = 0; kb < q->n_keys; kb += kProbeMaxKeysPerPass) {
+                const uint32_t nk = std::min<uint32_t>(kProbeMaxKeysPerPass, q->n_keys - kb);
+                CUDA_TRY(launch_probe_tiles(plan, tiles, c->t_items, d_n_items, c->d_words, q->d_hashes, q->k_slot, kb, nk,
+                                            q->kind_mask, q->k_matrix, q->row_words32, s, ctx->d_trace, ctx->trace_slots));
+                ++launches;
+            }
+        } else if (c->t_staged) {
+            CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_t_staged_list, c->t_staged, q->d_hashes,
+                                         q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
+                                         d_parent_mask32));
+            ++launches;
+        }
+        if (c->t_gather) {
+            CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_t_gather_list, c->t_gather, q->d_hashes,
+                                         q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
+                                         d_parent_mask32));
+            ++launches;
+        }
+    } else if (q->n_keys && c->n_units) {
         // --- choose the data path for the stageable units ---
         bool use_staged = c->n_staged > 0;
         if (path == BSG_PROBE_GATHER) use_staged = false;

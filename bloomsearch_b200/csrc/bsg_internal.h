@@ -95,6 +95,80 @@ struct ProbeStagedPlan {
     uint32_t relax_sleep_ns;  // sleep between polls of a phase-B warp waiting for phase A (0 = none)
     int variant;          // 0 = probe_staged (one phase), 1..5 = probe_staged2 shapes (kernels_probe.cu)
 };
+// ---- tile ring (probe_tiles_kernel, the default staged probe) --------------------------------
+// The corpus is cut into TILES, the unit of the shared-memory ring.  Two modes, fixed per corpus:
+//   UNIT mode (parts = 1): a tile = up to kTileMaxUnits consecutive whole units (small units, e.g. the
+//             flush-shaped 1 000-row blocks: one mbarrier wait and one refill serve several units);
+//   KIND mode (parts = 2): a tile = one unit's {field, token} filters or its {fieldtoken} filter (large
+//             units, e.g. merged 10 000-row blocks: half-size stages give a ring twice as deep, and the
+//             batch's keys are sorted by kind so only the warps holding that kind work on the tile).
+// One 512-byte TileRec per tile, bulk-copied into the stage header; the 64-byte TileFill of the tile
+// that will occupy the same stage next travels with it, so a refill never waits on a global load.
+constexpr uint32_t kTileMaxUnits = 8;
+struct __align__(16) TileFilter {  // staged filters: m < 2^30, k < 2^16, at most 1 MB into the tile data
+    uint32_t m;        // bits; 0 = filter absent (cannot disqualify, query_exec.go:137-151)
+    uint32_t ih, il;   // hi / lo halves of floor(2^64/m), see mod_m32
+    uint32_t krel;     // k << 16 | (byte offset of the filter's words inside the tile data) >> 4
+};
+struct __align__(16) TileFill {    // what the thread that (re)fills a stage needs
+    uint64_t word_base;            // first word of the tile's data in the corpus words array (even)
+    uint32_t data_bytes;           // all filters of the tile, 16-byte multiple
+    uint32_t rec_bytes;            // bytes of the TileRec to copy: kTileRecFixedBytes + 48 * n_units
+    uint16_t nb16[kTileMaxUnits][3];  // padded bytes / 16 of each filter, in storage order
+};
+static_assert(sizeof(TileFill) == 64, "TileFill must be 64 bytes");
+struct __align__(16) TileRec {
+    uint32_t n_units;     // 1..kTileMaxUnits
+    uint32_t part_kinds;  // kinds this tile covers (7 in UNIT mode; 3 or 4 in KIND mode)
+    uint32_t flags;       // kTileFirstPart | kTileLastPart | kTileSmallK
+    uint32_t pad0;
+    TileFill fill;
+    uint32_t unit[kTileMaxUnits];         // global unit ids (matrix rows)
+    TileFilter f[kTileMaxUnits][3];       // [unit in tile][kind]
+    uint32_t pad1[4];
+};
+static_assert(sizeof(TileRec) == 512, "TileRec must be 512 bytes");
+constexpr uint32_t kTileRecFixedBytes = 16 + 64 + 32;   // head + fill + unit ids; the descriptors follow
+constexpr uint32_t kTileDescOff = kTileRecFixedBytes;
+constexpr uint32_t kTileFirstPart = 1u, kTileLastPart = 2u, kTileSmallK = 4u;  // SmallK: some filter has k < 4
+// stage = [TileRec 512][next tile's TileFill 64][pad 64][survivor bitmaps: units_cap x 128 B][tile data]
+constexpr uint32_t kTileNextFillOff = 512;
+constexpr uint32_t kTileBitmapOff = 640;
+inline uint32_t tile_header_bytes(uint32_t units_cap) { return kTileBitmapOff + 128u * units_cap; }
+// fixed shared memory of probe_tiles_kernel in front of the ring
+constexpr uint32_t kTilesPrefixBytes = 512;   // full[16] + aready[16] mbarriers, done[16] counters
+constexpr uint32_t kTilesSlotInfoBytes = 2 * kProbeMaxKeysPerPass;  // u16 per sorted key slot
+constexpr uint32_t kTilesPerBWarpBytes = 2 * kProbeMaxKeysPerPass + 128;  // survivor list + result row
+inline uint32_t tiles_fixed_smem(uint32_t n_b_warps, uint32_t n_keys) {
+    const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
+    return kTilesPrefixBytes + kTilesSlotInfoBytes + n_b_warps * kTilesPerBWarpBytes + hash_bytes;
+}
+
+struct ProbeTilesPlan {
+    int n_stages;
+    uint32_t stage_data_bytes;   // per-stage capacity for filter words (16-byte multiple)
+    uint32_t units_cap;          // units per tile the corpus was cut for (header size)
+    uint32_t parts;              // 1 = UNIT mode, 2 = KIND mode
+    size_t smem_bytes;
+    int grid;
+    int shape;                   // index into the compiled shapes (kernels_probe_tiles.cu)
+    int pdl;
+    const uint8_t* fuse_keys;    // fused hashing: packed key bytes / offsets on the device (else d_hashes)
+    const uint64_t* fuse_key_off;
+};
+cudaError_t probe_tiles_configure(int max_smem_optin);
+int probe_tiles_b_warps(int shape);       // B warps of a compiled shape (smem planning)
+int probe_tiles_n_shapes();
+const char* probe_tiles_shape_name(int shape);
+cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
+                               const uint32_t* d_n_items, const uint64_t* d_words, const uint64_t* d_hashes,
+                               const uint16_t* d_slotinfo, uint32_t key_base, uint32_t n_keys, uint32_t kind_mask,
+                               uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s, uint64_t* d_trace = nullptr,
+                               uint32_t trace_slots = 0);
+// hierarchical probe: keep the items (tiles, or pairs of tiles in KIND mode) with a unit whose parent survived
+cudaError_t launch_compact_tiles(const TileRec* d_tiles, uint32_t n_items, uint32_t parts, const uint32_t* d_parent,
+                                 const uint32_t* d_parent_mask32, TileRec* d_out, uint32_t* d_n_out, cudaStream_t s);
+
 cudaError_t probe_staged_configure(int max_smem_optin);
 cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_stab, uint32_t n_list,
                                 const uint64_t* d_words, const uint64_t* d_hashes, const uint8_t* d_kinds,

@@ -293,47 +293,6 @@ constexpr uint32_t kStage2QueueOff = kStage2CntOff + 16;                   // 10
 static_assert(kStage2QueueOff + 2 * kProbeMaxKeysPerPass == kProbeStage2HeaderBytes, "stage2 header layout");
 static_assert(kProbeStage2HeaderBytes % 16 == 0, "bulk copies need 16-byte aligned destinations");
 
-__device__ __forceinline__ uint32_t ld_volatile_shared_u32(const void* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-
-// locations START..k-1 of a survivor (k > START, START in 1..4), in groups of up to four locations:
-// the tests of a group are independent (no branch between them -> ILP 4, the dependent chain of a
-// test is ~14 instructions + one shared-memory load), the early exit sits between groups.  A warp
-// runs until its slowest lane is done anyway, so testing a whole group costs no extra issue slots
-// but a quarter of the latency.  location(i): i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2.
-// A location index >= k is computed but masked out (its bit index is < m, the load is in bounds).
-template <int START>
-__device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
-                                              uint32_t ih, uint32_t il, uint32_t k,
-                                              const uint32_t* __restrict__ w32) {
-    static_assert(START >= 1 && START <= 4, "phase A runs 1..4 tests");
-    auto probe = [&](uint64_t loc) -> uint32_t {
-        const uint32_t bit = mod_m32(loc, m, ih, il);
-        return (w32[bit >> 5] >> (bit & 31u)) & 1u;
-    };
-    if (START < 4) {  // first group: locations START..3
-        uint32_t ok = 1u;
-        if (START <= 1) ok &= probe(h1 + h3);
-        if (START <= 2) ok &= probe(h0 + 2 * h3) | static_cast<uint32_t>(k <= 2u);
-        if (START <= 3) ok &= probe(h1 + 3 * h2) | static_cast<uint32_t>(k <= 3u);
-        if (!ok) return false;
-    }
-    uint64_t ih2 = 4 * h2, ih3 = 4 * h3;  // i*h2, i*h3 at i = 4, 8, ...
-    for (uint32_t i = 4; i < k; i += 4) {
-        uint32_t ok = probe(h0 + ih2);
-        ok &= probe(h1 + ih3 + h3) | static_cast<uint32_t>(i + 1 >= k);
-        ok &= probe(h0 + ih3 + 2 * h3) | static_cast<uint32_t>(i + 2 >= k);
-        ok &= probe(h1 + ih2 + 3 * h2) | static_cast<uint32_t>(i + 3 >= k);
-        if (!ok) return false;
-        ih2 += 4 * h2;
-        ih3 += 4 * h3;
-    }
-    return true;
-}
-
 template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
 __global__ void __launch_bounds__((NA + NB) * 32, 1)
 probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,

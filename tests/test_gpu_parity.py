@@ -859,3 +859,111 @@ def test_probe_staged_variants_low_k_full_queue_and_refills(variant, stages, n_u
         corpus.close()
     finally:
         c2.close()
+
+
+# ------------------------------- tile ring (probe_tiles_kernel): shapes, modes, masked fills ---
+def _tiles_case(monkeypatch, env, n_units, key_kinds=(0, 1, 2), big=False, n_keys_cap=None):
+    """probe_tiles_kernel against the oracle for one (shape, mode, grouping, ring length) setting:
+    k = 1..5 and 30, absent filters, keys present in every unit (every key survives phase A), a ragged
+    second pass, and — key_kinds — batches that touch only some filter kinds (masked stage fills)."""
+    from tests.conftest import _has_gpu
+    if not _has_gpu():
+        pytest.skip("no CUDA device in this process")
+    monkeypatch.setenv("BSG_PROBE_VARIANT", "6")
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    rng = random.Random(777 + n_units + len(env))
+    shared_tok = rand_keys(rng, 700, 2, 14)       # present in every unit
+    shared_ft = rand_keys(rng, 500, 6, 24)
+    unit_keys = []
+    for u in range(n_units):
+        extra_t = 40 + u % 50 + (9000 if big and u % 3 == 0 else 0)
+        extra_f = 30 + u % 40 + (14000 if big and u % 5 == 0 else 0)
+        unit_keys.append((rand_keys(rng, 6, 3, 9), shared_tok + rand_keys(rng, extra_t, 15, 20),
+                          shared_ft + rand_keys(rng, extra_f, 25, 32)))
+    fprs = [0.6, 0.3, 0.2, 0.1, 0.05, 0.001, 1e-9]
+    absent = {(5, 1), (6, 2), (7, 0), (8, 0), (8, 1), (8, 2), (n_units - 1, 1)}
+    desc, words = _units_with_fprs(unit_keys, fprs, absent)
+    keys = shared_tok + shared_ft[:324]
+    kinds = [1] * len(shared_tok) + [2] * 324
+    extra, extra_kinds = _mixed_keys(rng, unit_keys[:50], 300, 401)
+    keys, kinds = keys + extra, kinds + extra_kinds
+    sel = [i for i, kd in enumerate(kinds) if kd in key_kinds]
+    if n_keys_cap:
+        sel = sel[:n_keys_cap]
+    keys, kinds = [keys[i] for i in sel], [kinds[i] for i in sel]
+    blob, off = N.pack_keys(keys)
+    kinds = np.asarray(kinds, dtype=np.uint8)
+    want = cref.probe_matrix(desc, words, n_units, blob, off, kinds)
+    c2 = bs.Context(0)
+    try:
+        corpus = bs.Corpus(c2, desc, words)
+        for _ in range(2):                         # twice: no state may leak between launches
+            q = bs.Query(corpus, keys, kinds, None)
+            q.run(N.PROBE_STAGED)
+            got, _ = q.fetch()
+            q.close()
+            assert np.array_equal(got, want), f"env {env} units {n_units} kinds {key_kinds}"
+        m, _ = corpus.probe(keys, kinds, None, want_mask=False)   # bsg_probe: hashing fused into the kernel
+        assert np.array_equal(m, want), f"bsg_probe env {env}"
+        corpus.close()
+    finally:
+        c2.close()
+
+
+@pytest.mark.parametrize("shape", range(7))
+def test_probe_tiles_every_shape(shape, monkeypatch):
+    _tiles_case(monkeypatch, {"BSG_TILES_SHAPE": shape}, 700)
+
+
+@pytest.mark.parametrize("env,n_units", [
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1}, 700),                          # UNIT mode, one unit per tile
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 3, "BSG_PROBE_STAGES": 2}, 700),   # ragged groups, 2-stage ring
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 8, "BSG_TILE_BYTES": 200000}, 1300),
+    ({"BSG_TILE_MODE": 1, "BSG_PROBE_STAGES": 1}, 700),                        # ring of one stage
+    ({"BSG_TILE_MODE": 2}, 700),                                               # KIND mode forced on small units
+    ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 3, "BSG_TILES_SHAPE": 3}, 700),
+    ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 1}, 450),
+    ({"BSG_PROBE_PDL": 0}, 300),
+])
+def test_probe_tiles_modes_groupings_rings(env, n_units, monkeypatch):
+    _tiles_case(monkeypatch, env, n_units)
+
+
+@pytest.mark.parametrize("env,key_kinds", [
+    ({"BSG_TILE_MODE": 1}, (1,)), ({"BSG_TILE_MODE": 1}, (0, 2)), ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 5}, (2,)),
+    ({"BSG_TILE_MODE": 2}, (1,)), ({"BSG_TILE_MODE": 2}, (2,)), ({"BSG_TILE_MODE": 2}, (0,)), ({"BSG_TILE_MODE": 2}, (0, 2)),
+])
+def test_probe_tiles_masked_fills(env, key_kinds, monkeypatch):
+    """A batch that touches only some kinds copies only those filters into the stages."""
+    _tiles_case(monkeypatch, env, 500, key_kinds=key_kinds)
+
+
+def test_probe_tiles_large_units_kind_mode_and_gather_mix(monkeypatch):
+    """Units of ~20-45 KB mixed with small ones: the corpus picks its mode by itself; small batches
+    still work (most A warps hold no key)."""
+    _tiles_case(monkeypatch, {}, 160, big=True)
+    _tiles_case(monkeypatch, {}, 90, big=True, n_keys_cap=7)
+
+
+@pytest.mark.parametrize("unit_kb", [100, 150, 400])
+def test_probe_units_beyond_the_old_75kb_limit(ctx, unit_kb):
+    """Units of 100 KB and 150 KB are staged per kind (probe_tiles KIND mode); 400 KB units exceed
+    shared memory and take the gather path.  All must equal the oracle."""
+    rng = random.Random(unit_kb)
+    n_tok = unit_kb * 1024 * 8 // 2 // 15          # ~14.4 bits per key at fpr 0.001, two big filters per unit
+    unit_keys = []
+    for u in range(5):
+        toks = [b"t%d-%d" % (u, i) for i in range(n_tok)]
+        fts = [b"f::t%d-%d" % (u, i) for i in range(n_tok)]
+        unit_keys.append(([b"f%d" % i for i in range(9)], toks, fts))
+    desc, words = oracle_units(unit_keys, 0.001)
+    keys, kinds = [], []
+    for u in range(5):
+        for i in rng.sample(range(n_tok), 40):
+            keys += [b"t%d-%d" % (u, i), b"f::t%d-%d" % (u, i)]
+            kinds += [1, 2]
+    for i in range(300):
+        keys.append(b"absent%d" % i)
+        kinds.append(i % 3)
+    _probe_case(ctx, desc, words, keys, kinds)
