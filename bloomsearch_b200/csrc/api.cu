@@ -811,7 +811,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
     // conservative ring budget: the largest fixed part any compiled shape needs for a full pass of keys
     int nb_max = 0;
-    for (int i = 0; i < probe_tiles_n_shapes(); ++i) nb_max = std::max(nb_max, probe_tiles_b_warps(i));
+    for (int i = 0; i < probe_tiles_n_shapes(); ++i) nb_max = std::max(nb_max, probe_tiles_teams(i));
     const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - tiles_fixed_smem(nb_max, kProbeMaxKeysPerPass);
     const uint64_t unit_limit = budget / 4 - tile_header_bytes(kTileMaxUnits);  // UNIT mode: a ring of >= 4 stages
     const uint64_t part_limit = budget / 2 - tile_header_bytes(1);              // KIND mode: >= 2 stages
@@ -1461,7 +1461,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             plan.stage_data_bytes = c->t_data_cap;
             plan.fuse_keys = fuse ? q->k_keys : nullptr;
             plan.fuse_key_off = fuse ? q->k_key_off : nullptr;
-            const uint32_t fixed = tiles_fixed_smem(probe_tiles_b_warps(plan.shape),
+            const uint32_t fixed = tiles_fixed_smem(probe_tiles_teams(plan.shape),
                                                     std::min<uint32_t>(q->n_keys, kProbeMaxKeysPerPass));
             const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
@@ -1832,4 +1832,5 @@ extern "C" float bsg_debug_last_build_kernel_ms(bsg_ctx* ctx) { return ctx ? ctx
 // ---- hooks for bsg_comm.cpp (keeps bsg_ctx's layout private to this file) ----
 extern "C" int bsg_ctx_device_internal(bsg_ctx* ctx) { return ctx->device; }
 extern "C" void** bsg_ctx_comm_slot_internal(bsg_ctx* ctx) { return &ctx->comm; }
+extern "C" void* bsg_ctx_stream_internal(bsg_ctx* ctx) { return ctx->cur_stream; }
 extern "C" int bsg_set_last_error_internal(int code, const char* msg) { return fail(code, "%s", msg); }

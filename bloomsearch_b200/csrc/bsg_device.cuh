@@ -229,6 +229,37 @@ __device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t
     return true;
 }
 
+// locations START..k-1 of a survivor in groups of FOUR starting at START (so the first group already has
+// ILP 4: a phase-B warp is latency bound, and 15/16 of the surviving absent keys die in it).  The location
+// pattern i%4 -> (h0|h1) + i*(h2|h3) is fixed per group member because the groups advance by 4.
+template <int START>
+__device__ __forceinline__ bool test_from_s32(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint32_t m,
+                                              uint32_t ih, uint32_t il, uint32_t k,
+                                              const uint32_t* __restrict__ w32) {
+    uint64_t loc[4], step[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int i = START + j;
+        const uint64_t a = (i & 1) ? h1 : h0;
+        const uint64_t b = (((i + (i & 1)) & 3) >> 1) ? h3 : h2;
+        loc[j] = a + static_cast<uint64_t>(i) * b;
+        step[j] = 4 * b;
+    }
+    for (uint32_t i0 = START; i0 < k; i0 += 4) {
+        uint32_t ok = 1u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t bit = mod_m32(loc[j], m, ih, il);
+            ok &= ((w32[bit >> 5] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(i0 + j >= k);
+            loc[j] += step[j];
+        }
+        if (!ok) return false;
+    }
+    return true;
+}
+
 // -------------------------------------------------- mbarrier / bulk copy ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

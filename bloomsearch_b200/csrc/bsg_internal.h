@@ -138,10 +138,11 @@ inline uint32_t tile_header_bytes(uint32_t units_cap) { return kTileBitmapOff + 
 // fixed shared memory of probe_tiles_kernel in front of the ring
 constexpr uint32_t kTilesPrefixBytes = 512;   // full[16] + aready[16] mbarriers, done[16] counters
 constexpr uint32_t kTilesSlotInfoBytes = 2 * kProbeMaxKeysPerPass;  // u16 per sorted key slot
-constexpr uint32_t kTilesPerBWarpBytes = 2 * kProbeMaxKeysPerPass + 128;  // survivor list + result row
-inline uint32_t tiles_fixed_smem(uint32_t n_b_warps, uint32_t n_keys) {
+// per B team: result row (128 B) + survivor counter (128-byte slot) + dense survivor list (u16 per key)
+constexpr uint32_t kTilesPerTeamBytes = 128 + 128 + 2 * kProbeMaxKeysPerPass;
+inline uint32_t tiles_fixed_smem(uint32_t n_teams, uint32_t n_keys) {
     const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
-    return kTilesPrefixBytes + kTilesSlotInfoBytes + n_b_warps * kTilesPerBWarpBytes + hash_bytes;
+    return kTilesPrefixBytes + kTilesSlotInfoBytes + n_teams * kTilesPerTeamBytes + hash_bytes;
 }
 
 struct ProbeTilesPlan {
@@ -157,7 +158,7 @@ struct ProbeTilesPlan {
     const uint64_t* fuse_key_off;
 };
 cudaError_t probe_tiles_configure(int max_smem_optin);
-int probe_tiles_b_warps(int shape);       // B warps of a compiled shape (smem planning)
+int probe_tiles_teams(int shape);         // B teams of a compiled shape (smem planning)
 int probe_tiles_n_shapes();
 const char* probe_tiles_shape_name(int shape);
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,

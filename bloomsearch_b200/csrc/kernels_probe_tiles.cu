@@ -14,16 +14,20 @@
 //   * every CTA keeps the batch's base hashes in shared memory (hashed in place by the CTA while the
 //     first fills are in flight, or copied from the hash kernel's output): phase B never leaves the SM;
 //   * phase A publishes survivors as BALLOT words (one store per 32 keys, no atomics, no queue); the
-//     phase-B warp that owns the unit expands the 1024-bit survivor bitmap into a dense list in its
-//     private scratch, tests locations NT..k-1 with dense lanes, ORs passing keys into its private
-//     result row (caller key order) and writes the row with one coalesced 128-byte store.
+//     phase-B team that owns the unit expands the 1024-bit survivor bitmap into one dense list (each
+//     warp of the team expands its share of the words), tests locations NT..k-1 with dense lanes in
+//     groups of four independent tests, ORs passing keys into the team's result row (caller key
+//     order) and writes the row with one coalesced 128-byte store.
 //
 //   phase A  warps 0..NA-1, KPT keys per thread, locations 0..NT-1 of each key in registers; walks the
 //            tiles in order; per unit of the tile: NT branch-free tests per key, one ballot per 32 keys.
-//   phase B  warps NA..NA+NB-1; warp w owns the units whose ordinal in this CTA's sequence is w mod NB
-//            (all parts of a unit go to the same warp, so the row is complete when its last part is).
-//            Every B warp visits every tile and arrives on its done counter (so no warp can fall two
-//            mbarrier phases behind a stage); the last arriver clears the bitmaps and refills the stage.
+//   phase B  warps NA..NA+NB-1 in NB/T teams of T warps; team g owns the units whose ordinal in this CTA's
+//            sequence is g mod NB/T (all parts of a unit go to the same team, so the row is complete when
+//            its last part is).  Two named barriers per task order list build -> tests -> row write-out; the
+//            survivor counter only grows, so nothing is reset between tasks.  Every B warp visits every
+//            tile and arrives on its done counter (so no warp can fall two mbarrier phases behind a
+//            stage); the last arriver clears the bitmaps and refills the stage.  (Measured: one warp per
+//            unit, 6-8 B warps, left phase B latency bound: 2b 25 us, 2a 68-80 us; see DESIGN.md.)
 #include <type_traits>
 
 #include "bsg_device.cuh"
@@ -109,17 +113,22 @@ __device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uin
     return pass != 0u;
 }
 
-template <int NA, int KPT, int NT, int NB, bool TRACE>
+__device__ __forceinline__ void team_barrier(uint32_t id, uint32_t n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
 __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const ProbeTilesArgs a) {
     static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
-    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4, "shape");
+    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0 && 32 % T == 0 && NB / T <= 15, "shape");
+    constexpr uint32_t NTEAMS = NB / T;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* aready = full + kProbeMaxStages;
     uint32_t* done = reinterpret_cast<uint32_t*>(aready + kProbeMaxStages);
     uint16_t* s_slot = reinterpret_cast<uint16_t*>(smem + kTilesPrefixBytes);
     uint8_t* bwarp_area = smem + kTilesPrefixBytes + kTilesSlotInfoBytes;
-    ulonglong2* htab = reinterpret_cast<ulonglong2*>(bwarp_area + NB * kTilesPerBWarpBytes);
+    ulonglong2* htab = reinterpret_cast<ulonglong2*>(bwarp_area + NTEAMS * kTilesPerTeamBytes);
     const uint32_t hash_bytes = ((a.n_keys + 31u) & ~31u) * 32u;
     uint8_t* stages = reinterpret_cast<uint8_t*>(htab) + hash_bytes;   // 128-byte aligned: every term is
 
@@ -142,6 +151,8 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
         }
         fence_barrier_init();
     }
+    for (uint32_t i = tid; i < NTEAMS * 64u; i += blockDim.x)  // team rows and survivor counters start at zero
+        reinterpret_cast<uint32_t*>(bwarp_area + (i / 64u) * kTilesPerTeamBytes)[i % 64u] = 0;
     for (uint32_t i = tid; i < S * a.units_cap * 32u; i += blockDim.x) {  // survivor bitmaps start clear
         const uint32_t s = i / (a.units_cap * 32u), r = i % (a.units_cap * 32u);
         reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(s) * a.stage_bytes + kTileBitmapOff)[r] = 0;
@@ -267,10 +278,15 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
     } else {
         // ------------------------------------------------------------------ phase B ---
         const uint32_t wb = warp - NA;
-        uint32_t* row = reinterpret_cast<uint32_t*>(bwarp_area + wb * kTilesPerBWarpBytes);
-        uint16_t* list = reinterpret_cast<uint16_t*>(bwarp_area + wb * kTilesPerBWarpBytes + 128);
+        const uint32_t team = wb / T, member = wb % T;
+        uint8_t* tarea = bwarp_area + team * kTilesPerTeamBytes;
+        uint32_t* row = reinterpret_cast<uint32_t*>(tarea);
+        uint32_t* tcnt = reinterpret_cast<uint32_t*>(tarea + 128);      // survivors appended so far (only grows)
+        uint16_t* list = reinterpret_cast<uint16_t*>(tarea + 256);
+        uint32_t cnt_base = 0;                                          // tcnt at the start of the current task
         const uint32_t out_words = (a.n_keys + 31) >> 5;
         uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
+        constexpr uint32_t WPM = 32 / T;                                // bitmap words each member expands
         for (uint32_t n = 0; n < my_tiles; ++n) {
             mbar_wait(&full[s], ph);  // the bulk copies' bytes (async proxy) are visible
             const uint4 head = *reinterpret_cast<const uint4*>(st);
@@ -278,33 +294,39 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
             for (uint32_t u = 0; u < head.x; ++u) {
                 // ordinal of the unit in this CTA's sequence; all parts of a unit share it
                 const uint32_t ord = P == 1 ? n * a.units_cap + u : (n >> 1);
-                if (ord % NB != wb) continue;
+                if (ord % NTEAMS != team) continue;
                 if (!waited) {  // every A warp has published its survivor words for this tile
                     mbar_wait_relaxed(&aready[s], ph, 1000u, 0u);
                     waited = true;
-                    if (TRACE && tr && lane == 0 && 4 + 4 * n < a.trace_slots) tr[4 + 4 * n] = globaltimer_ns();
+                    if (TRACE && tr && lane == 0 && member == 0 && 4 + 4 * n < a.trace_slots) tr[4 + 4 * n] = globaltimer_ns();
                 }
-                if (head.z & kTileFirstPart) row[lane] = 0;
-                // expand the 1024-bit survivor bitmap into a dense list of sorted slots
-                uint32_t w = ld_volatile_shared_u32(st + kTileBitmapOff + u * 128u + lane * 4u);
+                // ---- expand this member's words of the 1024-bit survivor bitmap into the team's dense list ----
+                const uint32_t widx = member + T * lane;                // interleaved: kinds are contiguous slot ranges
+                uint32_t w = lane < WPM ? ld_volatile_shared_u32(st + kTileBitmapOff + u * 128u + widx * 4u) : 0u;
                 const uint32_t cnt = __popc(w);
                 uint32_t incl = cnt;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
+                for (int d = 1; d < static_cast<int>(WPM); d <<= 1) {
                     const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= static_cast<uint32_t>(d)) incl += v;
                 }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t pos = incl - cnt;
+                const uint32_t mine = __shfl_sync(0xffffffffu, incl, WPM - 1);
+                uint32_t base = 0;
+                if (lane == 0 && mine) base = atomicAdd(tcnt, mine);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint32_t pos = base - cnt_base + incl - cnt;
                 while (w) {
                     const uint32_t b = __ffs(w) - 1;
-                    list[pos++] = static_cast<uint16_t>(lane * 32 + b);
+                    list[pos++] = static_cast<uint16_t>(widx * 32 + b);
                     w &= w - 1;
                 }
                 __syncwarp();
+                team_barrier(1 + team, T * 32);                          // the list and its length are complete
+                const uint32_t total = ld_volatile_shared_u32(tcnt) - cnt_base;
+                cnt_base += total;
                 const uint8_t* desc = st + kTileDescOff + u * 48u;
                 const uint8_t* data = st + a.hdr_bytes;
-                for (uint32_t c = 0; c < total; c += 32) {
+                for (uint32_t c = member * 32; c < total; c += T * 32) {
                     const uint32_t idx = c + lane;
                     if (idx < total) {
                         const uint32_t slot = list[idx];
@@ -313,20 +335,22 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                         const uint4 f = *reinterpret_cast<const uint4*>(desc + (si >> 14) * 16u);
                         bool pass = true;
                         if (f.x != 0)
-                            pass = test_tail_s32<NT>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
+                            pass = test_from_s32<NT>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
                                                      reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4)));
                         if (pass) atomicOr(&row[(si & 0x3ffu) >> 5], 1u << (si & 31u));
                     }
                 }
                 __syncwarp();
-                if (head.z & kTileLastPart) {  // the unit's row is complete: one coalesced store
+                team_barrier(1 + team, T * 32);                          // every member's tests are in the row
+                if (member == 0 && (head.z & kTileLastPart)) {           // the unit's row is complete: one coalesced store
                     const uint32_t unit = *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * u);
-                    if (lane < out_words)
-                        out_base[static_cast<size_t>(unit) * a.row_words32 + lane] = ld_volatile_shared_u32(&row[lane]);
+                    const uint32_t v = ld_volatile_shared_u32(&row[lane]);
+                    if (lane < out_words) out_base[static_cast<size_t>(unit) * a.row_words32 + lane] = v;
+                    row[lane] = 0;   // the next task's ORs come after its first barrier, which this warp joins later
                 }
-                __syncwarp();
             }
             // every B warp arrives for every tile; the last one clears the bitmaps and refills the stage
+            __syncwarp();
             uint32_t last = 0;
             if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == NB - 1;
             __syncwarp();
@@ -362,28 +386,29 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
     }
 }
 
-// ---- compiled shapes: <A warps, keys per A thread, A tests, B warps> ----
+// ---- compiled shapes: <A warps, keys per A thread, A tests, B warps, B team size> ----
 #define BSG_TILES_SHAPES(X) \
-    X(0, 16, 2, 3, 6) X(1, 16, 2, 2, 6) X(2, 16, 2, 3, 8) X(3, 16, 2, 3, 4) X(4, 8, 4, 3, 6) X(5, 8, 4, 2, 6) X(6, 16, 2, 2, 8)
+    X(0, 16, 2, 3, 16, 4) X(1, 16, 2, 2, 16, 4) X(2, 16, 2, 3, 12, 4) X(3, 16, 2, 3, 8, 2) X(4, 8, 4, 3, 16, 4) \
+    X(5, 16, 2, 3, 16, 8) X(6, 16, 2, 3, 16, 2) X(7, 8, 4, 2, 16, 4)
 
 int probe_tiles_n_shapes() {
     int n = 0;
-#define X(id, na, kpt, nt, nb) ++n;
+#define X(id, na, kpt, nt, nb, t) ++n;
     BSG_TILES_SHAPES(X)
 #undef X
     return n;
 }
-int probe_tiles_b_warps(int shape) {
+int probe_tiles_teams(int shape) {
     switch (shape) {
-#define X(id, na, kpt, nt, nb) case id: return nb;
+#define X(id, na, kpt, nt, nb, t) case id: return nb / t;
         BSG_TILES_SHAPES(X)
 #undef X
-        default: return 6;
+        default: return 4;
     }
 }
 const char* probe_tiles_shape_name(int shape) {
     switch (shape) {
-#define X(id, na, kpt, nt, nb) case id: return "probe_tiles_kernel<" #na "," #kpt "," #nt "," #nb ">";
+#define X(id, na, kpt, nt, nb, t) case id: return "probe_tiles_kernel<" #na "," #kpt "," #nt "," #nb "," #t ">";
         BSG_TILES_SHAPES(X)
 #undef X
         default: return "probe_tiles_kernel<?>";
@@ -392,19 +417,19 @@ const char* probe_tiles_shape_name(int shape) {
 
 cudaError_t probe_tiles_configure(int max_smem_optin) {
     cudaError_t e = cudaSuccess;
-#define X(id, na, kpt, nt, nb)                                                                                  \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             max_smem_optin);                                                                   \
-    if (e != cudaSuccess) return e;                                                                             \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             max_smem_optin);                                                                   \
+#define X(id, na, kpt, nt, nb, t)                                                                                  \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             max_smem_optin);                                                                      \
+    if (e != cudaSuccess) return e;                                                                                \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             max_smem_optin);                                                                      \
     if (e != cudaSuccess) return e;
     BSG_TILES_SHAPES(X)
 #undef X
     return e;
 }
 
-template <int NA, int KPT, int NT, int NB>
+template <int NA, int KPT, int NT, int NB, int T>
 static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs& args, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
@@ -416,8 +441,8 @@ static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.pdl ? 1 : 0;
-    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, true>, args);
-    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, false>, args);
+    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, T, true>, args);
+    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, T, false>, args);
 }
 
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
@@ -449,7 +474,7 @@ cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tile
     a.trace = d_trace;
     a.trace_slots = d_trace ? trace_slots : 0;
     switch (plan.shape) {
-#define X(id, na, kpt, nt, nb) case id: return tiles_launch<na, kpt, nt, nb>(plan, a, s);
+#define X(id, na, kpt, nt, nb, t) case id: return tiles_launch<na, kpt, nt, nb, t>(plan, a, s);
         BSG_TILES_SHAPES(X)
 #undef X
         default: return cudaErrorInvalidValue;
