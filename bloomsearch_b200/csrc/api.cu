@@ -435,6 +435,59 @@ extern "C" int bsg_hash_keys(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* 
 }
 
 // ------------------------------------------------------------------- build ---
+namespace {
+// Validated launch plan of a build: filter descriptors over the caller's out_words layout, and the key
+// groups split so that one CTA never owns more than kSplit keys (sub-groups share the filters; the staged
+// bitset is merged with RED.OR).  group_begin is a CSR array, so sub-group boundaries stay contiguous.
+struct BuildPlan {
+    std::vector<BuildFilter> bf;
+    std::vector<uint64_t> gbe;
+    std::vector<uint32_t> gf, gf2;
+    uint32_t n_sub = 0;
+    uint32_t smem_cap = 0;
+};
+int plan_build(bsg_ctx* ctx, uint64_t n_keys, const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_filter,
+               const uint32_t* group_filter2, const bsg_filter_desc* desc, uint32_t n_filters, uint64_t n_words,
+               BuildPlan& P) {
+    P.bf.resize(n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+        if (desc[f].m == 0) return fail(BSG_ERR_INVALID, "filter %u: m == 0", f);
+        int rc = validate_filter(desc[f], n_words, "filter", f);
+        if (rc) return rc;
+        P.bf[f] = BuildFilter{desc[f].word_off, desc[f].m, reciprocal(desc[f].m), static_cast<uint32_t>(desc[f].k),
+                              static_cast<uint32_t>(words_for(desc[f].m))};
+    }
+    constexpr uint64_t kSplit = 16384;
+    P.gbe.reserve(static_cast<size_t>(n_groups) + 1);
+    P.gf.reserve(n_groups);
+    if (group_filter2) P.gf2.reserve(n_groups);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        const uint64_t b = group_begin[g], e = group_begin[g + 1];
+        if (e < b || e > n_keys) return fail(BSG_ERR_INVALID, "group %u: key range [%llu,%llu) invalid", g,
+                                             (unsigned long long)b, (unsigned long long)e);
+        if (group_filter[g] >= n_filters) return fail(BSG_ERR_INVALID, "group %u: filter id out of range", g);
+        if (group_filter2 && group_filter2[g] != BSG_NO_FILTER && group_filter2[g] >= n_filters)
+            return fail(BSG_ERR_INVALID, "group %u: secondary filter id out of range", g);
+        for (uint64_t s0 = b; s0 < e; s0 += kSplit) {
+            P.gbe.push_back(s0);
+            P.gf.push_back(group_filter[g]);
+            if (group_filter2) P.gf2.push_back(group_filter2[g]);
+        }
+    }
+    P.gbe.push_back(n_groups ? group_begin[n_groups] : 0);
+    if (P.gf.size() > 0x7fffffffull) return fail(BSG_ERR_INVALID, "too many groups");
+    P.n_sub = static_cast<uint32_t>(P.gf.size());
+    // shared-memory staging capacity: largest primary filter that still lets 2 CTAs share an SM
+    const uint32_t cap_limit = static_cast<uint32_t>(std::min<int>(ctx->max_smem_optin, 100 * 1024));
+    P.smem_cap = 0;
+    for (uint32_t g = 0; g < P.n_sub; ++g) {
+        const uint64_t bytes = static_cast<uint64_t>(P.bf[P.gf[g]].nwords) * 8;
+        if (bytes <= cap_limit) P.smem_cap = std::max<uint32_t>(P.smem_cap, static_cast<uint32_t>((bytes + 15) & ~15ull));
+    }
+    return BSG_OK;
+}
+}  // namespace
+
 extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
                          const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_filter,
                          const uint32_t* group_filter2, const bsg_filter_desc* desc, uint32_t n_filters,
@@ -448,50 +501,15 @@ extern "C" int bsg_build(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_
         const uint64_t bad = first_bad_offset(key_off, n_keys);
         if (bad != n_keys) return fail(BSG_ERR_INVALID, "key_off not monotone at %llu", (unsigned long long)bad);
     }
-    std::vector<BuildFilter> bf(n_filters);
-    for (uint32_t f = 0; f < n_filters; ++f) {
-        if (desc[f].m == 0) return fail(BSG_ERR_INVALID, "filter %u: m == 0", f);
-        int rc = validate_filter(desc[f], n_words, "filter", f);
-        if (rc) return rc;
-        bf[f].word_off = desc[f].word_off;
-        bf[f].m = desc[f].m;
-        bf[f].inv = reciprocal(desc[f].m);
-        bf[f].k = static_cast<uint32_t>(desc[f].k);
-        bf[f].nwords = static_cast<uint32_t>(words_for(desc[f].m));
+    BuildPlan P;
+    {
+        int prc = plan_build(ctx, n_keys, group_begin, n_groups, group_filter, group_filter2, desc, n_filters, n_words, P);
+        if (prc) return prc;
     }
-    // Split oversized groups so one CTA never owns more than kSplit keys (sub-groups
-    // share the filters; the staged bitset is merged with RED.OR).  group_begin is a
-    // CSR array, so sub-group boundaries stay contiguous.
-    constexpr uint64_t kSplit = 16384;
-    std::vector<uint64_t> gbe;
-    std::vector<uint32_t> gf, gf2;
-    gbe.reserve(static_cast<size_t>(n_groups) + 1);
-    gf.reserve(n_groups);
-    if (group_filter2) gf2.reserve(n_groups);
-    for (uint32_t g = 0; g < n_groups; ++g) {
-        const uint64_t b = group_begin[g], e = group_begin[g + 1];
-        if (e < b || e > n_keys) return fail(BSG_ERR_INVALID, "group %u: key range [%llu,%llu) invalid", g,
-                                             (unsigned long long)b, (unsigned long long)e);
-        if (group_filter[g] >= n_filters) return fail(BSG_ERR_INVALID, "group %u: filter id out of range", g);
-        if (group_filter2 && group_filter2[g] != BSG_NO_FILTER && group_filter2[g] >= n_filters)
-            return fail(BSG_ERR_INVALID, "group %u: secondary filter id out of range", g);
-        for (uint64_t s0 = b; s0 < e; s0 += kSplit) {
-            gbe.push_back(s0);
-            gf.push_back(group_filter[g]);
-            if (group_filter2) gf2.push_back(group_filter2[g]);
-        }
-    }
-    gbe.push_back(n_groups ? group_begin[n_groups] : 0);
-    if (gf.size() > 0x7fffffffull) return fail(BSG_ERR_INVALID, "too many groups");
-    const uint32_t n_sub = static_cast<uint32_t>(gf.size());
-
-    // shared-memory staging capacity: largest primary filter that still lets 2 CTAs share an SM
-    const uint32_t cap_limit = static_cast<uint32_t>(std::min<int>(ctx->max_smem_optin, 100 * 1024));
-    uint32_t smem_cap = 0;
-    for (uint32_t g = 0; g < n_sub; ++g) {
-        const uint64_t bytes = static_cast<uint64_t>(bf[gf[g]].nwords) * 8;
-        if (bytes <= cap_limit) smem_cap = std::max<uint32_t>(smem_cap, static_cast<uint32_t>((bytes + 15) & ~15ull));
-    }
+    const std::vector<BuildFilter>& bf = P.bf;
+    const std::vector<uint64_t>& gbe = P.gbe;
+    const std::vector<uint32_t>&gf = P.gf, &gf2 = P.gf2;
+    const uint32_t n_sub = P.n_sub, smem_cap = P.smem_cap;
 
     cudaStream_t s = pool_get(ctx);
     if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
@@ -641,6 +659,31 @@ extern "C" int bsg_build_fieldtokens(bsg_ctx* ctx, const uint8_t* strings, const
     return rc;
 }
 
+// Counts on device-resident keys (shared by bsg_count_distinct and bsg_keyset_count_distinct).
+static int count_distinct_device(bsg_ctx* ctx, const uint8_t* d_keys, const uint64_t* d_off, uint64_t n_keys,
+                                 const uint64_t* d_gb, uint32_t n_groups, const uint32_t* group_parent, uint32_t n_parents,
+                                 uint64_t* out_group_counts, uint64_t* out_parent_counts, cudaStream_t s) {
+    (void)ctx;
+    DevBuf<uint8_t> d_em;
+    DevBuf<uint32_t> d_gp;
+    DevBuf<unsigned long long> d_gc, d_pc;
+    if (d_gc.alloc(n_groups) != cudaSuccess || d_em.alloc(count_distinct_scratch_bytes(n_keys)) != cudaSuccess ||
+        (group_parent && (d_gp.alloc(n_groups) != cudaSuccess || d_pc.alloc(n_parents) != cudaSuccess)))
+        return fail(BSG_ERR_NOMEM, "device alloc");
+    cudaError_t e = cudaMemsetAsync(d_gc.p, 0, n_groups * 8, s);
+    if (e == cudaSuccess && group_parent) e = cudaMemsetAsync(d_pc.p, 0, std::max<uint32_t>(n_parents, 1) * 8, s);
+    if (e == cudaSuccess && group_parent) e = cudaMemcpyAsync(d_gp.p, group_parent, n_groups * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+        e = launch_count_distinct(d_keys, d_off, n_keys, d_gb, n_groups, group_parent ? d_gp.p : nullptr, d_em.p, d_gc.p,
+                                  group_parent ? d_pc.p : nullptr, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_group_counts, d_gc.p, n_groups * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && group_parent)
+        e = cudaMemcpyAsync(out_parent_counts, d_pc.p, n_parents * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(BSG_ERR_CUDA, "count_distinct: %s", cudaGetErrorString(e));
+    return BSG_OK;
+}
+
 // (f.3) exact distinct counts per group and per parent union — replaces the dedup the Go maps do.
 extern "C" int bsg_count_distinct(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
                                   const uint64_t* group_begin, uint32_t n_groups, const uint32_t* group_parent,
@@ -667,39 +710,204 @@ extern "C" int bsg_count_distinct(bsg_ctx* ctx, const uint8_t* keys, const uint6
     if (n_keys == 0 || n_groups == 0) return BSG_OK;
     cudaStream_t s = pool_get(ctx);
     if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
-    DevBuf<uint8_t> d_keys, d_em;
+    DevBuf<uint8_t> d_keys;
     DevBuf<uint64_t> d_off, d_gb;
-    DevBuf<uint32_t> d_gp;
-    DevBuf<unsigned long long> d_gc, d_pc;
     int rc = BSG_OK;
     do {
         if (d_keys.alloc(nbytes + kKeyPad) != cudaSuccess || d_off.alloc(n_keys + 1) != cudaSuccess ||
-            d_gb.alloc(n_groups + 1) != cudaSuccess || d_gc.alloc(n_groups) != cudaSuccess ||
-            d_em.alloc(count_distinct_scratch_bytes(n_keys)) != cudaSuccess ||
-            (group_parent && (d_gp.alloc(n_groups) != cudaSuccess || d_pc.alloc(n_parents) != cudaSuccess))) {
+            d_gb.alloc(n_groups + 1) != cudaSuccess) {
             rc = fail(BSG_ERR_NOMEM, "device alloc");
             break;
         }
-        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
-        cudaError_t e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_gc.p, 0, n_groups * 8, s);
-        if (e == cudaSuccess && group_parent) e = cudaMemsetAsync(d_pc.p, 0, std::max<uint32_t>(n_parents, 1) * 8, s);
-        if (e == cudaSuccess) e = upload(ctx, d_keys.p, keys, nbytes, s);
-        if (e == cudaSuccess) e = upload(ctx, d_off.p, key_off, (n_keys + 1) * 8, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_gb.p, group_begin, (static_cast<size_t>(n_groups) + 1) * 8, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess && group_parent) e = cudaMemcpyAsync(d_gp.p, group_parent, n_groups * 4, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess)
-            e = launch_count_distinct(d_keys.p, d_off.p, n_keys, d_gb.p, n_groups, group_parent ? d_gp.p : nullptr, d_em.p,
-                                      d_gc.p, group_parent ? d_pc.p : nullptr, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_group_counts, d_gc.p, n_groups * 8, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && group_parent)
-            e = cudaMemcpyAsync(out_parent_counts, d_pc.p, n_parents * 8, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "bsg_count_distinct: %s", cudaGetErrorString(e));
+        cudaError_t e;
+        {
+            std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+            e = cudaMemsetAsync(d_keys.p + nbytes, 0, kKeyPad, s);
+            if (e == cudaSuccess) e = upload(ctx, d_keys.p, keys, nbytes, s);
+            if (e == cudaSuccess) e = upload(ctx, d_off.p, key_off, (n_keys + 1) * 8, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_gb.p, group_begin, (static_cast<size_t>(n_groups) + 1) * 8, cudaMemcpyHostToDevice, s);
+        }
+        if (e != cudaSuccess) { rc = fail(BSG_ERR_CUDA, "bsg_count_distinct: %s", cudaGetErrorString(e)); break; }
+        rc = count_distinct_device(ctx, d_keys.p, d_off.p, n_keys, d_gb.p, n_groups, group_parent, n_parents, out_group_counts,
+                                   out_parent_counts, s);
     } while (0);
     pool_put(ctx, s);
     return rc;
 }
+
+// ---------------------------------------------------------------- key sets ---
+// A key set is a batch of grouped keys resident in HBM: the build side's counterpart of bsg_query.  The
+// emissions of a flush cross PCIe ONCE; exact distinct counts (bsg_keyset_count_distinct), filter sizing
+// on the host, and the build (bsg_keyset_build) then all read the resident copy.  bsg_keyset_build is
+// asynchronous on the ctx stream and can write into any device buffer, e.g. symmetric memory that
+// bsg_or_reduce_device combines across GPUs afterwards.
+struct bsg_keyset {
+    int device = 0;
+    uint64_t n_keys = 0;
+    uint32_t n_groups = 0;
+    uint8_t* d_keys = nullptr;
+    uint64_t* d_off = nullptr;
+    uint64_t* d_gb = nullptr;            // caller's group_begin
+    std::vector<uint64_t> h_gb;
+    // set by bsg_keyset_set_filters
+    bool planned = false;
+    uint32_t n_sub = 0, smem_cap = 0, n_filters = 0;
+    bool has_gf2 = false;
+    uint64_t n_words = 0;
+    uint64_t* d_sub_gb = nullptr;
+    uint32_t *d_gf = nullptr, *d_gf2 = nullptr;
+    BuildFilter* d_bf = nullptr;
+    uint64_t* d_out = nullptr;           // internal output (when the caller passes no buffer)
+    size_t cap_out = 0;
+    const uint64_t* last_out = nullptr;  // where the last build wrote
+};
+
+extern "C" void bsg_keyset_free(bsg_keyset* k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    cudaFree(k->d_keys);
+    cudaFree(k->d_off);
+    cudaFree(k->d_gb);
+    cudaFree(k->d_sub_gb);
+    cudaFree(k->d_gf);
+    cudaFree(k->d_gf2);
+    cudaFree(k->d_bf);
+    cudaFree(k->d_out);
+    delete k;
+}
+
+extern "C" int bsg_keyset_create(bsg_ctx* ctx, const uint8_t* keys, const uint64_t* key_off, uint64_t n_keys,
+                                 const uint64_t* group_begin, uint32_t n_groups, bsg_keyset** out) {
+    if (!ctx || !out || !key_off || (n_groups && !group_begin)) return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
+    if (nbytes && !keys) return fail(BSG_ERR_INVALID, "keys is NULL");
+    {
+        const uint64_t bad = first_bad_offset(key_off, n_keys);
+        if (bad != n_keys) return fail(BSG_ERR_INVALID, "key_off not monotone at %llu", (unsigned long long)bad);
+    }
+    for (uint32_t g = 0; g < n_groups; ++g)
+        if (group_begin[g + 1] < group_begin[g] || group_begin[g + 1] > n_keys)
+            return fail(BSG_ERR_INVALID, "group %u: key range invalid", g);
+    if (n_groups && (group_begin[0] != 0 || group_begin[n_groups] != n_keys))
+        return fail(BSG_ERR_INVALID, "groups must cover all keys");
+    bsg_keyset* k = new (std::nothrow) bsg_keyset();
+    if (!k) return fail(BSG_ERR_NOMEM, "keyset alloc");
+    k->device = ctx->device;
+    k->n_keys = n_keys;
+    k->n_groups = n_groups;
+    k->h_gb.assign(group_begin, group_begin + (n_groups ? n_groups + 1 : 0));
+    if (k->h_gb.empty()) k->h_gb.push_back(0);
+    cudaStream_t s = pool_get(ctx);
+    if (!s) { delete k; return fail(BSG_ERR_CUDA, "stream create failed"); }
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_keys), nbytes + kKeyPad));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_off), (n_keys + 1) * 8));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_gb), k->h_gb.size() * 8));
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+        CUDA_TRY(cudaMemsetAsync(k->d_keys + nbytes, 0, kKeyPad, s));
+        CUDA_TRY(upload(ctx, k->d_keys, keys, nbytes, s));
+        CUDA_TRY(upload(ctx, k->d_off, key_off, (n_keys + 1) * 8, s));
+        CUDA_TRY(cudaMemcpyAsync(k->d_gb, k->h_gb.data(), k->h_gb.size() * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return BSG_OK;
+    };
+    int rc = body();
+    pool_put(ctx, s);
+    if (rc) { bsg_keyset_free(k); return rc; }
+    *out = k;
+    return BSG_OK;
+}
+
+extern "C" int bsg_keyset_count_distinct(bsg_ctx* ctx, bsg_keyset* k, const uint32_t* group_parent, uint32_t n_parents,
+                                         uint64_t* out_group_counts, uint64_t* out_parent_counts) {
+    if (!ctx || !k || (k->n_groups && !out_group_counts) || ((group_parent != nullptr) != (out_parent_counts != nullptr)))
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint32_t n_groups = k->n_groups;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        out_group_counts[g] = 0;
+        if (group_parent && group_parent[g] >= n_parents) return fail(BSG_ERR_INVALID, "group %u: parent out of range", g);
+    }
+    for (uint32_t p = 0; group_parent && p < n_parents; ++p) out_parent_counts[p] = 0;
+    if (k->n_keys == 0 || n_groups == 0) return BSG_OK;
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    int rc = count_distinct_device(ctx, k->d_keys, k->d_off, k->n_keys, k->d_gb, n_groups, group_parent, n_parents,
+                                   out_group_counts, out_parent_counts, s);
+    pool_put(ctx, s);
+    return rc;
+}
+
+extern "C" int bsg_keyset_set_filters(bsg_ctx* ctx, bsg_keyset* k, const uint32_t* group_filter, const uint32_t* group_filter2,
+                                      const bsg_filter_desc* desc, uint32_t n_filters, uint64_t n_words) {
+    if (!ctx || !k || !desc || (k->n_groups && !group_filter)) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    BuildPlan P;
+    int rc = plan_build(ctx, k->n_keys, k->h_gb.data(), k->n_groups, group_filter, group_filter2, desc, n_filters, n_words, P);
+    if (rc) return rc;
+    cudaFree(k->d_sub_gb); cudaFree(k->d_gf); cudaFree(k->d_gf2); cudaFree(k->d_bf);
+    k->d_sub_gb = nullptr; k->d_gf = nullptr; k->d_gf2 = nullptr; k->d_bf = nullptr;
+    k->planned = false;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_sub_gb), P.gbe.size() * 8));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_gf), std::max<size_t>(P.gf.size(), 1) * 4));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_bf), std::max<size_t>(P.bf.size(), 1) * sizeof(BuildFilter)));
+    CUDA_TRY(cudaMemcpy(k->d_sub_gb, P.gbe.data(), P.gbe.size() * 8, cudaMemcpyHostToDevice));
+    if (!P.gf.empty()) CUDA_TRY(cudaMemcpy(k->d_gf, P.gf.data(), P.gf.size() * 4, cudaMemcpyHostToDevice));
+    if (!P.bf.empty()) CUDA_TRY(cudaMemcpy(k->d_bf, P.bf.data(), P.bf.size() * sizeof(BuildFilter), cudaMemcpyHostToDevice));
+    k->has_gf2 = group_filter2 != nullptr;
+    if (k->has_gf2) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_gf2), std::max<size_t>(P.gf2.size(), 1) * 4));
+        if (!P.gf2.empty()) CUDA_TRY(cudaMemcpy(k->d_gf2, P.gf2.data(), P.gf2.size() * 4, cudaMemcpyHostToDevice));
+    }
+    k->n_sub = P.n_sub;
+    k->smem_cap = P.smem_cap;
+    k->n_filters = n_filters;
+    k->n_words = n_words;
+    k->planned = true;
+    return BSG_OK;
+}
+
+extern "C" int bsg_keyset_build(bsg_ctx* ctx, bsg_keyset* k, uint64_t* d_out_words) {
+    if (!ctx || !k) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!k->planned) return fail(BSG_ERR_INVALID, "bsg_keyset_set_filters has not been called");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->cur_stream;
+    uint64_t* out = d_out_words;
+    if (!out) {
+        if (k->cap_out < k->n_words * 8 || !k->d_out) {
+            cudaFree(k->d_out);
+            k->d_out = nullptr;
+            k->cap_out = 0;
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&k->d_out), std::max<uint64_t>(k->n_words, 1) * 8));
+            k->cap_out = std::max<uint64_t>(k->n_words, 1) * 8;
+        }
+        out = k->d_out;
+    }
+    CUDA_TRY(cudaMemsetAsync(out, 0, std::max<uint64_t>(k->n_words, 1) * 8, s));
+    CUDA_TRY(launch_build(k->d_keys, k->d_off, k->d_sub_gb, k->n_sub, k->d_gf, k->has_gf2 ? k->d_gf2 : nullptr, k->d_bf, out,
+                          k->smem_cap, s));
+    k->last_out = out;
+    return BSG_OK;
+}
+
+extern "C" int bsg_keyset_fetch(bsg_ctx* ctx, bsg_keyset* k, uint64_t* out_words) {
+    if (!ctx || !k || !out_words) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!k->last_out) return fail(BSG_ERR_INVALID, "bsg_keyset_build has not been called");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->cur_stream));
+    if (k->n_words == 0) return BSG_OK;
+    if (k->n_words * 8 < kStageThreshold) {
+        CUDA_TRY(cudaMemcpy(out_words, k->last_out, k->n_words * 8, cudaMemcpyDeviceToHost));
+    } else {
+        std::unique_lock<std::mutex> stage_lk(ctx->stage_mu);
+        CUDA_TRY(staged_copy(ctx, const_cast<uint64_t*>(k->last_out), out_words, k->n_words * 8, false));
+    }
+    return BSG_OK;
+}
+
+extern "C" const uint64_t* bsg_keyset_device_words(const bsg_keyset* k) { return k ? k->last_out : nullptr; }
 
 // ------------------------------------------------------------------ corpus ---
 struct bsg_corpus {

@@ -138,8 +138,9 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
     const uint32_t G = gridDim.x;
     const uint32_t S = a.n_stages;
     const uint32_t P = a.parts;
-    // optional timeline (profiling only), per CTA: [0] start, [1] hashes ready; per tile n:
-    // [2+4n] resident (A warp 0), [3+4n] A warp 0 done, [4+4n] all A done (first B task), [5+4n] released
+    // optional timeline (profiling only), per CTA: [0] start, [1] hashes ready; per tile n, base b = 2+8n:
+    // [b] resident (A warp 0), [b+1] A warp 0 done, [b+2] all A done (a B task starts), [b+3] released,
+    // [b+4] list expanded, [b+5] after team barrier 1, [b+6] tests done, [b+7] after team barrier 2 (member 0 of a team)
     uint64_t* tr = (TRACE && a.trace) ? a.trace + static_cast<size_t>(blockIdx.x) * a.trace_slots : nullptr;
     if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
 
@@ -242,36 +243,67 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
         warp_kinds = __reduce_or_sync(0xffffffffu, warp_kinds);
         for (uint32_t n = 0; n < my_tiles; ++n) {
             mbar_wait(&full[s], ph);
-            if (TRACE && tr && tid == 0 && 2 + 4 * n < a.trace_slots) tr[2 + 4 * n] = globaltimer_ns();
+            if (TRACE && tr && tid == 0 && 2 + 8 * n < a.trace_slots) tr[2 + 8 * n] = globaltimer_ns();
             const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
             if (warp_kinds & head.y) {
                 const uint8_t* data = st + a.hdr_bytes;
-                uint32_t* bm = reinterpret_cast<uint32_t*>(st + kTileBitmapOff) + warp * KPT;
                 const uint8_t* desc = st + kTileDescOff;
+                // Ballot words stay in registers until the tile is done (lane u*KPT+j keeps the word of unit u,
+                // key slot j): no shared-memory store inside the loop, so the loads and modulo chains of
+                // consecutive keys / units can overlap (phase A is latency bound, not issue bound).
+                uint32_t mybits = 0;
                 auto unit_loop = [&](auto small_k) {
                     constexpr bool SMALLK = decltype(small_k)::value;
-                    for (uint32_t u = 0; u < head.x; ++u, desc += 48, bm += 32) {
+#pragma unroll 2
+                    for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
+                        uint4 f[KPT];
+                        bool act[KPT], pass[KPT];
 #pragma unroll
                         for (int j = 0; j < KPT; ++j) {
-                            bool surv = false;
-                            if (kbit[j] & head.y) {
-                                const uint4 f = *reinterpret_cast<const uint4*>(desc + koff[j]);
-                                // absent filter: cannot disqualify (query_exec.go:137-151) -> phase B sets the bit
-                                surv = f.x == 0 ? true : first_tests<NT, SMALLK>(loc[j], f, data);
+                            act[j] = (kbit[j] & head.y) != 0;
+                            f[j] = make_uint4(0, 0, 0, 0);
+                            if (act[j]) f[j] = *reinterpret_cast<const uint4*>(desc + koff[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < KPT; ++j) {
+                            // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> phase B sets the bit
+                            const bool test = act[j] && f[j].x != 0;
+                            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f[j].w & 0xffffu) << 4));
+                            uint32_t bit[NT], wv[NT];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f[j].x, f[j].y, f[j].z);
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
+                            uint32_t p = 1u;
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) {
+                                uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
+                                if (SMALLK) b |= static_cast<uint32_t>((f[j].w >> 16) <= static_cast<uint32_t>(t));
+                                p &= b;
                             }
-                            const uint32_t bits = __ballot_sync(0xffffffffu, surv);
-                            if (lane == 0) bm[j] = bits;
+                            pass[j] = act[j] && (f[j].x == 0 || p != 0u);
+                        }
+#pragma unroll
+                        for (int j = 0; j < KPT; ++j) {
+                            const uint32_t bits = __ballot_sync(0xffffffffu, pass[j]);
+                            if (lane == u * KPT + j) mybits = bits;
                         }
                     }
                 };
                 if (head.z & kTileSmallK) unit_loop(std::true_type{});
                 else unit_loop(std::false_type{});
+                // lane 0 publishes the words (it is also the lane that arrives on the barrier below)
+                uint32_t* bm = reinterpret_cast<uint32_t*>(st + kTileBitmapOff) + warp * KPT;
+                for (uint32_t i = 0; i < head.x * KPT; ++i) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, mybits, i);
+                    if (lane == 0) bm[(i / KPT) * 32 + (i % KPT)] = v;
+                }
             }
             // lane 0 wrote this warp's bitmap words and lane 0 arrives (release): a B warp's try_wait
             // (acquire) on aready orders its loads after them
             if (lane == 0) mbar_arrive(&aready[s]);
             __syncwarp();
-            if (TRACE && tr && tid == 0 && 3 + 4 * n < a.trace_slots) tr[3 + 4 * n] = globaltimer_ns();
+            if (TRACE && tr && tid == 0 && 3 + 8 * n < a.trace_slots) tr[3 + 8 * n] = globaltimer_ns();
             st += a.stage_bytes;
             if (++s == S) { s = 0; ph ^= 1u; st = stages; }
         }
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                 if (!waited) {  // every A warp has published its survivor words for this tile
                     mbar_wait_relaxed(&aready[s], ph, 1000u, 0u);
                     waited = true;
-                    if (TRACE && tr && lane == 0 && member == 0 && 4 + 4 * n < a.trace_slots) tr[4 + 4 * n] = globaltimer_ns();
+                    if (TRACE && tr && lane == 0 && member == 0 && 4 + 8 * n < a.trace_slots) tr[4 + 8 * n] = globaltimer_ns();
                 }
                 // ---- expand this member's words of the 1024-bit survivor bitmap into the team's dense list ----
                 const uint32_t widx = member + T * lane;                // interleaved: kinds are contiguous slot ranges
@@ -321,7 +353,9 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                     w &= w - 1;
                 }
                 __syncwarp();
+                if (TRACE && tr && lane == 0 && member == 0 && 6 + 8 * n < a.trace_slots) tr[6 + 8 * n] = globaltimer_ns();
                 team_barrier(1 + team, T * 32);                          // the list and its length are complete
+                if (TRACE && tr && lane == 0 && member == 0 && 7 + 8 * n < a.trace_slots) tr[7 + 8 * n] = globaltimer_ns();
                 const uint32_t total = ld_volatile_shared_u32(tcnt) - cnt_base;
                 cnt_base += total;
                 const uint8_t* desc = st + kTileDescOff + u * 48u;
@@ -341,7 +375,9 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                     }
                 }
                 __syncwarp();
+                if (TRACE && tr && lane == 0 && member == 0 && 8 + 8 * n < a.trace_slots) tr[8 + 8 * n] = globaltimer_ns();
                 team_barrier(1 + team, T * 32);                          // every member's tests are in the row
+                if (TRACE && tr && lane == 0 && member == 0 && 9 + 8 * n < a.trace_slots) tr[9 + 8 * n] = globaltimer_ns();
                 if (member == 0 && (head.z & kTileLastPart)) {           // the unit's row is complete: one coalesced store
                     const uint32_t unit = *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * u);
                     const uint32_t v = ld_volatile_shared_u32(&row[lane]);
@@ -360,7 +396,7 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                     reinterpret_cast<uint32_t*>(st + kTileBitmapOff)[u * 32 + lane] = 0;
                 __syncwarp();
                 if (lane == 0) {
-                    if (TRACE && tr && 5 + 4 * n < a.trace_slots) tr[5 + 4 * n] = globaltimer_ns();
+                    if (TRACE && tr && 5 + 8 * n < a.trace_slots) tr[5 + 8 * n] = globaltimer_ns();
                     done[s] = 0;
                     const uint32_t nxt = n + S;
                     if (nxt < my_tiles) {
