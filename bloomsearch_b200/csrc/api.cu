@@ -921,6 +921,7 @@ struct bsg_corpus {
     uint32_t n_staged = 0;
     uint32_t* d_gather_list = nullptr;
     uint32_t n_gather = 0;
+    uint32_t* d_bad32 = nullptr;   // sections loader: bit u = unit u's filter section failed to parse (never a candidate)
     uint32_t* d_parent = nullptr;  // optional: unit -> index of its parent unit in another corpus (block -> file)
     uint64_t n_parents = 0;        // number of units in the parent corpus
     uint32_t stage_cap_bytes = 0;  // largest staged unit (all kinds), 16-byte multiple
@@ -949,6 +950,7 @@ extern "C" void bsg_corpus_free(bsg_corpus* c) {
     cudaFree(c->d_staged_list);
     cudaFree(c->d_gather_list);
     cudaFree(c->d_parent);
+    cudaFree(c->d_bad32);
     cudaFree(c->d_tiles);
     cudaFree(c->d_t_staged_list);
     cudaFree(c->d_t_gather_list);
@@ -1311,10 +1313,15 @@ extern "C" int bsg_corpus_load_sections(bsg_ctx* ctx, const uint8_t* sections, c
         CUDA_TRY(launch_parse_sections(d_sec.p, d_off.p, n_units, verify_crc, d_info.p, s));
         if (n_units) CUDA_TRY(cudaMemcpyAsync(info.data(), d_info.p, n_units * sizeof(SectionInfo), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        std::vector<uint32_t> bad32((n_units + 31) / 32 + 2, 0u);
         for (uint64_t u = 0; u < n_units; ++u) {
-            if (info[u].status != 0) ++bad;
+            if (info[u].status != 0) { ++bad; bad32[u >> 5] |= 1u << (u & 31); }
             if (unit_status) unit_status[u] = info[u].status;
             for (int k = 0; k < 3; ++k) desc[u * 3 + k] = bsg_filter_desc{info[u].m[k], info[u].k[k], 0};
+        }
+        if (bad) {
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_bad32), bad32.size() * 4));
+            CUDA_TRY(cudaMemcpy(c->d_bad32, bad32.data(), bad32.size() * 4, cudaMemcpyHostToDevice));
         }
         Layout L;
         int r = make_layout(desc.data(), n_units, L);
@@ -1803,6 +1810,10 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             CUDA_TRY(launch_fill_mask(q->d_mask32, c->n_units, s));
         }
         ++launches;
+        if (c->d_bad32) {  // a unit whose section failed to parse is an error, not a candidate
+            CUDA_TRY(launch_mask_andnot(q->d_mask32, c->d_bad32, c->n_units, s));
+            ++launches;
+        }
     }
     q->last_launches = launches;
     return BSG_OK;

@@ -138,8 +138,8 @@ inline uint32_t tile_header_bytes(uint32_t units_cap) { return kTileBitmapOff + 
 // fixed shared memory of probe_tiles_kernel in front of the ring
 constexpr uint32_t kTilesPrefixBytes = 512;   // full[16] + aready[16] mbarriers, done[16] counters
 constexpr uint32_t kTilesSlotInfoBytes = 2 * kProbeMaxKeysPerPass;  // u16 per sorted key slot
-// per B team: result row (128 B) + survivor counter (128-byte slot) + dense survivor list (u16 per key)
-constexpr uint32_t kTilesPerTeamBytes = 128 + 128 + 2 * kProbeMaxKeysPerPass;
+// per B team: two result rows (128 B each, alternating by unit)
+constexpr uint32_t kTilesPerTeamBytes = 256;
 inline uint32_t tiles_fixed_smem(uint32_t n_teams, uint32_t n_keys) {
     const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
     return kTilesPrefixBytes + kTilesSlotInfoBytes + n_teams * kTilesPerTeamBytes + hash_bytes;
@@ -188,6 +188,7 @@ cudaError_t launch_parent_mask(uint32_t* d_mask32, uint64_t n_units, const uint3
 cudaError_t launch_compact_rows(const StageRow* d_stab, uint32_t n_rows, const uint32_t* d_parent,
                                 const uint32_t* d_parent_mask32, StageRow* d_out, uint32_t* d_n_out, cudaStream_t s);
 cudaError_t launch_fill_mask(uint32_t* d_mask32, uint64_t n_units, cudaStream_t s);
+cudaError_t launch_mask_andnot(uint32_t* d_mask32, const uint32_t* d_bad32, uint64_t n_units, cudaStream_t s);
 
 cudaError_t build_configure(int max_smem_optin);
 cudaError_t launch_build(const uint8_t* d_keys, const uint64_t* d_key_off, const uint64_t* d_group_begin,

@@ -839,6 +839,21 @@ cudaError_t launch_compact_rows(const StageRow* d_stab, uint32_t n_rows, const u
     return cudaGetLastError();
 }
 
+// mask &= ~bad: units whose filter section failed to parse are never candidates (query_exec.go:580-590:
+// the reference records the error and `continue`s, the block is not scanned)
+__global__ void __launch_bounds__(256)
+mask_andnot_kernel(uint32_t* __restrict__ mask32, const uint32_t* __restrict__ bad32, uint64_t n_words32) {
+    const uint64_t w = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w < n_words32) mask32[w] &= ~__ldg(&bad32[w]);
+}
+
+cudaError_t launch_mask_andnot(uint32_t* d_mask32, const uint32_t* d_bad32, uint64_t n_units, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
+    const uint64_t n_words = (n_units + 31) / 32;
+    mask_andnot_kernel<<<static_cast<uint32_t>((n_words + 255) / 256), 256, 0, s>>>(d_mask32, d_bad32, n_words);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_mask(uint32_t* d_mask32, uint64_t n_units, cudaStream_t s) {
     if (n_units == 0) return cudaSuccess;
     const uint64_t n_words = (n_units + 31) / 32;

@@ -120,7 +120,7 @@ __device__ __forceinline__ void team_barrier(uint32_t id, uint32_t n_threads) {
 template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
 __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const ProbeTilesArgs a) {
     static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
-    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0 && 32 % T == 0 && NB / T <= 15, "shape");
+    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0 && 32 % T == 0 && (T == 1 || NB / T <= 15), "shape");
     constexpr uint32_t NTEAMS = NB / T;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
         }
         fence_barrier_init();
     }
-    for (uint32_t i = tid; i < NTEAMS * 64u; i += blockDim.x)  // team rows and survivor counters start at zero
+    for (uint32_t i = tid; i < NTEAMS * 64u; i += blockDim.x)  // the teams' result rows start at zero
         reinterpret_cast<uint32_t*>(bwarp_area + (i / 64u) * kTilesPerTeamBytes)[i % 64u] = 0;
     for (uint32_t i = tid; i < S * a.units_cap * 32u; i += blockDim.x) {  // survivor bitmaps start clear
         const uint32_t s = i / (a.units_cap * 32u), r = i % (a.units_cap * 32u);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
         }
         warp_kinds = __reduce_or_sync(0xffffffffu, warp_kinds);
         for (uint32_t n = 0; n < my_tiles; ++n) {
-            mbar_wait(&full[s], ph);
+            mbar_wait_relaxed(&full[s], ph, 128u, 0u);
             if (TRACE && tr && tid == 0 && 2 + 8 * n < a.trace_slots) tr[2 + 8 * n] = globaltimer_ns();
             const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
             if (warp_kinds & head.y) {
@@ -309,18 +309,20 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
         }
     } else {
         // ------------------------------------------------------------------ phase B ---
+        // Per-lane state machines over the survivor bitmap: lane l of the team's member j owns bits
+        // [j*32/T, (j+1)*32/T) of bitmap word l.  A lane pulls its next survivor as soon as its current one
+        // is decided, so the geometric tail of TestString (half of the remaining absent keys die at every
+        // location) does not idle the warp: no list, no scan, no atomics, no barrier inside a task.
         const uint32_t wb = warp - NA;
         const uint32_t team = wb / T, member = wb % T;
-        uint8_t* tarea = bwarp_area + team * kTilesPerTeamBytes;
-        uint32_t* row = reinterpret_cast<uint32_t*>(tarea);
-        uint32_t* tcnt = reinterpret_cast<uint32_t*>(tarea + 128);      // survivors appended so far (only grows)
-        uint16_t* list = reinterpret_cast<uint16_t*>(tarea + 256);
-        uint32_t cnt_base = 0;                                          // tcnt at the start of the current task
+        uint32_t* rows = reinterpret_cast<uint32_t*>(bwarp_area + team * kTilesPerTeamBytes);  // two rows, by unit parity
+        uint32_t units_done = 0;
         const uint32_t out_words = (a.n_keys + 31) >> 5;
         uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
-        constexpr uint32_t WPM = 32 / T;                                // bitmap words each member expands
+        constexpr uint32_t BPM = 32 / T;                                // bits of every bitmap word a member owns
+        const uint32_t my_bits = (T == 1 ? 0xffffffffu : ((1u << BPM) - 1u)) << (member * BPM);
         for (uint32_t n = 0; n < my_tiles; ++n) {
-            mbar_wait(&full[s], ph);  // the bulk copies' bytes (async proxy) are visible
+            mbar_wait_relaxed(&full[s], ph, 128u, 0u);  // the bulk copies' bytes (async proxy) are visible
             const uint4 head = *reinterpret_cast<const uint4*>(st);
             bool waited = false;
             for (uint32_t u = 0; u < head.x; ++u) {
@@ -328,61 +330,73 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
                 const uint32_t ord = P == 1 ? n * a.units_cap + u : (n >> 1);
                 if (ord % NTEAMS != team) continue;
                 if (!waited) {  // every A warp has published its survivor words for this tile
-                    mbar_wait_relaxed(&aready[s], ph, 1000u, 0u);
+                    mbar_wait_relaxed(&aready[s], ph, 256u, 0u);
                     waited = true;
                     if (TRACE && tr && lane == 0 && member == 0 && 4 + 8 * n < a.trace_slots) tr[4 + 8 * n] = globaltimer_ns();
                 }
-                // ---- expand this member's words of the 1024-bit survivor bitmap into the team's dense list ----
-                const uint32_t widx = member + T * lane;                // interleaved: kinds are contiguous slot ranges
-                uint32_t w = lane < WPM ? ld_volatile_shared_u32(st + kTileBitmapOff + u * 128u + widx * 4u) : 0u;
-                const uint32_t cnt = __popc(w);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int d = 1; d < static_cast<int>(WPM); d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= static_cast<uint32_t>(d)) incl += v;
-                }
-                const uint32_t mine = __shfl_sync(0xffffffffu, incl, WPM - 1);
-                uint32_t base = 0;
-                if (lane == 0 && mine) base = atomicAdd(tcnt, mine);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                uint32_t pos = base - cnt_base + incl - cnt;
-                while (w) {
-                    const uint32_t b = __ffs(w) - 1;
-                    list[pos++] = static_cast<uint16_t>(widx * 32 + b);
-                    w &= w - 1;
-                }
-                __syncwarp();
-                if (TRACE && tr && lane == 0 && member == 0 && 6 + 8 * n < a.trace_slots) tr[6 + 8 * n] = globaltimer_ns();
-                team_barrier(1 + team, T * 32);                          // the list and its length are complete
-                if (TRACE && tr && lane == 0 && member == 0 && 7 + 8 * n < a.trace_slots) tr[7 + 8 * n] = globaltimer_ns();
-                const uint32_t total = ld_volatile_shared_u32(tcnt) - cnt_base;
-                cnt_base += total;
+                uint32_t* row = rows + (units_done & 1u) * 32u;
+                uint32_t w = ld_volatile_shared_u32(st + kTileBitmapOff + u * 128u + lane * 4u) & my_bits;
                 const uint8_t* desc = st + kTileDescOff + u * 48u;
                 const uint8_t* data = st + a.hdr_bytes;
-                for (uint32_t c = member * 32; c < total; c += T * 32) {
-                    const uint32_t idx = c + lane;
-                    if (idx < total) {
-                        const uint32_t slot = list[idx];
+                bool alive = false;
+                uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0, ih2 = 0, ih3 = 0;   // ih2 = i*h2, ih3 = i*h3
+                uint32_t fm = 1, fih = 0, fil = 0, fk = 0, i = 0, pos = 0;
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data);
+                while (__any_sync(0xffffffffu, alive || w != 0u)) {
+                    if (!alive && w != 0u) {                              // next survivor of this lane
+                        const uint32_t b = __ffs(w) - 1;
+                        w &= w - 1;
+                        const uint32_t slot = lane * 32 + b;
                         const uint32_t si = s_slot[slot];
-                        const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
+                        pos = si & 0x3ffu;
                         const uint4 f = *reinterpret_cast<const uint4*>(desc + (si >> 14) * 16u);
-                        bool pass = true;
-                        if (f.x != 0)
-                            pass = test_from_s32<NT>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
-                                                     reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4)));
-                        if (pass) atomicOr(&row[(si & 0x3ffu) >> 5], 1u << (si & 31u));
+                        if (f.x == 0 || (f.w >> 16) <= static_cast<uint32_t>(NT)) {
+                            // absent filter cannot disqualify (query_exec.go:137-151); k <= NT: every location passed
+                            atomicOr(&row[pos >> 5], 1u << (pos & 31u));
+                        } else {
+                            const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
+                            h0 = x.x; h1 = x.y; h2 = y.x; h3 = y.y;
+                            ih2 = static_cast<uint64_t>(NT) * h2;
+                            ih3 = static_cast<uint64_t>(NT) * h3;
+                            fm = f.x; fih = f.y; fil = f.z; fk = f.w >> 16;
+                            w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                            i = NT;
+                            alive = true;
+                        }
+                    }
+                    if (alive) {
+                        // two locations per step (independent chains): i and i+1; location(h,i) = h[i&1] + i*h[2 + ...]
+                        // i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2
+                        const uint64_t a0 = (i & 1u) ? h1 : h0, a1 = (i & 1u) ? h0 : h1;
+                        const bool s0 = (((i + (i & 1u)) & 3u) >> 1) != 0u;              // true: h3
+                        const bool s1 = ((((i + 1u) + ((i + 1u) & 1u)) & 3u) >> 1) != 0u;
+                        const uint64_t l0 = a0 + (s0 ? ih3 : ih2);
+                        const uint64_t l1 = a1 + (s1 ? ih3 + h3 : ih2 + h2);
+                        const uint32_t b0 = mod_m32(l0, fm, fih, fil), b1 = mod_m32(l1, fm, fih, fil);
+                        const uint32_t v0 = w32[b0 >> 5], v1 = w32[b1 >> 5];
+                        const uint32_t ok0 = (v0 >> (b0 & 31u)) & 1u;
+                        const uint32_t ok1 = ((v1 >> (b1 & 31u)) & 1u) | static_cast<uint32_t>(i + 1u >= fk);
+                        i += 2u;
+                        ih2 += 2 * h2;
+                        ih3 += 2 * h3;
+                        if (!(ok0 & ok1)) {
+                            alive = false;
+                        } else if (i >= fk) {
+                            atomicOr(&row[pos >> 5], 1u << (pos & 31u));
+                            alive = false;
+                        }
                     }
                 }
-                __syncwarp();
-                if (TRACE && tr && lane == 0 && member == 0 && 8 + 8 * n < a.trace_slots) tr[8 + 8 * n] = globaltimer_ns();
-                team_barrier(1 + team, T * 32);                          // every member's tests are in the row
-                if (TRACE && tr && lane == 0 && member == 0 && 9 + 8 * n < a.trace_slots) tr[9 + 8 * n] = globaltimer_ns();
-                if (member == 0 && (head.z & kTileLastPart)) {           // the unit's row is complete: one coalesced store
-                    const uint32_t unit = *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * u);
-                    const uint32_t v = ld_volatile_shared_u32(&row[lane]);
-                    if (lane < out_words) out_base[static_cast<size_t>(unit) * a.row_words32 + lane] = v;
-                    row[lane] = 0;   // the next task's ORs come after its first barrier, which this warp joins later
+                if (head.z & kTileLastPart) {                            // the unit's row is complete: one coalesced store
+                    if (T > 1) team_barrier(1 + team, T * 32); else __syncwarp();
+                    if (member == 0) {
+                        const uint32_t unit = *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * u);
+                        const uint32_t v = ld_volatile_shared_u32(&row[lane]);
+                        if (lane < out_words) out_base[static_cast<size_t>(unit) * a.row_words32 + lane] = v;
+                        row[lane] = 0;   // reused two units later, after a team barrier this warp joins later
+                    }
+                    ++units_done;
+                    if (TRACE && tr && lane == 0 && member == 0 && 6 + 8 * n < a.trace_slots) tr[6 + 8 * n] = globaltimer_ns();
                 }
             }
             // every B warp arrives for every tile; the last one clears the bitmaps and refills the stage
@@ -424,8 +438,8 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
 
 // ---- compiled shapes: <A warps, keys per A thread, A tests, B warps, B team size> ----
 #define BSG_TILES_SHAPES(X) \
-    X(0, 16, 2, 3, 16, 4) X(1, 16, 2, 2, 16, 4) X(2, 16, 2, 3, 12, 4) X(3, 16, 2, 3, 8, 2) X(4, 8, 4, 3, 16, 4) \
-    X(5, 16, 2, 3, 16, 8) X(6, 16, 2, 3, 16, 2) X(7, 8, 4, 2, 16, 4)
+    X(0, 16, 2, 3, 16, 1) X(1, 16, 2, 2, 16, 1) X(2, 16, 2, 3, 8, 1) X(3, 16, 2, 3, 16, 2) X(4, 16, 2, 3, 16, 4) \
+    X(5, 16, 2, 3, 8, 4) X(6, 8, 4, 3, 16, 1) X(7, 16, 2, 2, 16, 4)
 
 int probe_tiles_n_shapes() {
     int n = 0;

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define BSG_ABI_VERSION 1
+#define BSG_ABI_VERSION 2
 
 typedef enum bsg_status {
     BSG_OK = 0,
@@ -54,6 +54,7 @@ typedef enum bsg_status {
 typedef struct bsg_ctx bsg_ctx;
 typedef struct bsg_corpus bsg_corpus;
 typedef struct bsg_query bsg_query;
+typedef struct bsg_keyset bsg_keyset;
 
 /* One bloom filter: m bits, k hash functions, words start at word_off (in uint64
  * units) inside the accompanying words array.  m == 0 means "filter absent"
@@ -141,6 +142,26 @@ int bsg_count_distinct(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_of
                        const uint64_t *group_begin, uint32_t n_groups, const uint32_t *group_parent,
                        uint32_t n_parents, uint64_t *out_group_counts, uint64_t *out_parent_counts);
 
+/* ---- resident key sets (build side) ----------------------------------------- *
+ * A key set is a batch of grouped keys resident in HBM, the build side's counterpart of bsg_query:
+ * the emissions of a flush cross PCIe once, then exact distinct counts (the `n` of
+ * NewWithEstimates, ingest.go:139-140), the sizing on the host and the build itself all read the
+ * resident copy.  Groups must cover [0, n_keys) (CSR group_begin).  bsg_keyset_build is
+ * asynchronous on the ctx stream; d_out_words is DEVICE memory of n_words uint64 (zeroed by the
+ * callee) or NULL for an internal buffer — e.g. symmetric memory from bsg_comm_alloc, so that
+ * partial file-level filters can be OR-combined across GPUs without leaving the device. */
+int bsg_keyset_create(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64_t n_keys,
+                      const uint64_t *group_begin, uint32_t n_groups, bsg_keyset **out);
+int bsg_keyset_count_distinct(bsg_ctx *ctx, bsg_keyset *ks, const uint32_t *group_parent, uint32_t n_parents,
+                              uint64_t *out_group_counts, uint64_t *out_parent_counts);
+int bsg_keyset_set_filters(bsg_ctx *ctx, bsg_keyset *ks, const uint32_t *group_filter,
+                           const uint32_t *group_filter2, const bsg_filter_desc *desc, uint32_t n_filters,
+                           uint64_t n_words);
+int bsg_keyset_build(bsg_ctx *ctx, bsg_keyset *ks, uint64_t *d_out_words);
+int bsg_keyset_fetch(bsg_ctx *ctx, bsg_keyset *ks, uint64_t *out_words); /* synchronises, copies the last build */
+const uint64_t *bsg_keyset_device_words(const bsg_keyset *ks);           /* where the last build wrote (device) */
+void bsg_keyset_free(bsg_keyset *ks);
+
 /* ---- corpus residency ------------------------------------------------------ *
  * A corpus is n_units "units" (data blocks, or files for the file-level stage),
  * each with up to three filters: desc[3*u + kind].  The words are copied to HBM
@@ -153,9 +174,12 @@ int bsg_corpus_load(bsg_ctx *ctx, const bsg_filter_desc *desc, uint64_t n_units,
  * unit u = sections[sec_off[u] .. sec_off[u+1]).  Framing is parsed and the
  * CRC32C verified (verify_crc != 0) — on the device; big-endian words are
  * swapped on the device.  unit_status (nullable, n_units ints) receives 0 or
- * the per-unit BSG_ERR_FORMAT detail code; a unit that fails to parse is kept
- * as "all filters absent" so it cannot be disqualified, mirroring the
- * reference's per-block error isolation (query_exec.go:580-590).  Returns
+ * the per-unit BSG_ERR_FORMAT detail code.  Per-block error isolation as in the
+ * reference (query_exec.go:580-590: the error is recorded, the loop continues
+ * and the block is NOT scanned): a unit that fails to parse never survives —
+ * its bit in every candidate mask of this corpus is 0 — and the caller reports
+ * unit_status[u] as that block's error.  (Its matrix row reads all ones: it has
+ * no filter that could disqualify a key; the mask is authoritative.)  Returns
  * BSG_OK even if some units failed; *n_bad (nullable) counts them. */
 int bsg_corpus_load_sections(bsg_ctx *ctx, const uint8_t *sections, const uint64_t *sec_off,
                              uint64_t n_units, int verify_crc, int32_t *unit_status,
@@ -212,6 +236,12 @@ int bsg_query_run(bsg_ctx *ctx, const bsg_corpus *corpus, bsg_query *q, int path
 int bsg_query_fetch(bsg_ctx *ctx, bsg_query *q, uint64_t n_units, uint64_t *out_matrix,
                     uint64_t *out_mask);
 void bsg_query_free(bsg_query *q);
+/* Second stage of a hierarchical probe with resident queries: run `q` on `blocks` only for units whose
+ * parent (bsg_corpus_set_parents) survived `parent_q`'s last run on the files corpus; the candidate
+ * mask stays on the device (bsg_query_device_mask: ceil(n_units/64) uint64 words, padded to a multiple
+ * of 2 words) so that bsg_allgather_masks_device can exchange it without a host round trip. */
+int bsg_query_run_child(bsg_ctx *ctx, const bsg_corpus *blocks, bsg_query *q, const bsg_query *parent_q, int path);
+const uint64_t *bsg_query_device_mask(const bsg_query *q);
 /* Number of kernels the last bsg_query_run launched (for launch accounting). */
 int bsg_query_last_launches(const bsg_query *q);
 
@@ -224,12 +254,37 @@ int bsg_timer_end(bsg_ctx *ctx, float *elapsed_ms); /* records, synchronises, re
  * and distributed by the host (the Go side would ship it over its own RPC). */
 int bsg_comm_unique_id(uint8_t out_id[128]);
 int bsg_comm_init(bsg_ctx *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
-/* In-place bitwise OR across ranks of equal-shape partial bitsets (file-level
- * filters built from disjoint shards of a file's entries).
- * words is HOST memory; result is identical on every rank. */
+/* rank / world of the communicator; *peer_memory = 1 when the collectives run as single kernels over
+ * peer memory (CUDA IPC mappings, NVLink loads / stores), 0 when they use NCCL send/recv;
+ * *last_nvlink_bytes = bytes this rank moved over NVLink in its last collective. */
+int bsg_comm_info(bsg_ctx *ctx, int *rank, int *world, int *peer_memory, uint64_t *last_nvlink_bytes);
+/* Symmetric device memory (collective: every rank calls with the same size, in the same order).  The
+ * returned pointer is this rank's buffer; the library maps every peer's copy so that the device
+ * collectives below can read and write peers directly.  Rounded up to 2 MiB. */
+int bsg_comm_alloc(bsg_ctx *ctx, size_t bytes, void **out_dev);
+int bsg_comm_free(bsg_ctx *ctx, void *dev);
+/* In-place bitwise OR across ranks of equal-shape partial bitsets (file-level filters built from
+ * disjoint shards of a file's entries: flush.go:221,253 builds that filter from the union of the entry
+ * sets, and OR of partials of equal (m,k) is the same bitset).  Result identical on
+ * every rank.  The _device form takes a 16-byte aligned pointer into bsg_comm_alloc memory, allocates
+ * nothing, and is asynchronous on the ctx stream: one kernel per rank (rank r ORs slice r out of every
+ * peer and stores it into every peer; 2*(W-1)/W * bytes over NVLink per rank).  The host form stages
+ * through a cached symmetric buffer and synchronises. */
+int bsg_or_reduce_device(bsg_ctx *ctx, uint64_t *d_words, uint64_t n_words);
 int bsg_or_reduce(bsg_ctx *ctx, uint64_t *words, uint64_t n_words);
-/* Gather every rank's candidate mask (n_words each, host) into all (world*n_words). */
+/* Gather every rank's candidate mask (n_words each) into all (world*n_words, rank-major).  _device:
+ * d_local is any device memory, d_all is bsg_comm_alloc memory; asynchronous on the ctx stream.  A rank
+ * must have consumed (stream-ordered) the previous result in d_all before it calls again. */
+int bsg_allgather_masks_device(bsg_ctx *ctx, const uint64_t *d_local, uint64_t n_words, uint64_t *d_all);
 int bsg_allgather_masks(bsg_ctx *ctx, const uint64_t *local, uint64_t n_words, uint64_t *all);
+/* Sharded hierarchical probe, one collective host call per query: every rank runs
+ * bsg_probe_hierarchical on its shard (files + their blocks), the per-rank block masks (padded to
+ * mask_words each) are all-gathered on the device, and out_all_block_masks receives
+ * world * mask_words words, rank-major (query_exec.go:372-433,572-615 with files dealt to GPUs). */
+int bsg_probe_hierarchical_gather(bsg_ctx *ctx, const bsg_corpus *files, const bsg_corpus *blocks,
+                                  const uint8_t *keys, const uint64_t *key_off, uint32_t n_keys,
+                                  const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
+                                  uint64_t mask_words, uint64_t *out_all_block_masks);
 
 #ifdef __cplusplus
 }

@@ -543,7 +543,9 @@ static void sections_range(void *p, uint64_t lo, uint64_t hi) {
     for (uint64_t u = lo; u < hi; u++) {
         bref_filter *f[3];
         int rc = bref_section_parse(c->sections + c->sec_off[u], (size_t)(c->sec_off[u + 1] - c->sec_off[u]), f);
-        int keep = 1;
+        /* query_exec.go:580-590: a section that fails to parse is an ERROR for that block — it is recorded
+         * and the loop `continue`s: the block is not a candidate (never scanned), not a survivor. */
+        int keep = 0;
         if (rc != 0) errs++;
         else {
             keep = bref_evaluate_bloom_filters(f[0], f[1], f[2], c->expr);

@@ -42,7 +42,7 @@ np.set_printoptions(precision=2, suppress=True, linewidth=250)
 print("workload", wl, "env", {k: v for k, v in os.environ.items() if k.startswith("BSG_")})
 print("CTA start spread us %.2f..%.2f; hashes ready mean %.2f max %.2f" %
       (np.nanmin(rel[:, 0]), np.nanmax(rel[:, 0]), np.nanmean(rel[:, 1]), np.nanmax(rel[:, 1])))
-names = ["resident", "A0 done ", "A done  ", "released", "expanded", "barrier1", "tested  ", "barrier2"]
+names = ["resident", "A0 done ", "A done  ", "released", "row out "]
 for cta in (0, 73):
     for j, nm in enumerate(names):
         print("cta", cta, nm, rel[cta, 2 + j::W])
@@ -53,6 +53,5 @@ for j, nm in enumerate(names):
 res, a0, ad, rl = rel[:, 2::W], rel[:, 3::W], rel[:, 4::W], rel[:, 5::W]
 print("mean: resident -> A warp 0 done %.2f us; resident -> all A done (B task starts) %.2f us; B (A done -> released) %.2f us; "
       "tile period %.2f us" % (np.nanmean(a0 - res), np.nanmean(ad - res), np.nanmean(rl - ad), np.nanmean(np.diff(res, axis=1))))
-ex, b1, te, b2 = rel[:, 6::W], rel[:, 7::W], rel[:, 8::W], rel[:, 9::W]
-print("B task of the last team to write (one unit): A done -> expanded %.2f, -> barrier 1 %.2f, -> tested %.2f, -> barrier 2 %.2f us"
-      % (np.nanmean(ex - ad), np.nanmean(b1 - ex), np.nanmean(te - b1), np.nanmean(b2 - te)))
+ro = rel[:, 6::W]
+print("B task (last team to write): A done -> unit row written %.2f us" % np.nanmean(ro - ad))

@@ -12,7 +12,7 @@ from bloomsearch_b200 import _native as N
 from oracle import bloomref as pyref
 from oracle import cref
 from synth.corpus import SynthCorpus
-from tests.helpers import oracle_units, rand_keys
+from tests.helpers import oracle_units, rand_keys, to_oracle_tuple
 
 pytestmark = pytest.mark.gpu
 
@@ -434,6 +434,16 @@ def test_load_sections_corruption_is_isolated_per_unit(ctx):
     wbits = bs.unpack_matrix(want, 3)
     for u in (0, 6, 7):
         assert np.array_equal(bits[u], wbits[u])
+    # candidate mask: a block whose section failed to parse is an error, never a candidate
+    # (query_exec.go:580-590 records the error and `continue`s) — with or without an expression
+    corpus, status = bs.Corpus.from_sections(ctx, blob_sec, sec_off)
+    q = bs.BloomQuery(bs.Or(bs.Token(keys[0]), bs.Token(unit_keys[3][1][5]), bs.Token(b"definitely-absent")))
+    got = corpus.evaluate_bloom_filters(q)
+    want_mask, errs = cref.probe_sections(blob_sec, sec_off, to_oracle_tuple(q.Expression))
+    assert errs == 5 and np.array_equal(got, bs.unpack_mask(want_mask, 8)) and not got[1:6].any()
+    got_all = corpus.evaluate_bloom_filters(None)
+    assert list(got_all) == [True, False, False, False, False, False, True, True]
+    corpus.close()
     # verify_crc=False accepts the payload-flipped section (like skipping the CRC would)
     corpus, status = bs.Corpus.from_sections(ctx, blob_sec, sec_off, verify_crc=False)
     assert status[1] == 0 and status[4] == -3
