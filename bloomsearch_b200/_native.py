@@ -65,6 +65,9 @@ ABI_SYMBOLS = [
     "bsg_corpus_unit_desc", "bsg_corpus_set_parents", "bsg_probe_hierarchical", "bsg_probe", "bsg_query_create", "bsg_query_run", "bsg_query_fetch", "bsg_query_free",
     "bsg_query_last_launches", "bsg_timer_begin", "bsg_timer_end", "bsg_comm_unique_id", "bsg_comm_init",
     "bsg_or_reduce", "bsg_allgather_masks",
+    "bsg_keyset_create", "bsg_keyset_count_distinct", "bsg_keyset_set_filters", "bsg_keyset_build", "bsg_keyset_fetch",
+    "bsg_keyset_device_words", "bsg_keyset_free", "bsg_query_run_child", "bsg_query_device_mask", "bsg_comm_info",
+    "bsg_comm_alloc", "bsg_comm_free", "bsg_or_reduce_device", "bsg_allgather_masks_device", "bsg_probe_hierarchical_gather",
 ]
 
 
@@ -120,6 +123,24 @@ def lib():
     L.bsg_comm_init.argtypes = [vp, i32, i32, vp]
     L.bsg_or_reduce.argtypes = [vp, vp, u64]
     L.bsg_allgather_masks.argtypes = [vp, vp, u64, vp]
+    L.bsg_keyset_create.argtypes = [vp, vp, vp, u64, vp, u32, C.POINTER(vp)]
+    L.bsg_keyset_count_distinct.argtypes = [vp, vp, vp, u32, vp, vp]
+    L.bsg_keyset_set_filters.argtypes = [vp, vp, vp, vp, vp, u32, u64]
+    L.bsg_keyset_build.argtypes = [vp, vp, vp]
+    L.bsg_keyset_fetch.argtypes = [vp, vp, vp]
+    L.bsg_keyset_device_words.argtypes = [vp]
+    L.bsg_keyset_device_words.restype = vp
+    L.bsg_keyset_free.argtypes = [vp]
+    L.bsg_keyset_free.restype = None
+    L.bsg_query_run_child.argtypes = [vp, vp, vp, vp, i32]
+    L.bsg_query_device_mask.argtypes = [vp]
+    L.bsg_query_device_mask.restype = vp
+    L.bsg_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(u64)]
+    L.bsg_comm_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.bsg_comm_free.argtypes = [vp, vp]
+    L.bsg_or_reduce_device.argtypes = [vp, vp, u64]
+    L.bsg_allgather_masks_device.argtypes = [vp, vp, u64, vp]
+    L.bsg_probe_hierarchical_gather.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, u32, u64, vp]
     _lib = L
     return L
 

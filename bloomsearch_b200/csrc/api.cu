@@ -71,6 +71,9 @@ struct bsg_ctx {
     std::vector<cudaStream_t> stream_pool;
     std::vector<bsg_query*> scratch_pool;  // reusable per-call query objects for bsg_probe
     void* comm = nullptr;  // bsg_comm.cpp
+    uint64_t* d_gather = nullptr;  // bsg_probe_hierarchical_gather: symmetric landing zone + padded local mask
+    size_t gather_cap = 0;
+    uint64_t* h_gather = nullptr;  // pinned copy-out buffer
     // large host<->device transfers of pageable caller memory (bsg_build): worker threads copy
     // slices through pinned double buffers on their own streams (see staged_copy)
     std::mutex stage_mu;
@@ -90,6 +93,7 @@ struct bsg_ctx {
     int tile_bytes = 32 * 1024;  // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
+    int tile_min_stages = 3;  // BSG_TILE_MIN_STAGES: UNIT mode keeps units small enough for a ring of this many stages
     // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
@@ -160,6 +164,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_TILE_BYTES")) ctx->tile_bytes = std::max(1024, atoi(w));
     if (const char* w = getenv("BSG_TILE_UNITS")) ctx->tile_units = std::min<int>(kTileMaxUnits, std::max(1, atoi(w)));
     if (const char* w = getenv("BSG_TILE_MODE")) ctx->tile_mode = std::min(2, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_TILE_MIN_STAGES")) ctx->tile_min_stages = std::min(8, std::max(1, atoi(w)));
     if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
     if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
@@ -179,7 +184,8 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);  // also frees the symmetric buffers (d_gather)
     for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
     for (bsg_query* q : ctx->scratch_pool) bsg_query_free(q);
     for (uint8_t* p : ctx->stage_pin) cudaFreeHost(p);
@@ -1019,12 +1025,14 @@ int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
 // small units, and lists the units no tile can hold (they take the gather kernel).
 int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
-    // conservative ring budget: the largest fixed part any compiled shape needs for a full pass of keys
-    int nb_max = 0;
-    for (int i = 0; i < probe_tiles_n_shapes(); ++i) nb_max = std::max(nb_max, probe_tiles_teams(i));
-    const uint64_t budget = static_cast<uint64_t>(ctx->max_smem_optin) - tiles_fixed_smem(nb_max, kProbeMaxKeysPerPass);
-    const uint64_t unit_limit = budget / 4 - tile_header_bytes(kTileMaxUnits);  // UNIT mode: a ring of >= 4 stages
-    const uint64_t part_limit = budget / 2 - tile_header_bytes(1);              // KIND mode: >= 2 stages
+    // ring budget for a full pass of keys: the fixed part grows with the units per tile (survivor lists, rows)
+    const uint32_t group_cap = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
+    auto ring_budget = [&](uint32_t units_cap) {
+        return static_cast<uint64_t>(ctx->max_smem_optin) - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass);
+    };
+    const uint64_t min_stages = static_cast<uint64_t>(ctx->tile_min_stages);
+    const uint64_t unit_limit = ring_budget(group_cap) / min_stages - tile_header_bytes(group_cap);  // UNIT mode
+    const uint64_t part_limit = ring_budget(1) / 2 - tile_header_bytes(1);                            // KIND mode: >= 2 stages
     auto part_bytes = [&](uint64_t u, int part) -> uint64_t {
         const UnitTab& t = L.utab[u];
         return part == 0 ? (static_cast<uint64_t>(t.nw[0]) + t.nw[1]) * 8 : static_cast<uint64_t>(t.nw[2]) * 8;
@@ -1091,7 +1099,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
             }
         }
     } else {
-        const uint32_t group_max = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
+        const uint32_t group_max = group_cap;
         const uint64_t target = static_cast<uint64_t>(ctx->tile_bytes);
         TileRec r;
         memset(&r, 0, sizeof(r));
@@ -1676,7 +1684,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             plan.stage_data_bytes = c->t_data_cap;
             plan.fuse_keys = fuse ? q->k_keys : nullptr;
             plan.fuse_key_off = fuse ? q->k_key_off : nullptr;
-            const uint32_t fixed = tiles_fixed_smem(probe_tiles_teams(plan.shape),
+            const uint32_t fixed = tiles_fixed_smem(c->t_units_cap,
                                                     std::min<uint32_t>(q->n_keys, kProbeMaxKeysPerPass));
             const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
@@ -1981,6 +1989,82 @@ extern "C" int bsg_probe_hierarchical(bsg_ctx* ctx, const bsg_corpus* files, con
     return rc;
 }
 
+extern "C" int bsg_query_run_child(bsg_ctx* ctx, const bsg_corpus* blocks, bsg_query* q, const bsg_query* parent_q, int path) {
+    if (!ctx || !blocks || !q || !parent_q) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!blocks->d_parent || blocks->n_parents != parent_q->n_units)
+        return fail(BSG_ERR_INVALID, "blocks corpus has no parents into the parent query's corpus (bsg_corpus_set_parents)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return query_run_on(ctx, blocks, q, path, 0, ctx->cur_stream, parent_q->d_mask32);
+}
+
+extern "C" const uint64_t* bsg_query_device_mask(const bsg_query* q) {
+    return q ? reinterpret_cast<const uint64_t*>(q->d_mask32) : nullptr;
+}
+
+// Sharded hierarchical probe: bsg_probe_hierarchical on this rank's shard, then the per-rank block masks are
+// all-gathered on the device (bsg_comm.cpp) and copied out once.
+extern "C" int bsg_allgather_masks_device(bsg_ctx* ctx, const uint64_t* d_local, uint64_t n_words, uint64_t* d_all);
+extern "C" int bsg_comm_info(bsg_ctx* ctx, int* rank, int* world, int* peer_memory, uint64_t* last_nvlink_bytes);
+extern "C" int bsg_comm_alloc(bsg_ctx* ctx, size_t bytes, void** out_dev);
+extern "C" int bsg_comm_free(bsg_ctx* ctx, void* dev);
+
+extern "C" int bsg_probe_hierarchical_gather(bsg_ctx* ctx, const bsg_corpus* files, const bsg_corpus* blocks,
+                                             const uint8_t* keys, const uint64_t* key_off, uint32_t n_keys,
+                                             const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
+                                             uint64_t mask_words, uint64_t* out_all_block_masks) {
+    if (!ctx || !files || !blocks || !out_all_block_masks) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!blocks->d_parent || blocks->n_parents != files->n_units)
+        return fail(BSG_ERR_INVALID, "blocks corpus has no parents into this files corpus (bsg_corpus_set_parents)");
+    if (mask_words < (blocks->n_units + 63) / 64) return fail(BSG_ERR_INVALID, "mask_words smaller than this rank's mask");
+    int world = 1;
+    int rc = bsg_comm_info(ctx, nullptr, &world, nullptr, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // gather landing zone (symmetric) + padded local mask, cached on the ctx; grows collectively
+    const size_t need = (static_cast<size_t>(world) + 1) * mask_words * 8;
+    if (need > ctx->gather_cap) {
+        if (ctx->d_gather) { rc = bsg_comm_free(ctx, ctx->d_gather); if (rc) return rc; }
+        ctx->d_gather = nullptr;
+        ctx->gather_cap = 0;
+        void* p = nullptr;
+        rc = bsg_comm_alloc(ctx, need * 2, &p);
+        if (rc) return rc;
+        ctx->d_gather = static_cast<uint64_t*>(p);
+        ctx->gather_cap = need * 2;
+        if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+        ctx->h_gather = nullptr;
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_gather), need * 2, cudaHostAllocDefault));
+    }
+    uint64_t* d_all = ctx->d_gather;
+    uint64_t* d_local = ctx->d_gather + static_cast<size_t>(world) * mask_words;
+    cudaStream_t s = ctx->cur_stream;   // collectives are ordered on the ctx stream
+    bsg_query* qf = scratch_get(ctx);
+    bsg_query* qb = scratch_get(ctx);
+    rc = (qf && qb) ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, files, keys, key_off, n_keys, key_kind, prog, prog_len, s, qf, true);
+    if (rc == BSG_OK) rc = query_run_on(ctx, files, qf, BSG_PROBE_AUTO, 0, s);
+    if (rc == BSG_OK) rc = query_prepare_on(ctx, blocks, keys, key_off, n_keys, key_kind, prog, prog_len, s, qb, true);
+    if (rc == BSG_OK) rc = query_run_on(ctx, blocks, qb, BSG_PROBE_AUTO, 0, s, qf->d_mask32);
+    if (rc == BSG_OK) {
+        const size_t mine = ((blocks->n_units + 63) / 64) * 8;
+        cudaError_t e = cudaMemsetAsync(d_local, 0, mask_words * 8, s);
+        if (e == cudaSuccess && mine) e = cudaMemcpyAsync(d_local, qb->d_mask32, mine, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "%s", cudaGetErrorString(e));
+    }
+    if (rc == BSG_OK) rc = bsg_allgather_masks_device(ctx, d_local, mask_words, d_all);
+    if (rc == BSG_OK) {
+        cudaError_t e = cudaMemcpyAsync(ctx->h_gather, d_all, static_cast<size_t>(world) * mask_words * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(BSG_ERR_CUDA, "%s", cudaGetErrorString(e));
+        else memcpy(out_all_block_masks, ctx->h_gather, static_cast<size_t>(world) * mask_words * 8);
+    } else {
+        cudaStreamSynchronize(s);
+    }
+    scratch_put(ctx, qf);
+    scratch_put(ctx, qb);
+    return rc;
+}
+
 // ---- profiling-only hooks (not part of include/bloomgpu.h): per-CTA timeline of the staged probe
 extern "C" int bsg_debug_trace_enable(bsg_ctx* ctx, uint32_t slots) {
     if (!ctx) return fail(BSG_ERR_INVALID, "ctx is NULL");
@@ -2043,6 +2127,15 @@ extern "C" int bsg_debug_run_cycle(bsg_ctx* ctx, bsg_corpus* const* corpora, bsg
         CUDA_TRY(cudaEventRecord(ctx->aux_events[k], ctx->aux_streams[k]));
         CUDA_TRY(cudaStreamWaitEvent(ctx->cur_stream, ctx->aux_events[k], 0));
     }
+    return BSG_OK;
+}
+
+// test / bench helper: synchronise the ctx stream, then copy device memory (e.g. a bsg_comm_alloc buffer) to the host
+extern "C" int bsg_debug_memcpy_d2h(bsg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx || !dst_host || !src_dev) return fail(BSG_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->cur_stream));
+    CUDA_TRY(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
     return BSG_OK;
 }
 

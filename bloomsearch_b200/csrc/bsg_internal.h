@@ -131,18 +131,17 @@ static_assert(sizeof(TileRec) == 512, "TileRec must be 512 bytes");
 constexpr uint32_t kTileRecFixedBytes = 16 + 64 + 32;   // head + fill + unit ids; the descriptors follow
 constexpr uint32_t kTileDescOff = kTileRecFixedBytes;
 constexpr uint32_t kTileFirstPart = 1u, kTileLastPart = 2u, kTileSmallK = 4u;  // SmallK: some filter has k < 4
-// stage = [TileRec 512][next tile's TileFill 64][pad 64][survivor bitmaps: units_cap x 128 B][tile data]
+// stage = [TileRec 512][next tile's TileFill 64][pad 64][tile data]
 constexpr uint32_t kTileNextFillOff = 512;
 constexpr uint32_t kTileBitmapOff = 640;
-inline uint32_t tile_header_bytes(uint32_t units_cap) { return kTileBitmapOff + 128u * units_cap; }
-// fixed shared memory of probe_tiles_kernel in front of the ring
-constexpr uint32_t kTilesPrefixBytes = 512;   // full[16] + aready[16] mbarriers, done[16] counters
+inline uint32_t tile_header_bytes(uint32_t /*units_cap*/) { return kTileBitmapOff; }
+// fixed shared memory of probe_tiles_kernel in front of the ring: mbarriers + list counters, slot table,
+// the tile's result rows, the two survivor lists (u16 per (unit, key): worst case every key survives), hashes
+constexpr uint32_t kTilesPrefixBytes = 512;
 constexpr uint32_t kTilesSlotInfoBytes = 2 * kProbeMaxKeysPerPass;  // u16 per sorted key slot
-// per B team: two result rows (128 B each, alternating by unit)
-constexpr uint32_t kTilesPerTeamBytes = 256;
-inline uint32_t tiles_fixed_smem(uint32_t n_teams, uint32_t n_keys) {
+inline uint32_t tiles_fixed_smem(uint32_t units_cap, uint32_t n_keys) {
     const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
-    return kTilesPrefixBytes + kTilesSlotInfoBytes + n_teams * kTilesPerTeamBytes + hash_bytes;
+    return kTilesPrefixBytes + kTilesSlotInfoBytes + units_cap * 128u + 2u * units_cap * 2u * kProbeMaxKeysPerPass + hash_bytes;
 }
 
 struct ProbeTilesPlan {
@@ -158,7 +157,6 @@ struct ProbeTilesPlan {
     const uint64_t* fuse_key_off;
 };
 cudaError_t probe_tiles_configure(int max_smem_optin);
-int probe_tiles_teams(int shape);         // B teams of a compiled shape (smem planning)
 int probe_tiles_n_shapes();
 const char* probe_tiles_shape_name(int shape);
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,

@@ -13,21 +13,9 @@
 //     so in KIND mode only the warps that hold keys of the tile's kinds touch it;
 //   * every CTA keeps the batch's base hashes in shared memory (hashed in place by the CTA while the
 //     first fills are in flight, or copied from the hash kernel's output): phase B never leaves the SM;
-//   * phase A publishes survivors as BALLOT words (one store per 32 keys, no atomics, no queue); the
-//     phase-B team that owns the unit expands the 1024-bit survivor bitmap into one dense list (each
-//     warp of the team expands its share of the words), tests locations NT..k-1 with dense lanes in
-//     groups of four independent tests, ORs passing keys into the team's result row (caller key
-//     order) and writes the row with one coalesced 128-byte store.
-//
-//   phase A  warps 0..NA-1, KPT keys per thread, locations 0..NT-1 of each key in registers; walks the
-//            tiles in order; per unit of the tile: NT branch-free tests per key, one ballot per 32 keys.
-//   phase B  warps NA..NA+NB-1 in NB/T teams of T warps; team g owns the units whose ordinal in this CTA's
-//            sequence is g mod NB/T (all parts of a unit go to the same team, so the row is complete when
-//            its last part is).  Two named barriers per task order list build -> tests -> row write-out; the
-//            survivor counter only grows, so nothing is reset between tasks.  Every B warp visits every
-//            tile and arrives on its done counter (so no warp can fall two mbarrier phases behind a
-//            stage); the last arriver clears the bitmaps and refills the stage.  (Measured: one warp per
-//            unit, 6-8 B warps, left phase B latency bound: 2b 25 us, 2a 68-80 us; see DESIGN.md.)
+//   * TestString is an AND over the k locations, so the order in which clear bits are found is free: the
+//     kernel runs it in three ROUNDS per tile with the survivors re-compacted in between (see the kernel),
+//     instead of one early-exit loop per lane (a third of the lanes busy) or specialised warps.
 #include <type_traits>
 
 #include "bsg_device.cuh"
@@ -113,22 +101,30 @@ __device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uin
     return pass != 0u;
 }
 
-__device__ __forceinline__ void team_barrier(uint32_t id, uint32_t n_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
-}
-
-template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
-__global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const ProbeTilesArgs a) {
-    static_assert(NA * KPT * 32 == static_cast<int>(kProbeMaxKeysPerPass), "A warps must cover one pass of keys");
-    static_assert(NA + NB <= 32 && NT >= 1 && NT <= 4 && NB % T == 0 && 32 % T == 0 && (T == 1 || NB / T <= 15), "shape");
-    constexpr uint32_t NTEAMS = NB / T;
+// One tile at a time, the whole CTA in lock step, three rounds separated by CTA barriers:
+//   round A   thread t owns sorted key slot t (locations 0..NT-1 in registers).  For every unit of the tile:
+//             NT branch-free tests; survivors (one in 2^NT of the absent keys, and every present key) are
+//             appended to list L1 as (unit, slot) with one shared-memory atomic per warp per unit.
+//   round B1  L1 is dense: entry e goes to thread e mod 1024.  Locations NT..NT+3 as four independent tests.
+//             A key that fails is final; a key whose last location was among them is final (bit set in the
+//             unit's result row); the rest (one in 16 of L1's absent keys) are appended to L2.
+//   round B2  L2, dense again: the remaining locations in groups of four with the early exit between groups.
+// Then the rows of the tile's units are written with one coalesced 128-byte store each and thread 0 refills
+// the stage.  Every round runs on all 32 warps, so no warp role can starve another (measured with
+// specialised A / B warps: the scheduler favoured the A warps and phase B ran 5-10x slower than its
+// instruction count), and the geometric tail of TestString is re-compacted twice instead of
+// idling lanes.
+template <int NT, bool TRACE>
+__global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesArgs a) {
+    static_assert(NT >= 1 && NT <= 4, "shape");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* aready = full + kProbeMaxStages;
-    uint32_t* done = reinterpret_cast<uint32_t*>(aready + kProbeMaxStages);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + 128);          // cnt[0] = |L1|, cnt[1] = |L2|
     uint16_t* s_slot = reinterpret_cast<uint16_t*>(smem + kTilesPrefixBytes);
-    uint8_t* bwarp_area = smem + kTilesPrefixBytes + kTilesSlotInfoBytes;
-    ulonglong2* htab = reinterpret_cast<ulonglong2*>(bwarp_area + NTEAMS * kTilesPerTeamBytes);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + kTilesPrefixBytes + kTilesSlotInfoBytes);
+    uint16_t* L1 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(rows) + a.units_cap * 128u);
+    uint16_t* L2 = L1 + a.units_cap * kProbeMaxKeysPerPass;
+    ulonglong2* htab = reinterpret_cast<ulonglong2*>(L2 + a.units_cap * kProbeMaxKeysPerPass);
     const uint32_t hash_bytes = ((a.n_keys + 31u) & ~31u) * 32u;
     uint8_t* stages = reinterpret_cast<uint8_t*>(htab) + hash_bytes;   // 128-byte aligned: every term is
 
@@ -139,25 +135,17 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
     const uint32_t S = a.n_stages;
     const uint32_t P = a.parts;
     // optional timeline (profiling only), per CTA: [0] start, [1] hashes ready; per tile n, base b = 2+8n:
-    // [b] resident (A warp 0), [b+1] A warp 0 done, [b+2] all A done (a B task starts), [b+3] released,
-    // [b+4] list expanded, [b+5] after team barrier 1, [b+6] tests done, [b+7] after team barrier 2 (member 0 of a team)
+    // [b] resident, [b+1] round A done, [b+2] round B1 done, [b+3] round B2 done, [b+4] |L1|, [b+5] |L2|
     uint64_t* tr = (TRACE && a.trace) ? a.trace + static_cast<size_t>(blockIdx.x) * a.trace_slots : nullptr;
     if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&aready[s], NA);
-            done[s] = 0;
-        }
+        for (uint32_t s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        cnt[0] = 0;
+        cnt[1] = 0;
         fence_barrier_init();
     }
-    for (uint32_t i = tid; i < NTEAMS * 64u; i += blockDim.x)  // the teams' result rows start at zero
-        reinterpret_cast<uint32_t*>(bwarp_area + (i / 64u) * kTilesPerTeamBytes)[i % 64u] = 0;
-    for (uint32_t i = tid; i < S * a.units_cap * 32u; i += blockDim.x) {  // survivor bitmaps start clear
-        const uint32_t s = i / (a.units_cap * 32u), r = i % (a.units_cap * 32u);
-        reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(s) * a.stage_bytes + kTileBitmapOff)[r] = 0;
-    }
+    for (uint32_t i = tid; i < a.units_cap * 32u; i += blockDim.x) rows[i] = 0;
     __syncthreads();
 
     // PDL: the first fills read only the immutable corpus, so they may overlap the tail of the previous
@@ -214,251 +202,177 @@ __global__ void __launch_bounds__((NA + NB) * 32, 1) probe_tiles_kernel(const Pr
     __syncthreads();
     if (TRACE && tr && tid == 0) tr[1] = globaltimer_ns();
 
+    // ---- this thread's key for round A ----
+    uint64_t loc[NT];        // location(h, 0..NT-1) = h0, h1+h3, h0+2*h3, h1+3*h2
+    uint32_t koff = 0, kbit = 0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) loc[t] = 0;
+    if (tid < a.n_keys) {
+        const ulonglong2 x = htab[2 * tid], y = htab[2 * tid + 1];
+        const uint64_t l4[4] = {x.x, x.y + y.y, x.x + 2 * y.y, x.y + 3 * y.x};
+#pragma unroll
+        for (int t = 0; t < NT; ++t) loc[t] = l4[t];
+        const uint32_t kind = s_slot[tid] >> 14;
+        koff = kind * 16u;
+        kbit = 1u << kind;
+    }
+    const uint32_t warp_kinds = __reduce_or_sync(0xffffffffu, kbit);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t out_words = (a.n_keys + 31) >> 5;
+    uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
+
     uint32_t s = 0, ph = 0;
     uint8_t* st = stages;
-    if (warp < NA) {
-        // ------------------------------------------------------------------ phase A ---
-        uint64_t loc[KPT][NT];   // location(h, 0..NT-1) = h0, h1+h3, h0+2*h3, h1+3*h2
-        uint32_t koff[KPT];      // byte offset of the key's kind inside a unit's descriptor triple
-        uint32_t kbit[KPT];      // 1 << kind, 0 = no key in this slot
-        uint32_t warp_kinds = 0;
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-            const uint32_t slot = (warp * KPT + j) * 32 + lane;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) loc[j][t] = 0;
-            koff[j] = 0;
-            kbit[j] = 0;
-            if (slot < a.n_keys) {
-                const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                const uint64_t l4[4] = {x.x, x.y + y.y, x.x + 2 * y.y, x.y + 3 * y.x};
-#pragma unroll
-                for (int t = 0; t < NT; ++t) loc[j][t] = l4[t];
-                const uint32_t kind = s_slot[slot] >> 14;
-                koff[j] = kind * 16u;
-                kbit[j] = 1u << kind;
-            }
-            warp_kinds |= kbit[j];
-        }
-        warp_kinds = __reduce_or_sync(0xffffffffu, warp_kinds);
-        for (uint32_t n = 0; n < my_tiles; ++n) {
-            mbar_wait_relaxed(&full[s], ph, 128u, 0u);
-            if (TRACE && tr && tid == 0 && 2 + 8 * n < a.trace_slots) tr[2 + 8 * n] = globaltimer_ns();
-            const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
-            if (warp_kinds & head.y) {
-                const uint8_t* data = st + a.hdr_bytes;
-                const uint8_t* desc = st + kTileDescOff;
-                // Ballot words stay in registers until the tile is done (lane u*KPT+j keeps the word of unit u,
-                // key slot j): no shared-memory store inside the loop, so the loads and modulo chains of
-                // consecutive keys / units can overlap (phase A is latency bound, not issue bound).
-                uint32_t mybits = 0;
-                auto unit_loop = [&](auto small_k) {
-                    constexpr bool SMALLK = decltype(small_k)::value;
+    for (uint32_t n = 0; n < my_tiles; ++n) {
+        mbar_wait(&full[s], ph);
+        if (TRACE && tr && tid == 0 && 2 + 8 * n < a.trace_slots) tr[2 + 8 * n] = globaltimer_ns();
+        const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
+        const uint32_t my_unit = warp < head.x ? *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * warp) : 0u;
+        const uint8_t* data = st + a.hdr_bytes;
+        // ---------------------------------------------------------------- round A ---
+        if (warp_kinds & head.y) {
+            const bool act = (kbit & head.y) != 0;
+            auto unit_loop = [&](auto small_k) {
+                constexpr bool SMALLK = decltype(small_k)::value;
+                const uint8_t* desc = st + kTileDescOff + koff;
 #pragma unroll 2
-                    for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
-                        uint4 f[KPT];
-                        bool act[KPT], pass[KPT];
+                for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
+                    uint4 f = make_uint4(0, 0, 0, 0);
+                    if (act) f = *reinterpret_cast<const uint4*>(desc);
+                    // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
+                    const bool test = act && f.x != 0;
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                    uint32_t bit[NT], wv[NT];
 #pragma unroll
-                        for (int j = 0; j < KPT; ++j) {
-                            act[j] = (kbit[j] & head.y) != 0;
-                            f[j] = make_uint4(0, 0, 0, 0);
-                            if (act[j]) f[j] = *reinterpret_cast<const uint4*>(desc + koff[j]);
-                        }
+                    for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
 #pragma unroll
-                        for (int j = 0; j < KPT; ++j) {
-                            // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> phase B sets the bit
-                            const bool test = act[j] && f[j].x != 0;
-                            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f[j].w & 0xffffu) << 4));
-                            uint32_t bit[NT], wv[NT];
+                    for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
+                    uint32_t p = 1u;
 #pragma unroll
-                            for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f[j].x, f[j].y, f[j].z);
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
-                            uint32_t p = 1u;
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) {
-                                uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
-                                if (SMALLK) b |= static_cast<uint32_t>((f[j].w >> 16) <= static_cast<uint32_t>(t));
-                                p &= b;
-                            }
-                            pass[j] = act[j] && (f[j].x == 0 || p != 0u);
-                        }
-#pragma unroll
-                        for (int j = 0; j < KPT; ++j) {
-                            const uint32_t bits = __ballot_sync(0xffffffffu, pass[j]);
-                            if (lane == u * KPT + j) mybits = bits;
-                        }
+                    for (int t = 0; t < NT; ++t) {
+                        uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
+                        if (SMALLK) b |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
+                        p &= b;
                     }
-                };
-                if (head.z & kTileSmallK) unit_loop(std::true_type{});
-                else unit_loop(std::false_type{});
-                // lane 0 publishes the words (it is also the lane that arrives on the barrier below)
-                uint32_t* bm = reinterpret_cast<uint32_t*>(st + kTileBitmapOff) + warp * KPT;
-                for (uint32_t i = 0; i < head.x * KPT; ++i) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, mybits, i);
-                    if (lane == 0) bm[(i / KPT) * 32 + (i % KPT)] = v;
+                    const bool pass = act && (f.x == 0 || p != 0u);
+                    const uint32_t bits = __ballot_sync(0xffffffffu, pass);
+                    if (bits) {  // warp-aggregated append
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&cnt[0], static_cast<uint32_t>(__popc(bits)));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (pass) L1[base + __popc(bits & lt_mask)] = static_cast<uint16_t>((u << 10) | tid);
+                    }
                 }
-            }
-            // lane 0 wrote this warp's bitmap words and lane 0 arrives (release): a B warp's try_wait
-            // (acquire) on aready orders its loads after them
-            if (lane == 0) mbar_arrive(&aready[s]);
-            __syncwarp();
-            if (TRACE && tr && tid == 0 && 3 + 8 * n < a.trace_slots) tr[3 + 8 * n] = globaltimer_ns();
-            st += a.stage_bytes;
-            if (++s == S) { s = 0; ph ^= 1u; st = stages; }
+            };
+            if (head.z & kTileSmallK) unit_loop(std::true_type{});
+            else unit_loop(std::false_type{});
         }
-    } else {
-        // ------------------------------------------------------------------ phase B ---
-        // Per-lane state machines over the survivor bitmap: lane l of the team's member j owns bits
-        // [j*32/T, (j+1)*32/T) of bitmap word l.  A lane pulls its next survivor as soon as its current one
-        // is decided, so the geometric tail of TestString (half of the remaining absent keys die at every
-        // location) does not idle the warp: no list, no scan, no atomics, no barrier inside a task.
-        const uint32_t wb = warp - NA;
-        const uint32_t team = wb / T, member = wb % T;
-        uint32_t* rows = reinterpret_cast<uint32_t*>(bwarp_area + team * kTilesPerTeamBytes);  // two rows, by unit parity
-        uint32_t units_done = 0;
-        const uint32_t out_words = (a.n_keys + 31) >> 5;
-        uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
-        constexpr uint32_t BPM = 32 / T;                                // bits of every bitmap word a member owns
-        const uint32_t my_bits = (T == 1 ? 0xffffffffu : ((1u << BPM) - 1u)) << (member * BPM);
-        for (uint32_t n = 0; n < my_tiles; ++n) {
-            mbar_wait_relaxed(&full[s], ph, 128u, 0u);  // the bulk copies' bytes (async proxy) are visible
-            const uint4 head = *reinterpret_cast<const uint4*>(st);
-            bool waited = false;
-            for (uint32_t u = 0; u < head.x; ++u) {
-                // ordinal of the unit in this CTA's sequence; all parts of a unit share it
-                const uint32_t ord = P == 1 ? n * a.units_cap + u : (n >> 1);
-                if (ord % NTEAMS != team) continue;
-                if (!waited) {  // every A warp has published its survivor words for this tile
-                    mbar_wait_relaxed(&aready[s], ph, 256u, 0u);
-                    waited = true;
-                    if (TRACE && tr && lane == 0 && member == 0 && 4 + 8 * n < a.trace_slots) tr[4 + 8 * n] = globaltimer_ns();
-                }
-                uint32_t* row = rows + (units_done & 1u) * 32u;
-                uint32_t w = ld_volatile_shared_u32(st + kTileBitmapOff + u * 128u + lane * 4u) & my_bits;
-                const uint8_t* desc = st + kTileDescOff + u * 48u;
-                const uint8_t* data = st + a.hdr_bytes;
-                bool alive = false;
-                uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0, ih2 = 0, ih3 = 0;   // ih2 = i*h2, ih3 = i*h3
-                uint32_t fm = 1, fih = 0, fil = 0, fk = 0, i = 0, pos = 0;
-                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data);
-                while (__any_sync(0xffffffffu, alive || w != 0u)) {
-                    if (!alive && w != 0u) {                              // next survivor of this lane
-                        const uint32_t b = __ffs(w) - 1;
-                        w &= w - 1;
-                        const uint32_t slot = lane * 32 + b;
-                        const uint32_t si = s_slot[slot];
-                        pos = si & 0x3ffu;
-                        const uint4 f = *reinterpret_cast<const uint4*>(desc + (si >> 14) * 16u);
-                        if (f.x == 0 || (f.w >> 16) <= static_cast<uint32_t>(NT)) {
-                            // absent filter cannot disqualify (query_exec.go:137-151); k <= NT: every location passed
-                            atomicOr(&row[pos >> 5], 1u << (pos & 31u));
-                        } else {
-                            const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                            h0 = x.x; h1 = x.y; h2 = y.x; h3 = y.y;
-                            ih2 = static_cast<uint64_t>(NT) * h2;
-                            ih3 = static_cast<uint64_t>(NT) * h3;
-                            fm = f.x; fih = f.y; fil = f.z; fk = f.w >> 16;
-                            w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
-                            i = NT;
-                            alive = true;
-                        }
-                    }
-                    if (alive) {
-                        // two locations per step (independent chains): i and i+1; location(h,i) = h[i&1] + i*h[2 + ...]
-                        // i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2
-                        const uint64_t a0 = (i & 1u) ? h1 : h0, a1 = (i & 1u) ? h0 : h1;
-                        const bool s0 = (((i + (i & 1u)) & 3u) >> 1) != 0u;              // true: h3
-                        const bool s1 = ((((i + 1u) + ((i + 1u) & 1u)) & 3u) >> 1) != 0u;
-                        const uint64_t l0 = a0 + (s0 ? ih3 : ih2);
-                        const uint64_t l1 = a1 + (s1 ? ih3 + h3 : ih2 + h2);
-                        const uint32_t b0 = mod_m32(l0, fm, fih, fil), b1 = mod_m32(l1, fm, fih, fil);
-                        const uint32_t v0 = w32[b0 >> 5], v1 = w32[b1 >> 5];
-                        const uint32_t ok0 = (v0 >> (b0 & 31u)) & 1u;
-                        const uint32_t ok1 = ((v1 >> (b1 & 31u)) & 1u) | static_cast<uint32_t>(i + 1u >= fk);
-                        i += 2u;
-                        ih2 += 2 * h2;
-                        ih3 += 2 * h3;
-                        if (!(ok0 & ok1)) {
-                            alive = false;
-                        } else if (i >= fk) {
-                            atomicOr(&row[pos >> 5], 1u << (pos & 31u));
-                            alive = false;
-                        }
-                    }
-                }
-                if (head.z & kTileLastPart) {                            // the unit's row is complete: one coalesced store
-                    if (T > 1) team_barrier(1 + team, T * 32); else __syncwarp();
-                    if (member == 0) {
-                        const uint32_t unit = *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * u);
-                        const uint32_t v = ld_volatile_shared_u32(&row[lane]);
-                        if (lane < out_words) out_base[static_cast<size_t>(unit) * a.row_words32 + lane] = v;
-                        row[lane] = 0;   // reused two units later, after a team barrier this warp joins later
-                    }
-                    ++units_done;
-                    if (TRACE && tr && lane == 0 && member == 0 && 6 + 8 * n < a.trace_slots) tr[6 + 8 * n] = globaltimer_ns();
-                }
-            }
-            // every B warp arrives for every tile; the last one clears the bitmaps and refills the stage
-            __syncwarp();
-            uint32_t last = 0;
-            if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == NB - 1;
-            __syncwarp();
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                for (uint32_t u = 0; u < head.x; ++u)
-                    reinterpret_cast<uint32_t*>(st + kTileBitmapOff)[u * 32 + lane] = 0;
-                __syncwarp();
-                if (lane == 0) {
-                    if (TRACE && tr && 5 + 8 * n < a.trace_slots) tr[5 + 8 * n] = globaltimer_ns();
-                    done[s] = 0;
-                    const uint32_t nxt = n + S;
-                    if (nxt < my_tiles) {
-                        const uint4* fp = reinterpret_cast<const uint4*>(st + kTileNextFillOff);
-                        const uint4 f0 = fp[0];
-                        uint16_t nb16[kTileMaxUnits * 3] = {};
-                        if (a.kind_mask != 7u) {
-                            const uint16_t* src16 = reinterpret_cast<const uint16_t*>(st + kTileNextFillOff + 16);
+        __syncthreads();
+        const uint32_t n1 = ld_volatile_shared_u32(&cnt[0]);
+        if (TRACE && tr && tid == 0 && 7 + 8 * n < a.trace_slots) { tr[3 + 8 * n] = globaltimer_ns(); tr[6 + 8 * n] = n1; }
+        // --------------------------------------------------------------- round B1 ---
+        for (uint32_t e0 = warp * 32; e0 < n1; e0 += blockDim.x) {
+            const uint32_t e = e0 + lane;
+            bool more = false;
+            uint32_t entry = 0;
+            if (e < n1) {
+                entry = L1[e];
+                const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
+                const uint32_t si = s_slot[slot];
+                const uint4 f = *reinterpret_cast<const uint4*>(st + kTileDescOff + u * 48u + (si >> 14) * 16u);
+                const uint32_t k = f.w >> 16;
+                bool fin = f.x == 0 || k <= static_cast<uint32_t>(NT);   // absent filter, or every location already passed
+                if (!fin) {
+                    const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                    uint32_t ok = 1u;
 #pragma unroll
-                            for (int i = 0; i < static_cast<int>(kTileMaxUnits) * 3; ++i) nb16[i] = src16[i];
-                        }
-                        const bool has_next = nxt + S < my_tiles;
-                        fence_proxy_async();
-                        fill_tile(st, &full[s], rec_of(nxt), has_next, has_next ? rec_of(nxt + S) : rec_of(nxt), a.words,
-                                  f0, nb16, a.kind_mask, a.hdr_bytes);
+                    for (int j = 0; j < 4; ++j) {   // locations NT..NT+3: i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int i = NT + j;
+                        const uint64_t aa = (i & 1) ? x.y : x.x;
+                        const uint64_t bb = (((i + (i & 1)) & 3) >> 1) ? y.y : y.x;
+                        const uint32_t bit = mod_m32(aa + static_cast<uint64_t>(i) * bb, f.x, f.y, f.z);
+                        ok &= ((w32[bit >> 5] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
                     }
+                    fin = ok != 0u && k <= static_cast<uint32_t>(NT + 4);
+                    more = ok != 0u && !fin;
                 }
-                __syncwarp();
+                if (fin) {
+                    const uint32_t pos = si & 0x3ffu;
+                    atomicOr(&rows[u * 32u + (pos >> 5)], 1u << (pos & 31u));
+                }
             }
-            st += a.stage_bytes;
-            if (++s == S) { s = 0; ph ^= 1u; st = stages; }
+            const uint32_t bits = __ballot_sync(0xffffffffu, more);
+            if (bits) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[1], static_cast<uint32_t>(__popc(bits)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (more) L2[base + __popc(bits & lt_mask)] = static_cast<uint16_t>(entry);
+            }
         }
+        __syncthreads();
+        if (tid == 0) cnt[0] = 0;   // L1 is consumed; the next tile's round A starts after the third barrier
+        const uint32_t n2 = ld_volatile_shared_u32(&cnt[1]);
+        if (TRACE && tr && tid == 0 && 7 + 8 * n < a.trace_slots) { tr[4 + 8 * n] = globaltimer_ns(); tr[7 + 8 * n] = n2; }
+        // --------------------------------------------------------------- round B2 ---
+        for (uint32_t e = tid; e < n2; e += blockDim.x) {
+            const uint32_t entry = L2[e];
+            const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
+            const uint32_t si = s_slot[slot];
+            const uint4 f = *reinterpret_cast<const uint4*>(st + kTileDescOff + u * 48u + (si >> 14) * 16u);
+            const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
+            if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
+                                      reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4)))) {
+                const uint32_t pos = si & 0x3ffu;
+                atomicOr(&rows[u * 32u + (pos >> 5)], 1u << (pos & 31u));
+            }
+        }
+        __syncthreads();
+        if (TRACE && tr && tid == 0 && 5 + 8 * n < a.trace_slots) tr[5 + 8 * n] = globaltimer_ns();
+        // ---- rows out (one coalesced store per unit), stage refill ----
+        if ((head.z & kTileLastPart) && warp < head.x) {
+            const uint32_t v = rows[warp * 32u + lane];
+            if (lane < out_words) out_base[static_cast<size_t>(my_unit) * a.row_words32 + lane] = v;
+            rows[warp * 32u + lane] = 0;
+        }
+        if (tid == 0) {
+            cnt[1] = 0;
+            const uint32_t nxt = n + S;
+            if (nxt < my_tiles) {
+                const uint4* fp = reinterpret_cast<const uint4*>(st + kTileNextFillOff);
+                const uint4 f0 = fp[0];
+                uint16_t nb16[kTileMaxUnits * 3] = {};
+                if (a.kind_mask != 7u) {
+                    const uint16_t* src16 = reinterpret_cast<const uint16_t*>(st + kTileNextFillOff + 16);
+#pragma unroll
+                    for (int i = 0; i < static_cast<int>(kTileMaxUnits) * 3; ++i) nb16[i] = src16[i];
+                }
+                const bool has_next = nxt + S < my_tiles;
+                fence_proxy_async();
+                fill_tile(st, &full[s], rec_of(nxt), has_next, has_next ? rec_of(nxt + S) : rec_of(nxt), a.words, f0, nb16,
+                          a.kind_mask, a.hdr_bytes);
+            }
+        }
+        st += a.stage_bytes;
+        if (++s == S) { s = 0; ph ^= 1u; st = stages; }
     }
 }
 
-// ---- compiled shapes: <A warps, keys per A thread, A tests, B warps, B team size> ----
-#define BSG_TILES_SHAPES(X) \
-    X(0, 16, 2, 3, 16, 1) X(1, 16, 2, 2, 16, 1) X(2, 16, 2, 3, 8, 1) X(3, 16, 2, 3, 16, 2) X(4, 16, 2, 3, 16, 4) \
-    X(5, 16, 2, 3, 8, 4) X(6, 8, 4, 3, 16, 1) X(7, 16, 2, 2, 16, 4)
+// ---- compiled shapes: <tests of round A> ----
+#define BSG_TILES_SHAPES(X) X(0, 3) X(1, 2) X(2, 4)
 
 int probe_tiles_n_shapes() {
     int n = 0;
-#define X(id, na, kpt, nt, nb, t) ++n;
+#define X(id, nt) ++n;
     BSG_TILES_SHAPES(X)
 #undef X
     return n;
 }
-int probe_tiles_teams(int shape) {
-    switch (shape) {
-#define X(id, na, kpt, nt, nb, t) case id: return nb / t;
-        BSG_TILES_SHAPES(X)
-#undef X
-        default: return 4;
-    }
-}
 const char* probe_tiles_shape_name(int shape) {
     switch (shape) {
-#define X(id, na, kpt, nt, nb, t) case id: return "probe_tiles_kernel<" #na "," #kpt "," #nt "," #nb "," #t ">";
+#define X(id, nt) case id: return "probe_tiles_kernel<NT=" #nt ">";
         BSG_TILES_SHAPES(X)
 #undef X
         default: return "probe_tiles_kernel<?>";
@@ -467,23 +381,21 @@ const char* probe_tiles_shape_name(int shape) {
 
 cudaError_t probe_tiles_configure(int max_smem_optin) {
     cudaError_t e = cudaSuccess;
-#define X(id, na, kpt, nt, nb, t)                                                                                  \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             max_smem_optin);                                                                      \
-    if (e != cudaSuccess) return e;                                                                                \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<na, kpt, nt, nb, t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             max_smem_optin);                                                                      \
+#define X(id, nt)                                                                                                     \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin); \
+    if (e != cudaSuccess) return e;                                                                                   \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);  \
     if (e != cudaSuccess) return e;
     BSG_TILES_SHAPES(X)
 #undef X
     return e;
 }
 
-template <int NA, int KPT, int NT, int NB, int T>
+template <int NT>
 static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs& args, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3((NA + NB) * 32);
+    cfg.blockDim = dim3(1024);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -491,8 +403,8 @@ static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.pdl ? 1 : 0;
-    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, T, true>, args);
-    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NA, KPT, NT, NB, T, false>, args);
+    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, true>, args);
+    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, false>, args);
 }
 
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
@@ -524,7 +436,7 @@ cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tile
     a.trace = d_trace;
     a.trace_slots = d_trace ? trace_slots : 0;
     switch (plan.shape) {
-#define X(id, na, kpt, nt, nb, t) case id: return tiles_launch<na, kpt, nt, nb, t>(plan, a, s);
+#define X(id, nt) case id: return tiles_launch<nt>(plan, a, s);
         BSG_TILES_SHAPES(X)
 #undef X
         default: return cudaErrorInvalidValue;

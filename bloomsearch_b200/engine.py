@@ -143,6 +143,35 @@ class Context:
         N.check(N.lib().bsg_allgather_masks(self._h, N.ptr(local), len(local), N.ptr(out)))
         return out
 
+    def read_device(self, dev_ptr: int, n_words: int) -> np.ndarray:
+        """Synchronise the ctx stream and copy n_words uint64 of device memory to the host (tests / bench)."""
+        out = np.zeros(max(int(n_words), 1), dtype=np.uint64)
+        L = N.lib()
+        L.bsg_debug_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        N.check(L.bsg_debug_memcpy_d2h(self._h, N.ptr(out), C.c_void_p(dev_ptr), int(n_words) * 8))
+        return out[:int(n_words)]
+
+    def comm_info(self) -> dict:
+        r, w, p, b = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        N.check(N.lib().bsg_comm_info(self._h, C.byref(r), C.byref(w), C.byref(p), C.byref(b)))
+        return {"rank": r.value, "world": w.value, "peer_memory": bool(p.value), "last_nvlink_bytes": b.value}
+
+    def comm_alloc(self, nbytes: int) -> int:
+        """Symmetric device memory (collective); returns this rank's device pointer."""
+        p = C.c_void_p()
+        N.check(N.lib().bsg_comm_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value
+
+    def comm_free(self, dev_ptr: int):
+        N.check(N.lib().bsg_comm_free(self._h, C.c_void_p(dev_ptr)))
+
+    def or_reduce_device(self, dev_ptr: int, n_words: int):
+        """In-place OR across ranks of a symmetric device buffer; asynchronous on the ctx stream."""
+        N.check(N.lib().bsg_or_reduce_device(self._h, C.c_void_p(dev_ptr), int(n_words)))
+
+    def allgather_masks_device(self, d_local: int, n_words: int, d_all: int):
+        N.check(N.lib().bsg_allgather_masks_device(self._h, C.c_void_p(d_local), int(n_words), C.c_void_p(d_all)))
+
 
 def estimate_parameters(n: int, fpr: float) -> tuple[int, int]:
     """bloom.EstimateParameters + New's clamp (bsg_estimate)."""
@@ -381,6 +410,72 @@ def probe_hierarchical(files: Corpus, blocks: Corpus, query: Optional[BloomQuery
     return unpack_mask(fmask, files.n_units), unpack_mask(bmask, blocks.n_units)
 
 
+class KeySet:
+    """Grouped keys resident in HBM (bsg_keyset): count distinct entries, size filters on the host, build —
+    the emissions cross PCIe once (ingest.go:24-145 on the device)."""
+
+    def __init__(self, ctx: Context, blob: np.ndarray, key_off: np.ndarray, group_begin: np.ndarray):
+        self.ctx = ctx
+        key_off = np.ascontiguousarray(key_off, dtype=np.uint64)
+        group_begin = np.ascontiguousarray(group_begin, dtype=np.uint64)
+        self.n_groups = len(group_begin) - 1
+        self.n_words = 0
+        self._h = C.c_void_p()
+        N.check(N.lib().bsg_keyset_create(ctx.handle, N.ptr(blob), N.ptr(key_off), len(key_off) - 1, N.ptr(group_begin),
+                                          self.n_groups, C.byref(self._h)))
+
+    def count_distinct(self, group_parent: Optional[np.ndarray] = None, n_parents: int = 0):
+        gp = None if group_parent is None else np.ascontiguousarray(group_parent, dtype=np.uint32)
+        gc = np.zeros(max(self.n_groups, 1), dtype=np.uint64)
+        pc = None if gp is None else np.zeros(max(int(n_parents), 1), dtype=np.uint64)
+        N.check(N.lib().bsg_keyset_count_distinct(self.ctx.handle, self._h, N.ptr(gp), int(n_parents), N.ptr(gc), N.ptr(pc)))
+        return gc[:self.n_groups], (None if pc is None else pc[:int(n_parents)])
+
+    def set_filters(self, group_filter, group_filter2, desc, n_words: int):
+        desc = np.ascontiguousarray(desc, dtype=N.DESC_DTYPE)
+        gf = np.ascontiguousarray(group_filter, dtype=np.uint32)
+        gf2 = None if group_filter2 is None else np.ascontiguousarray(group_filter2, dtype=np.uint32)
+        N.check(N.lib().bsg_keyset_set_filters(self.ctx.handle, self._h, N.ptr(gf), N.ptr(gf2), N.ptr(desc), len(desc),
+                                               int(n_words)))
+        self.n_words = int(n_words)
+
+    def build(self, d_out: Optional[int] = None):
+        """Asynchronous on the ctx stream; d_out = device pointer (e.g. Context.comm_alloc) or None."""
+        N.check(N.lib().bsg_keyset_build(self.ctx.handle, self._h, C.c_void_p(d_out) if d_out else None))
+
+    def fetch(self) -> np.ndarray:
+        out = np.zeros(max(self.n_words, 1), dtype=np.uint64)
+        N.check(N.lib().bsg_keyset_fetch(self.ctx.handle, self._h, N.ptr(out)))
+        return out[:self.n_words]
+
+    def device_words(self) -> int:
+        return N.lib().bsg_keyset_device_words(self._h)
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_keyset_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def probe_hierarchical_gather(files: "Corpus", blocks: "Corpus", query: Optional[BloomQuery], mask_words: int, world: int):
+    """Collective: every rank probes its shard hierarchically, the per-rank block masks are all-gathered on
+    the device; returns uint64[world, mask_words]."""
+    cq = compile_bloom_query(query)
+    blob, off = N.pack_keys(cq.keys)
+    kinds = np.ascontiguousarray(cq.kinds, dtype=np.uint8)
+    out = np.zeros((world, mask_words), dtype=np.uint64)
+    pp, pl = (None, 0) if cq.prog is None else (N.ptr(cq.prog), len(cq.prog))
+    N.check(N.lib().bsg_probe_hierarchical_gather(files.ctx.handle, files.handle, blocks.handle, N.ptr(blob), N.ptr(off),
+                                                  len(cq.keys), N.ptr(kinds), pp, pl, int(mask_words), N.ptr(out)))
+    return out
+
+
 class Query:
     """Device-resident query (keys hashed once) for repeated / timed probes."""
 
@@ -397,6 +492,13 @@ class Query:
     def run(self, path: int = N.PROBE_AUTO, corpus: Optional[Corpus] = None):
         c = corpus or self.corpus
         N.check(N.lib().bsg_query_run(c.ctx.handle, c.handle, self._h, path, 1))
+
+    def run_child(self, blocks: Corpus, parent: "Query", path: int = N.PROBE_AUTO):
+        """Second stage of a hierarchical probe: only units of `blocks` whose parent survived `parent`'s run."""
+        N.check(N.lib().bsg_query_run_child(blocks.ctx.handle, blocks.handle, self._h, parent._h, path))
+
+    def device_mask(self) -> int:
+        return N.lib().bsg_query_device_mask(self._h)
 
     def launches(self) -> int:
         return N.lib().bsg_query_last_launches(self._h)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Profiling helper: per-CTA timeline of probe_tiles_kernel (TRACE instantiation): CTA start, hashes
-ready, and per tile: resident (A warp 0) / A warp 0 done / all A done (first B task) / released; us."""
+ready, and per tile: resident / round A done / round B1 done / round B2 done (us), |L1|, |L2|."""
 import ctypes as C
 import os
 import sys
@@ -42,16 +42,18 @@ np.set_printoptions(precision=2, suppress=True, linewidth=250)
 print("workload", wl, "env", {k: v for k, v in os.environ.items() if k.startswith("BSG_")})
 print("CTA start spread us %.2f..%.2f; hashes ready mean %.2f max %.2f" %
       (np.nanmin(rel[:, 0]), np.nanmax(rel[:, 0]), np.nanmean(rel[:, 1]), np.nanmax(rel[:, 1])))
-names = ["resident", "A0 done ", "A done  ", "released", "row out "]
+names = ["resident", "A done  ", "B1 done ", "B2 done "]
 for cta in (0, 73):
     for j, nm in enumerate(names):
         print("cta", cta, nm, rel[cta, 2 + j::W])
-ends = np.nanmax(rel, axis=1)
+ends = np.nanmax(rel[:, 2:][:, [i for i in range(slots - 2) if i % W < 4]], axis=1)
 print("end per CTA: min %.1f median %.1f max %.1f us" % (np.nanmin(ends), np.nanmedian(ends), np.nanmax(ends)))
 for j, nm in enumerate(names):
     print("mean", nm, np.nanmean(rel[:, 2 + j::W], axis=0))
-res, a0, ad, rl = rel[:, 2::W], rel[:, 3::W], rel[:, 4::W], rel[:, 5::W]
-print("mean: resident -> A warp 0 done %.2f us; resident -> all A done (B task starts) %.2f us; B (A done -> released) %.2f us; "
-      "tile period %.2f us" % (np.nanmean(a0 - res), np.nanmean(ad - res), np.nanmean(rl - ad), np.nanmean(np.diff(res, axis=1))))
-ro = rel[:, 6::W]
-print("B task (last team to write): A done -> unit row written %.2f us" % np.nanmean(ro - ad))
+res, ad, b1, b2 = rel[:, 2::W], rel[:, 3::W], rel[:, 4::W], rel[:, 5::W]
+n1 = out[:, 6::W].astype(float); n2 = out[:, 7::W].astype(float)
+n1[np.isnan(res)] = np.nan; n2[np.isnan(res)] = np.nan
+wait = res[:, 1:] - b2[:, :-1]
+print("mean per tile: round A %.2f us, round B1 %.2f us, round B2 + barrier %.2f us, wait for the next tile %.2f us, period %.2f us; "
+      "|L1| %.0f, |L2| %.0f" % (np.nanmean(ad - res), np.nanmean(b1 - ad), np.nanmean(b2 - b1), np.nanmean(wait),
+                               np.nanmean(np.diff(res, axis=1)), np.nanmean(n1), np.nanmean(n2)))

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     lib = N.lib()
-    assert lib.bsg_abi_version() == 1
+    assert lib.bsg_abi_version() == 2
     assert lib.bsg_strerror(0) == b"ok"
     assert b"invalid" in lib.bsg_strerror(-1)
     assert b"CUDA" in lib.bsg_strerror(-2)

@@ -921,7 +921,7 @@ def _tiles_case(monkeypatch, env, n_units, key_kinds=(0, 1, 2), big=False, n_key
         c2.close()
 
 
-@pytest.mark.parametrize("shape", range(8))
+@pytest.mark.parametrize("shape", range(3))
 def test_probe_tiles_every_shape(shape, monkeypatch):
     _tiles_case(monkeypatch, {"BSG_TILES_SHAPE": shape}, 700)
 
@@ -932,7 +932,8 @@ def test_probe_tiles_every_shape(shape, monkeypatch):
     ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 8, "BSG_TILE_BYTES": 200000}, 1300),
     ({"BSG_TILE_MODE": 1, "BSG_PROBE_STAGES": 1}, 700),                        # ring of one stage
     ({"BSG_TILE_MODE": 2}, 700),                                               # KIND mode forced on small units
-    ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 3, "BSG_TILES_SHAPE": 3}, 700),
+    ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 3, "BSG_TILES_SHAPE": 1}, 700),
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1, "BSG_TILE_MIN_STAGES": 2, "BSG_TILES_SHAPE": 2}, 300),
     ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 1}, 450),
     ({"BSG_PROBE_PDL": 0}, 300),
 ])

@@ -67,9 +67,67 @@ def _worker(rank, world, uid_q, res_q):
         wmask = cref.probe_mask(d2, words, c2.n_blocks, b2, o2, cq.kinds, cq.prog)
         want_bits = bs.unpack_mask(wmask, c2.n_blocks)
         ok_probe = bool(np.array_equal(got, want_bits)) and bool(want_bits.any()) and not bool(want_bits.all())
+        info = ctx.comm_info()
+        assert info["world"] == world and info["rank"] == rank
+
+        # ---- (3) the same two exchanges on DEVICE buffers: partial built straight into symmetric memory, one
+        #      OR kernel over peer memory, twice (buffer reuse), plus an odd word count ----
+        ks = bs.KeySet(ctx, blob, off, np.array([0, len(mine)], np.uint64))
+        ks.set_filters(np.zeros(1, np.uint32), None, desc, nw)
+        d_part = ctx.comm_alloc(nw * 8)
+        ok_dev = True
+        for _ in range(2):
+            ks.build(d_part)
+            ctx.or_reduce_device(d_part, nw)
+            ok_dev &= bool(np.array_equal(ctx.read_device(d_part, nw), want.words()))
+        assert info["peer_memory"] == ctx.comm_info()["peer_memory"]
+        nvl = ctx.comm_info()["last_nvlink_bytes"]
+        ok_dev &= nvl == 2 * (world - 1) * ((nw + world - 1) // world) * 8
+        ks.close()
+        # resident query -> device mask -> device all-gather
+        dq = bs.Query(local, cq.keys, cq.kinds, cq.prog)
+        dq.run(N.PROBE_AUTO)
+        mw = sh.local_mask_words()
+        d_all = ctx.comm_alloc(world * mw * 8)
+        for _ in range(2):
+            ctx.allgather_masks_device(dq.device_mask(), mw, d_all)
+            gathered = ctx.read_device(d_all, world * mw).reshape(world, mw)
+            ok_dev &= bool(np.array_equal(sh.assemble(gathered), want_bits))
+        dq.close()
+
+        # ---- (4) sharded hierarchical probe in one collective call (files dealt to ranks) ----
+        fd = np.zeros(c2.n_files * 3, dtype=N.DESC_DTYPE)
+        fsets = []
+        for f in range(c2.n_files):
+            for kind in range(3):
+                ks_ = sorted({c2.key(i) for b in range(f * c2.blocks_per_file, (f + 1) * c2.blocks_per_file)
+                              for i in range(int(c2.group_begin[3 * b + kind]), int(c2.group_begin[3 * b + kind + 1]))})
+                fsets.append(cref.Filter.build_sized(ks_, 0.001))
+        fwo = 0
+        fchunks = []
+        for i, flt in enumerate(fsets):
+            fd[i] = (flt.m, flt.k, fwo)
+            fchunks.append(flt.words())
+            fwo += len(fchunks[-1])
+        fwords = np.concatenate(fchunks)
+        my_files = sh.files_of(rank)
+        files_local = bs.Corpus(ctx, fd.reshape(-1, 3)[my_files].reshape(-1), fwords)
+        parent = np.repeat(np.arange(len(my_files), dtype=np.uint32), c2.blocks_per_file)
+        local.set_parents(parent, len(my_files))
+        q2 = bs.BloomQuery(bs.And(bs.Or(bs.Token(c2.key(int(c2.group_begin[3 * 5 + 1]) + 3)), bs.FieldToken(b"level", b"nope")),
+                                  bs.Field(b"nested.az")))
+        allm = bs.probe_hierarchical_gather(files_local, local, q2, mw, world)
+        got_h = sh.assemble(allm)
+        cq2 = bs.compile_bloom_query(q2)
+        b3, o3 = N.pack_keys(cq2.keys)
+        fm = bs.unpack_mask(cref.probe_mask(fd, fwords, c2.n_files, b3, o3, cq2.kinds, cq2.prog), c2.n_files)
+        bm = bs.unpack_mask(cref.probe_mask(d2, words, c2.n_blocks, b3, o3, cq2.kinds, cq2.prog), c2.n_blocks)
+        want_h = bm & np.repeat(fm, c2.blocks_per_file)
+        ok_dev &= bool(np.array_equal(got_h, want_h)) and bool(want_h.any())
+        files_local.close()
         local.close()
         ctx.close()
-        res_q.put((rank, ok_or, ok_probe, ""))
+        res_q.put((rank, ok_or, ok_probe and ok_dev, "" if ok_dev else "device collectives / hierarchical gather mismatch; peer_memory=%s" % info["peer_memory"]))
     except Exception as e:  # noqa: BLE001
         import traceback
         res_q.put((rank, False, False, traceback.format_exc()))
