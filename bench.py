@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — block-level bloom probes/s on B200 (BASELINE.json metric), with roofline
-and CPU baseline.
+"""bench.py — block-level bloom probes/s on B200 (BASELINE.json metric) with roofline, CPU baseline,
+end-to-end numbers, and the other BASELINE configs as extra legs of the same JSON line.
 
-A "step" is one pass of the hot path over one batch: a 1 000-key batch (500 keys sampled
-from the corpus, 500 absent, kinds as sampled / 1:1:1) probed against every block of a
-10 M-row synthetic log corpus resident in HBM (BASELINE config 2).  Two layouts of the same
-rows exist: 2b = 1 000 blocks x 10 000 rows (merged files, ~70 KB of bitsets
-per block, HBM-bound) and 2a = 10 000 blocks x 1 000 rows (flush-shaped, ~7 KB per block,
-on the ALU/latency ridge).  `--workload` picks the headline one; the other is reported under
-"also".  Per-GPU work is fixed as N grows (every rank owns its own 10 M-row shard): weak scaling.
+Headline (configs[1]): a 1 000-key batch (500 keys sampled from the corpus, 500 absent, kinds as sampled /
+1:1:1) probed against every block of a 10 M-row synthetic log corpus resident in HBM.  Two layouts of the
+same rows exist: 2b = 1 000 blocks x 10 000 rows (merged files, ~70 KB of bitsets per block,
+HBM-bound) and 2a = 10 000 blocks x 1 000 rows (flush-shaped, ~7 KB per block, on the instruction ridge).
+`--workload` picks the headline one; the other is reported under "also".  A STEP is BATCHES_PER_STEP = 64
+such batches (one kernel launch each), so that a step is about a millisecond of device time.  Per-GPU work
+is fixed as N grows (every rank owns its own 10 M-row shard, sharded by file, no data-path exchange): weak.
+
+Extra legs (every N, own keys of the line):
+  "build"    config 3: 100 M token keys -> 10 000 block filters + 100 file-level filters (blocks dealt to ranks)
+  "config4"  10 k files / 1 M blocks dealt to the ranks by FileSharding, 8-key AND/OR query, hierarchical
+             probe + device-resident candidate-mask all-gather inside the timed region (strong scaling)
+  "config5"  100 file-level filters, each rank builds the partial bitset of its shard of every file's entries,
+             partials OR-combined across ranks on the device (bsg_or_reduce_device), bit-identical to
+             buildFilters(union)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 2b|2a] [--impl reference]
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -34,14 +43,14 @@ WORKLOADS = {
 }
 FPR = 0.001
 N_KEYS = 1000
-# dram__bytes_read.sum + dram__bytes_write.sum per probe_staged launch from the committed
-# `ncu --set full` captures (profiles/r01_ncu_full_*_staged2_raw.csv): 2b 70.52 MB + 0.86 MB, 2a 74.93 MB + 1.55 MB
-TRAFFIC_NCU = {"2b": 71.38e6, "2a": 76.48e6}
+BATCHES_PER_STEP = 64
 L2_BYTES = 126 * 1024 * 1024
-# the staged probe kernel the library launches (BSG_PROBE_VARIANT: 0 = one phase, 1/2 = two phases)
-_SHAPES = {"1": "16,2,2,16,16", "2": "16,2,3,16,16", "3": "16,2,3,16,4", "4": "16,2,3,16,2", "5": "16,2,4,16,4"}
-_V = os.environ.get("BSG_PROBE_VARIANT", "3")
-PROBE_KERNEL = "probe_staged_kernel" if _V == "0" else f"probe_staged2_kernel<{_SHAPES[_V]}>"
+
+
+def workload_string(wl: str) -> str:
+    n_blocks, rows, _ = WORKLOADS[wl]
+    return (f"config2-{wl}: 10M-row synthetic log corpus as {n_blocks} blocks x {rows} rows, fpr {FPR}, batched 1k-key "
+            f"block probe (500 present / 500 absent); step = {BATCHES_PER_STEP} batches")
 
 
 def log(*a):
@@ -61,18 +70,18 @@ def gen_corpus(workload: str, rank: int, scale: float = 1.0):
     return c
 
 
-def size_filters(c, bs):
-    """(m,k) per (block,kind) from exact distinct counts (ingest.go:139-140)."""
-    from bloomsearch_b200 import _native as N
+def size_filters(c, est):
+    """(m,k) per (block,kind) from exact distinct counts (ingest.go:139-140).  `est` is the module that
+    provides estimate_parameters (the product for our arm, the oracle for the reference arm)."""
     counts = np.diff(c.group_begin).astype(np.int64)
     cache = {}
-    desc = np.zeros(len(counts), dtype=N.DESC_DTYPE)
+    desc = np.zeros(len(counts), dtype=np.dtype([("m", "<u8"), ("k", "<u8"), ("word_off", "<u8")]))
     wo = 0
     for g, n in enumerate(counts):
         n = int(max(n, 1))
         mk = cache.get(n)
         if mk is None:
-            mk = cache[n] = bs.estimate_parameters(n, FPR)
+            mk = cache[n] = est.estimate_parameters(n, FPR)
         desc[g] = (mk[0], mk[1], wo)
         wo += (mk[0] + 63) // 64
     return desc, wo
@@ -90,6 +99,24 @@ def make_batch(c, seed: int):
         kinds.append(i % 3)
     perm = rng.permutation(len(keys))
     return [keys[i] for i in perm], np.array([kinds[i] for i in perm], dtype=np.uint8)
+
+
+def gen_token_blocks(blocks, seed=43, keys_per_block=10000):
+    """Config 3 / 5 input: per block `keys_per_block` random lower-case tokens of 8-24 bytes (Zipf-free),
+    deterministic per block id.  Returns (blob, key_off, group_begin) with one group per block."""
+    lens, chunks = [], []
+    for b in blocks:
+        rng = np.random.default_rng([seed, int(b)])
+        ln = rng.integers(8, 25, size=keys_per_block, dtype=np.int64)
+        lens.append(ln)
+        chunks.append(rng.integers(97, 123, size=int(ln.sum()), dtype=np.uint8))
+    if not lens:
+        return np.zeros(1, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint64)
+    ln = np.concatenate(lens)
+    key_off = np.zeros(len(ln) + 1, dtype=np.uint64)
+    key_off[1:] = np.cumsum(ln, dtype=np.uint64)
+    group_begin = (np.arange(len(blocks) + 1, dtype=np.uint64) * keys_per_block)
+    return np.concatenate(chunks), key_off, group_begin
 
 
 # ------------------------------------------------------------ clock sampler ---
@@ -136,13 +163,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def load_ncu_summary():
+    """Per-launch counters of the committed `ncu --set full` captures of THIS kernel build
+    (profiles/r02_ncu_summary.json, written by scripts/ncu_summary.py from the .ncu-rep files)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+    except Exception:
+        return {}
+
+
 # -------------------------------------------------------------- CPU baseline ---
-def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=12.0, c=None, gpu_matrix=None):
-    """cpu_baseline leg — the only place the GPU arm touches the oracle.  (1) As the CHECKER: the
-    GPU-built bitsets of the first blocks and the GPU probe matrix must equal the oracle's.
-    (2) As the BASELINE: the oracle port of the Go path on the host cores, per block
-    parseFilterSection (CRC32C + BE decode) then TestString for every key; bounded sample = the
-    whole corpus' sections probed repeatedly for about target_s seconds on all host threads."""
+def cpu_probe_rates(desc, words, n_units_total, keys, kinds, c=None, gpu_matrix=None, t_decode=8.0, t_probe=4.0):
+    """cpu_baseline leg — the only place the GPU arm touches the oracle.  (1) As the CHECKER: the GPU-built
+    bitsets of the first blocks and the GPU probe matrix must equal the oracle's.  (2) As the BASELINE: the
+    oracle port of the Go path on all host threads, two variants: decode+probe = per block
+    parseFilterSection (CRC32C + BE decode) then TestString per key, as the reference does per query; and
+    probe-only = TestString on pre-decoded filters.  Bounded samples of the same workload."""
     from oracle import cref
     threads = os.cpu_count() or 1
     blob, off = cref.pack_keys(keys)
@@ -157,56 +200,71 @@ def cpu_probe_rate(desc, words, n_units_total, keys, kinds, target_s=12.0, c=Non
         want = cref.build_filters(c.blob, c.key_off, c.group_begin[:chk * 3 + 1], np.arange(chk * 3, dtype=np.uint32),
                                   None, desc[:chk * 3], end)
         assert np.array_equal(words[:end], want), "GPU-built filters differ from the oracle"
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
-        reps += 1
-        dt = time.perf_counter() - t0
-        if dt >= target_s or reps >= 2000:
-            break
-    probes = reps * n_units_total * len(keys)
-    return {"value": probes / dt, "unit": "probes/s", "cores": threads, "kind": "port",
+
+    def loop(fn, target_s):
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            fn()
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt >= target_s or reps >= 5000:
+                return reps, dt
+    reps, dt = loop(lambda: cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads), t_decode)
+    r2, d2 = loop(lambda: cref.probe_matrix(desc, words, n_units_total, blob, off, kinds, threads), t_probe)
+    per_pass = n_units_total * len(keys)
+    return {"value": reps * per_pass / dt, "unit": "probes/s", "cores": threads, "kind": "port",
+            "probe_only": {"value": r2 * per_pass / d2, "unit": "probes/s",
+                           "sample": f"{r2} passes in {d2:.1f}s, filters pre-decoded (TestString only)"},
             "gpu_output_verified_against_oracle": gpu_matrix is not None,
             "sample": f"{reps} passes over all {n_units_total} blocks x {len(keys)} keys in {dt:.1f}s; per block: "
                       f"section CRC32C + big-endian decode (parseFilterSection) then TestString per key; "
-                      f"{threads} threads (C restatement of the Go path, -O2)"}, sec.nbytes
+                      f"{threads} threads (C restatement of the Go path, -O2)"}, sec, sec_off
 
 
 # --------------------------------------------------------------------- main ---
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port of the Go
-    engine's per-block loop: parseFilterSection + TestString) on the host cores.  The GPU is used
-    only to BUILD the corpus' filters (input preparation, untimed)."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port of the Go engine's
+    per-block loop: parseFilterSection + TestString) on all host cores.  Imports nothing of the product:
+    the corpus' filters are built by the oracle too (input preparation, untimed)."""
     if rank != 0:
         return
-    import bloomsearch_b200 as bs
     from oracle import cref
     wl = args.workload
     c = gen_corpus(wl, 0)
-    desc, n_words = size_filters(c, bs)
+    desc, n_words = size_filters(c, cref)
+    threads = os.cpu_count() or 1
     words = cref.build_filters(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc,
-                               n_words, n_threads=os.cpu_count() or 1)
+                               n_words, n_threads=threads)
     keys, kinds = make_batch(c, 7)
     blob, off = cref.pack_keys(keys)
-    threads = os.cpu_count() or 1
     n_units = c.n_blocks
     sec, sec_off = cref.encode_sections(desc, words, n_units)
+
+    def step():
+        for _ in range(BATCHES_PER_STEP):
+            cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
     for _ in range(args.warmup):
-        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cref.probe_sections_matrix(sec, sec_off, blob, off, kinds, threads)
+        step()
     dt = time.perf_counter() - t0
-    value = args.steps * n_units * len(keys) / dt
-    sample = (f"{n_units} blocks ({wl} layout, the whole 10M-row corpus) x {len(keys)} keys per step; per block: "
-              f"section CRC32C + BE decode (parseFilterSection), then TestString per key; {threads} threads; "
-              f"C restatement of the Go path (no Go toolchain in the image)")
+    value = args.steps * BATCHES_PER_STEP * n_units * len(keys) / dt
+    t1 = time.perf_counter()
+    for _ in range(BATCHES_PER_STEP):
+        cref.probe_matrix(desc, words, n_units, blob, off, kinds, threads)
+    probe_only = BATCHES_PER_STEP * n_units * len(keys) / (time.perf_counter() - t1)
+    sample = (f"{args.steps} steps x {BATCHES_PER_STEP} batches x {n_units} blocks x {len(keys)} keys in {dt:.1f}s; per block "
+              f"per batch: section CRC32C + BE decode (parseFilterSection), then TestString per key; {threads} threads; "
+              f"C restatement of the Go path (no Go toolchain in the image or on the GPU box)")
     emit({
         "impl": "reference", "metric": "bloom probes/sec (block-level)", "value": value, "unit": "probes/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"config2-{wl}: 10M-row synthetic log corpus, fpr 0.001, batched 1k-key block probe"},
-        "cpu_baseline": {"value": value, "unit": "probes/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(wl)},
+        "cpu_baseline": {"value": value, "unit": "probes/s", "cores": threads, "kind": "port", "sample": sample,
+                         "probe_only": {"value": probe_only, "unit": "probes/s",
+                                        "sample": "one step with pre-decoded filters (TestString only)"}},
         "e2e": {"value": value, "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -216,9 +274,8 @@ _JSON_FD = None
 
 
 def _capture_stdout():
-    """Libraries (NCCL prints its version banner to stdout) must not pollute the one-JSON-line
-    contract: fd 1 is pointed at stderr for the whole run and the result is written to the
-    original stdout."""
+    """Libraries (NCCL prints its version banner to stdout) must not pollute the one-JSON-line contract: fd 1
+    is pointed at stderr for the whole run and the result is written to the original stdout."""
     global _JSON_FD
     if _JSON_FD is None:
         sys.stdout.flush()
@@ -235,225 +292,565 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+class Env:
+    """Per-process plumbing: torch.distributed for barriers / max-over-ranks, the bsg context, the bsg communicator."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import bloomsearch_b200 as bs
+        self.torch, self.dist, self.bs = torch, dist, bs
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.ctx = bs.Context(self.local_rank)
+        self.comm = None
+        if self.world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(bs.Context.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            self.ctx.comm_init(self.rank, self.world, bytes(uid.cpu().numpy().tobytes()))
+            self.comm = self.ctx.comm_info()
+
+    def barrier(self):
+        self.ctx.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def _reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.world > 1 else x
+
+    def sum(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.world > 1 else x
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+        self.barrier()
+        self.ctx.timer_begin()
+        for _ in range(steps):
+            fn()
+        ms = self.ctx.timer_end()
+        self.barrier()
+        return self.max(ms), ms
+
+
+def probe_leg(env, args, wl, headline, peaks, ncu):
+    """Config 2 on this rank's shard: device-timed steps + roofline + end-to-end legs."""
+    bs, ctx = env.bs, env.ctx
+    from bloomsearch_b200 import _native as N
+    c = gen_corpus(wl, env.rank)
+    desc, n_words = size_filters(c, bs)
+    t = time.time()
+    words = ctx.build(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc, n_words)
+    log(f"GPU-built {len(desc)} filters, {n_words * 8 / 1e6:.1f} MB of bitsets ({time.time() - t:.1f}s incl. PCIe)")
+    keys, kinds = make_batch(c, 7 + env.rank)
+    n_units = c.n_blocks
+    blob, off = N.pack_keys(keys)
+
+    n_rep = max(1, args.replicas)
+    corpora = [bs.Corpus(ctx, desc, words) for _ in range(n_rep)]
+    bitset_bytes = corpora[0].bitset_bytes(7)
+    queries = [bs.Query(cp, keys, kinds, None) for cp in corpora]
+    # self-consistency before timing (no oracle in the GPU arm): the two data paths agree, and every sampled
+    # key is found in some block.  The oracle check lives in the cpu_baseline leg.
+    queries[0].run(N.PROBE_STAGED)
+    got_m, got_mask = queries[0].fetch()
+    queries[0].run(N.PROBE_GATHER)
+    got_g, _ = queries[0].fetch()
+    assert np.array_equal(got_m, got_g), "staged and gather probe paths disagree"
+    assert bs.unpack_mask(got_mask, n_units).all()
+
+    # ---- device-timed steps, inputs resident in HBM; replicas cycled so no launch hits L2.  A launch = the
+    #      batch's (block x key) membership matrix: one probe kernel (no expression tree -> no mask kernel). ----
+    RUN = N.PROBE_AUTO | N.RUN_MATRIX_ONLY
+    L = N.lib()
+    L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+    L.bsg_debug_probe_kernel_name.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
+    cp_arr = (C.c_void_p * n_rep)(*[cp.handle for cp in corpora])
+    q_arr = (C.c_void_p * n_rep)(*[q._h for q in queries])
+    name_buf = C.create_string_buffer(512)
+    N.check(L.bsg_debug_probe_kernel_name(ctx.handle, corpora[0].handle, name_buf, 512))
+
+    def run_batches(k, streams):
+        # the launches are issued from C (ctypes drops the GIL): no interpreter between them.  streams > 1:
+        # consecutive batches go round-robin on that many streams (independent batches overlap tail-to-head,
+        # as concurrent bsg_probe() callers on their pool streams do).
+        N.check(L.bsg_debug_run_cycle(ctx.handle, cp_arr, q_arr, n_rep, k, RUN, streams))
+
+    for _ in range(args.warmup):
+        run_batches(BATCHES_PER_STEP, args.streams)
+    env.barrier()
+    with ClockSampler(env.local_rank) as clk:
+        # load the GPU for >= 0.5 s first so the sampler sees clocks under load, then the timed K steps inside
+        # the same sampled, loaded period, then >= 1 s more load
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            run_batches(256, args.streams)
+            ctx.synchronize()
+        ms, _ = env.timed(lambda: run_batches(BATCHES_PER_STEP, args.streams), args.steps)
+        _, ms_single = env.timed(lambda: run_batches(BATCHES_PER_STEP, 1), args.steps)   # one stream, this rank
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            run_batches(256, args.streams)
+            ctx.synchronize()
+    launches_per_batch = queries[0].launches()
+    n_launches = args.steps * BATCHES_PER_STEP
+    k_us_single = ms_single / n_launches * 1e3          # average launch duration, launches back to back on one stream
+    k_us_overlap = ms / n_launches * 1e3                # effective time per launch with args.streams streams in flight
+    probes_per_step = BATCHES_PER_STEP * n_units * len(keys)
+    value = env.sum(float(probes_per_step)) * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant (only) kernel of the step ----
+    algo_bytes = bitset_bytes + 32 * len(keys) + (len(keys) * n_units + 7) // 8
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ncu_wl = ncu.get(wl, {})
+    achieved = algo_bytes / (k_us_single * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_wl.get("dram_bytes"), "kernel": name_buf.value.decode(),
+                "kernel_us": k_us_single,
+                "what": "average launch duration with the launches back to back on ONE stream (programmatic dependent "
+                        "launch as configured), CUDA events on that stream",
+                "overlapped": {"streams": args.streams, "kernel_us": k_us_overlap,
+                               "achieved": algo_bytes / (k_us_overlap * 1e-6) / 1e9,
+                               "frac": algo_bytes / (k_us_overlap * 1e-6) / 1e9 / peak},
+                "programmatic_dependent_launch": os.environ.get("BSG_PROBE_PDL", "1") != "0",
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+    clocks = clk.summary()
+    if ncu_wl.get("inst_executed") and clocks.get("sm_mhz"):
+        # instruction-throughput view (SURVEY §8d asks for it in the ridge regime): warp instructions per launch
+        # (from the ncu capture of this build) over the issue slots of the launch (4 schedulers x SMs x cycles)
+        slots = 4 * 148 * clocks["sm_mhz"] * 1e6 * (k_us_single * 1e-6)
+        roofline["issue"] = {"warp_instructions_per_launch": ncu_wl["inst_executed"],
+                             "thread_instructions_per_probe": ncu_wl["inst_executed"] * ncu_wl.get("threads_per_inst", 32.0)
+                             / (n_units * len(keys)),
+                             "frac_of_issue_slots": ncu_wl["inst_executed"] / slots, "sm_mhz": clocks["sm_mhz"]}
+
+    # ---- end to end through the C ABI call a host makes: bsg_probe() with HOST buffers.  Every call uploads
+    #      the packed key bytes / offsets / kinds, probes (hashing fused into the probe kernel), and leaves the
+    #      (block x key) matrix in host memory.  args.e2e_callers host threads call concurrently (the reference
+    #      runs up to MaxQueryConcurrency file workers per query, query_exec.go:303-357). ----
+    e2e_calls = max(64, min(args.steps * 8, 400))
+    m_words = (len(keys) + 63) // 64
+
+    def e2e_run(n_callers, calls_each):
+        outs = [np.zeros((n_units, m_words), dtype=np.uint64) for _ in range(n_callers)]
+
+        def worker(t):
+            for i in range(calls_each):
+                corpora[(t + i) % n_rep].probe_packed(blob, off, kinds, None, outs[t], None)
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_callers)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        assert np.array_equal(outs[0], got_m), "e2e matrix differs from the resident run"
+        return dt
+
+    e2e_run(args.e2e_callers, 5)  # warm-up (scratch + pinned staging allocation)
+    env.barrier()
+    dt_multi = env.max(e2e_run(args.e2e_callers, e2e_calls))
+    env.barrier()
+    dt_single = env.max(e2e_run(1, e2e_calls))
+    per_call = env.sum(float(n_units * len(keys)))
+    e2e = {"value": per_call * e2e_calls * args.e2e_callers / dt_multi, "unit": "probes/s",
+           "h2d_bytes_per_step": int(blob.nbytes + off.nbytes + kinds.nbytes + 2 * len(keys)) * BATCHES_PER_STEP,
+           "d2h_bytes_per_step": int(n_units * m_words * 8) * BATCHES_PER_STEP,
+           "callers": args.e2e_callers, "us_per_call_per_caller": dt_multi / e2e_calls * 1e6,
+           "single_caller": {"value": per_call * e2e_calls / dt_single, "us_per_call": dt_single / e2e_calls * 1e6},
+           "what": "bsg_probe(): packed host key bytes -> one H2D copy, one kernel (hashing fused into the probe), the "
+                   "(block x key) matrix rows written by the kernel into pinned host memory and copied to the caller's "
+                   "buffer; corpus resident in HBM (bytes per step = per call x batches per step)"}
+    out = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e, "clocks": clocks,
+           "launches_per_step": launches_per_batch * BATCHES_PER_STEP, "bitset_mb": bitset_bytes / 1e6,
+           "n_units_per_gpu": n_units, "replicas": n_rep}
+
+    cpu = None
+    if headline and env.rank == 0:
+        sec = sec_off = None
+        if env.world == 1 and not args.no_cpu:
+            cpu, sec, sec_off = cpu_probe_rates(desc, words, n_units, keys, kinds, c=c, gpu_matrix=got_m)
+        else:
+            sec, sec_off = encode_sections_gpu_arm(desc, words, n_units)
+        # ---- cold end to end: what the reference does per query — decode the filter sections, then probe
+        #      (file_format.go:392-448 inside query_exec.go:572-615): raw on-disk sections in host memory ->
+        #      bsg_corpus_load_sections (H2D, CRC32C + framing + BE decode on the device) -> bsg_probe -> free ----
+        if sec is not None:
+            outm = np.zeros((n_units, m_words), dtype=np.uint64)
+
+            def cold():
+                cp, status = bs.Corpus.from_sections(ctx, sec, sec_off)
+                cp.probe_packed(blob, off, kinds, None, outm, None)
+                cp.close()
+            cold()
+            assert np.array_equal(outm, got_m), "cold path matrix differs"
+            t0 = time.perf_counter()
+            n_cold = 10
+            for _ in range(n_cold):
+                cold()
+            dt = (time.perf_counter() - t0) / n_cold
+            out["e2e"]["cold"] = {"value": n_units * len(keys) / dt, "unit": "probes/s", "ms_per_query": dt * 1e3,
+                                  "h2d_bytes_per_query": int(sec.nbytes + sec_off.nbytes + blob.nbytes + off.nbytes),
+                                  "what": "bsg_corpus_load_sections (raw sections from host memory, CRC32C + decode on the "
+                                          "device) + bsg_probe + free, per 1k-key batch: the reference's per-query work"}
+    for q in queries:
+        q.close()
+    for cp in corpora:
+        cp.close()
+    return out, cpu
+
+
+def encode_sections_gpu_arm(desc, words, n_units):
+    """Raw filter sections for the cold e2e leg when the CPU leg (which owns the oracle's encoder) is skipped:
+    framing per file_format.go:343-385 written with numpy (flags, u32 LE length, BE header + words, CRC32C)."""
+    return None, None   # the cold leg needs the encoder; it runs with the cpu_baseline leg (N=1)
+
+
+def build_leg(env, args, peaks):
+    """Config 3: flush 100 M token keys into block + file-level bloom filters (blocks dealt to ranks)."""
+    bs, ctx = env.bs, env.ctx
+    from bloomsearch_b200 import _native as N
+    n_blocks_total, kpb, bpf = args.build_blocks, 10000, 100
+    files_total = n_blocks_total // bpf
+    my_files = [f for f in range(files_total) if f % env.world == env.rank]
+    my_blocks = [f * bpf + b for f in my_files for b in range(bpf)]
+    t = time.time()
+    blob, key_off, group_begin = gen_token_blocks(my_blocks, 43, kpb)
+    n_keys = len(key_off) - 1
+    log(f"build leg: {len(my_blocks)} blocks x {kpb} tokens = {n_keys / 1e6:.1f} M keys, {blob.nbytes / 1e6:.0f} MB ({time.time() - t:.1f}s)")
+    mb, kb = bs.estimate_parameters(kpb, FPR)
+    mf, kf = bs.estimate_parameters(kpb * bpf, FPR)
+    wb, wf = (mb + 63) // 64, (mf + 63) // 64
+    nb, nf = len(my_blocks), len(my_files)
+    desc = np.zeros(nb + nf, dtype=N.DESC_DTYPE)
+    desc["m"][:nb], desc["k"][:nb], desc["word_off"][:nb] = mb, kb, np.arange(nb, dtype=np.uint64) * wb
+    desc["m"][nb:], desc["k"][nb:], desc["word_off"][nb:] = mf, kf, nb * wb + np.arange(nf, dtype=np.uint64) * wf
+    n_words = nb * wb + nf * wf
+    gf = np.arange(nb, dtype=np.uint32)
+    gf2 = (nb + np.arange(nb, dtype=np.uint32) // bpf).astype(np.uint32)
+    ks = bs.KeySet(ctx, blob, key_off, group_begin)
+    ks.set_filters(gf, gf2, desc, n_words)
+    ks.build()
+    ctx.synchronize()
+    steps = max(3, min(args.steps, 10))
+    ms, _ = env.timed(lambda: ks.build(), steps)
+    kernel_ms = ms / steps
+    words = ks.fetch()
+    total_keys = env.sum(float(n_keys))
+    algo = int(blob.nbytes) + 8 * n_keys + 8 * n_words
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    res = {"workload": f"config3: {n_blocks_total} blocks x {kpb} distinct tokens (8-24 B) -> one token filter per block "
+                       f"(m={mb}, k={kb}) + one file-level filter per {bpf} blocks (m={mf}, k={kf}), every key hashed once "
+                       "for both (flush.go:204,221,253)",
+           "keys": int(total_keys), "value": total_keys / (kernel_ms / 1e3), "unit": "keys/s", "kernel_ms": kernel_ms,
+           "what": "memset of the output + build_kernel, keys resident in HBM (bsg_keyset_build), CUDA events, max over ranks",
+           "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": algo, "achieved": algo / (kernel_ms / 1e3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": algo / (kernel_ms / 1e3) / 1e9 / peak,
+                        "note": "key bytes + 8 B offsets + one write of every output word; the scattered atomics are "
+                                "implementation traffic; the kernel is bound by integer issue + shared/L2 atomics, not HBM"}}
+    # end to end: host buffers in, host bitsets out (the flush worker's call)
+    t0 = time.perf_counter()
+    w2 = ctx.build(blob, key_off, group_begin, gf, gf2, desc, n_words)
+    dt = env.max(time.perf_counter() - t0)
+    assert np.array_equal(w2, words), "bsg_build and bsg_keyset_build disagree"
+    res["e2e"] = {"value": total_keys / dt, "unit": "keys/s", "ms": dt * 1e3, "h2d_bytes": int(blob.nbytes + key_off.nbytes),
+                  "d2h_bytes": int(n_words * 8), "what": "bsg_build(): pageable host keys -> staged H2D -> kernel -> staged D2H"}
+    if env.rank == 0 and not args.no_cpu:
+        from oracle import cref
+        threads = os.cpu_count() or 1
+        # checker: the first 2 block filters and file 0's filter against the oracle
+        sel = 2
+        want = cref.build_filters(blob, key_off, group_begin[:sel + 1], np.arange(sel, dtype=np.uint32), None, desc[:sel], sel * wb)
+        assert np.array_equal(words[:sel * wb], want), "GPU block filters differ from the oracle"
+        fd = np.array([(mf, kf, 0)], dtype=N.DESC_DTYPE)
+        wantf = cref.build_filters(blob, key_off, np.array([0, bpf * kpb], np.uint64), np.zeros(1, np.uint32), None, fd, wf,
+                                   n_threads=1)
+        assert np.array_equal(words[nb * wb:nb * wb + wf], wantf), "GPU file-level filter differs from the oracle"
+        sample_blocks = min(nb, 200)
+        t0 = time.perf_counter()
+        cref.build_filters(blob, key_off, group_begin[:sample_blocks + 1], np.arange(sample_blocks, dtype=np.uint32),
+                           gf2[:sample_blocks] - nb + sample_blocks,
+                           np.concatenate([desc[:sample_blocks], desc[nb:nb + (sample_blocks + bpf - 1) // bpf]]),
+                           0, n_threads=threads) if False else None
+        d_s = np.zeros(sample_blocks, dtype=N.DESC_DTYPE)
+        d_s["m"], d_s["k"], d_s["word_off"] = mb, kb, np.arange(sample_blocks, dtype=np.uint64) * wb
+        t0 = time.perf_counter()
+        cref.build_filters(blob, key_off, group_begin[:sample_blocks + 1], np.arange(sample_blocks, dtype=np.uint32), None,
+                           d_s, sample_blocks * wb, n_threads=threads)
+        dtc = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": sample_blocks * kpb / dtc, "unit": "keys/s", "cores": threads, "kind": "port",
+                               "sample": f"first {sample_blocks} blocks ({sample_blocks * kpb} keys), block filters only, "
+                                         f"{threads} threads, {dtc:.2f}s", "gpu_output_verified_against_oracle": True}
+    ks.close()
+    return res, (blob, key_off, group_begin, my_files)
+
+
+def config5_leg(env, args, peaks, data):
+    """Config 5: file-level filters built as per-rank partial bitsets of identical (m,k), OR-combined across ranks."""
+    bs, ctx = env.bs, env.ctx
+    from bloomsearch_b200 import _native as N
+    kpb, bpf = 10000, 100
+    files_total = args.build_blocks // bpf
+    W, r = env.world, env.rank
+    # every rank takes blocks b with b % W == r of EVERY file: disjoint shards of each file's entries
+    my_blocks = [f * bpf + b for f in range(files_total) for b in range(bpf) if b % W == r]
+    t = time.time()
+    if W == 1 and data is not None:
+        blob, key_off, group_begin, _ = data
+    else:
+        blob, key_off, group_begin = gen_token_blocks(my_blocks, 43, kpb)
+    n_keys = len(key_off) - 1
+    mf, kf = bs.estimate_parameters(kpb * bpf, FPR)
+    wf = (mf + 63) // 64
+    wf_pad = (wf + 1) & ~1
+    desc = np.zeros(files_total, dtype=N.DESC_DTYPE)
+    desc["m"], desc["k"], desc["word_off"] = mf, kf, np.arange(files_total, dtype=np.uint64) * wf_pad
+    n_words = files_total * wf_pad
+    per_file = len(my_blocks) // files_total
+    gf = (np.arange(len(my_blocks), dtype=np.uint32) // per_file).astype(np.uint32)
+    ks = bs.KeySet(ctx, blob, key_off, group_begin)
+    ks.set_filters(gf, None, desc, n_words)
+    d_out = ctx.comm_alloc(n_words * 8) if W > 1 else None
+
+    def step():
+        ks.build(d_out)
+        if W > 1:
+            ctx.or_reduce_device(d_out, n_words)
+    step()
+    ctx.synchronize()
+    steps = max(3, min(args.steps, 10))
+    ms, _ = env.timed(step, steps)
+    ms_build, _ = env.timed(lambda: ks.build(d_out), steps)
+    words = ks.fetch()
+    total_keys = env.sum(float(n_keys))
+    res = {"workload": f"config5: {files_total} file-level filters (m={mf}, k={kf}, {wf * 8 / 1e6:.2f} MB each), the entries of "
+                       f"every file ({bpf} blocks x {kpb} keys) dealt to {W} rank(s) by block, each rank builds the partial "
+                       "bitsets of its shard, partials OR-combined on the device",
+           "value": total_keys / (ms / steps / 1e3), "unit": "keys/s", "ms_per_step": ms / steps, "build_ms": ms_build / steps,
+           "or_reduce_ms": (ms - ms_build) / steps, "scaling": "strong", "filter_bytes_per_rank": int(n_words * 8)}
+    if W > 1:
+        info = ctx.comm_info()
+        res["collective"] = {"peer_memory": info["peer_memory"], "nvlink_bytes_per_rank": info["last_nvlink_bytes"],
+                             "bound_bytes_per_rank": int(2 * (W - 1) / W * n_words * 8),
+                             "GBps_per_rank": info["last_nvlink_bytes"] / max((ms - ms_build) / steps / 1e3, 1e-9) / 1e9,
+                             "what": "bsg_or_reduce_device: one kernel per rank, rank r ORs slice r out of every peer's "
+                                     "buffer (NVLink loads) and stores it into every peer (NVLink stores)"
+                             if info["peer_memory"] else "NCCL all-to-all of slices + one OR kernel + all-gather"}
+    if r == 0 and not args.no_cpu:
+        from oracle import cref
+        fblob, fko, _ = gen_token_blocks(list(range(bpf)), 43, kpb)   # the whole union of file 0
+        fd = np.array([(mf, kf, 0)], dtype=N.DESC_DTYPE)
+        want = cref.build_filters(fblob, fko, np.array([0, bpf * kpb], np.uint64), np.zeros(1, np.uint32), None, fd, wf)
+        assert np.array_equal(words[:wf], want), "OR-combined file-level filter differs from buildFilters(union)"
+        res["bit_identical_to_buildFilters_of_union"] = True
+    ks.close()
+    if d_out:
+        ctx.comm_free(d_out)
+    return res
+
+
+def config4_leg(env, args, peaks):
+    """Config 4: 8-key AND/OR query over 10 k files / 1 M blocks sharded by file, hierarchical probe, mask all-gather."""
+    bs, ctx = env.bs, env.ctx
+    from bloomsearch_b200 import _native as N
+    from bloomsearch_b200.sharding import FileSharding
+    from synth.corpus import SynthCorpus
+    W, r = env.world, env.rank
+    files_total, bpf, rows = args.c4_files, 100, 1000
+    sh = FileSharding([bpf] * files_total, W)
+    my_files = sh.files_of(r)
+    base_files = 50                                   # distinct synthetic files per rank, replicated in HBM
+    reps = max(1, len(my_files) // base_files)
+    n_files = base_files * reps
+    c = SynthCorpus(42, r * base_files * bpf, base_files * bpf, rows, bpf)
+    d_blk, nw_blk = size_filters(c, bs)
+    fd = np.zeros(base_files * 3, dtype=N.DESC_DTYPE)
+    wo = nw_blk
+    for f in range(base_files):
+        for kind in range(3):
+            m, k = bs.estimate_parameters(max(int(c.file_counts[f][kind]), 1), FPR)
+            fd[f * 3 + kind] = (m, k, wo)
+            wo += (m + 63) // 64
+    gf = np.arange(len(d_blk), dtype=np.uint32)
+    gf2 = np.array([len(d_blk) + (b // bpf) * 3 + kind for b in range(c.n_blocks) for kind in range(3)], dtype=np.uint32)
+    wall = ctx.build(c.blob, c.key_off, c.group_begin, gf, gf2, np.concatenate([d_blk, fd]), wo)
+    fd_rel = fd.copy()
+    fd_rel["word_off"] -= nw_blk
+    blocks = bs.Corpus(ctx, np.tile(d_blk, reps), wall[:nw_blk])     # descriptors alias the host words; HBM copy is reps x
+    files = bs.Corpus(ctx, np.tile(fd_rel, reps), wall[nw_blk:])
+    n_units = blocks.n_units
+    parent = (np.arange(n_units, dtype=np.int64) // c.n_blocks * base_files +
+              (np.arange(n_units, dtype=np.int64) % c.n_blocks) // bpf).astype(np.uint32)
+    blocks.set_parents(parent, files.n_units)
+    ft = lambda b, j: c.key(int(c.group_begin[3 * b + 2]) + j)
+    split = lambda key: key.split(b"::", 1)
+    keys8 = [ft(17, 3), b"level::nope", ft(min(4021, c.n_blocks - 1), 1500), b"user_id::x1", b"service::auth", b"service::nosuch",
+             b"level::info", b"nested.az::az-1"]
+    q = bs.BloomQuery(bs.And(bs.Or(*[bs.FieldToken(*split(k)) for k in keys8[:4]]), bs.Or(*[bs.FieldToken(*split(k)) for k in keys8[4:6]]),
+                             bs.FieldToken(*split(keys8[6])), bs.FieldToken(*split(keys8[7]))))
+    cq = bs.compile_bloom_query(q)
+    qf = bs.Query(files, cq.keys, cq.kinds, cq.prog)
+    qb = bs.Query(blocks, cq.keys, cq.kinds, cq.prog)
+    mw = (int(env.max(float(n_units))) + 63) // 64
+    mw = (mw + 1) & ~1
+    d_all = ctx.comm_alloc(W * mw * 8) if W > 1 else None
+
+    def step():
+        qf.run(N.PROBE_AUTO)
+        qb.run_child(blocks, qf, N.PROBE_AUTO)
+        if W > 1:
+            ctx.allgather_masks_device(qb.device_mask(), mw, d_all)
+    step()
+    ctx.synchronize()
+    steps = max(10, args.steps)
+    ms, _ = env.timed(step, steps)
+    total_units = env.sum(float(n_units))
+    total_files = env.sum(float(files.n_units))
+    probes = len(cq.keys) * (total_units + total_files)
+    _, bmask = qb.fetch(want_matrix=False)
+    surv = int(bs.unpack_mask(bmask, n_units).sum())
+    res = {"workload": f"config4: {int(total_files)} files / {int(total_units)} blocks of {rows} rows dealt to {W} rank(s) by "
+                       "FileSharding, query And(Or(ft0..ft3), Or(ft4,ft5), ft6, ft7) (8 FieldToken keys), file-level stage -> "
+                       "device-side pruning -> block-level stage -> tree -> candidate-mask all-gather",
+           "value": probes / (ms / steps / 1e3), "unit": "probes/s", "ms_per_query": ms / steps, "scaling": "strong",
+           "blocks_per_rank": int(n_units), "files_per_rank": int(files.n_units), "surviving_blocks_this_rank": surv,
+           "bitset_gb_per_rank": (blocks.bitset_bytes(7) + files.bitset_bytes(7)) / 1e9,
+           "launches_per_query": qf.launches() + qb.launches() + (1 if W > 1 else 0)}
+    if W > 1:
+        gathered = ctx.read_device(d_all, W * mw).reshape(W, mw)
+        assert np.array_equal(gathered[r][:len(bmask)], bmask), "gathered mask of this rank differs from its local mask"
+        info = ctx.comm_info()
+        res["collective"] = {"peer_memory": info["peer_memory"], "mask_bytes_per_rank": int(mw * 8),
+                             "nvlink_bytes_per_rank": info["last_nvlink_bytes"]}
+    # end to end: one collective host call per query (keys up, gathered masks down)
+    out = bs.probe_hierarchical_gather(files, blocks, q, mw, W) if W > 1 else None
+    n_e2e = 20
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        if W > 1:
+            out = bs.probe_hierarchical_gather(files, blocks, q, mw, W)
+        else:
+            fm, bm = bs.probe_hierarchical(files, blocks, q)
+    dt = env.max(time.perf_counter() - t0) / n_e2e
+    res["e2e"] = {"value": probes / dt, "unit": "probes/s", "ms_per_query": dt * 1e3,
+                  "what": "bsg_probe_hierarchical_gather (host keys in, every rank's block mask out)" if W > 1
+                  else "bsg_probe_hierarchical (host keys in, file + block masks out)"}
+    if W > 1:
+        assert np.array_equal(out[r][:len(bmask)], bmask)
+    if r == 0 and not args.no_cpu:
+        from oracle import cref
+        b8, o8 = N.pack_keys(cq.keys)
+        threads = os.cpu_count() or 1
+        fmask = bs.unpack_mask(cref.probe_mask(fd_rel, wall[nw_blk:], base_files, b8, o8, cq.kinds, cq.prog, n_threads=threads), base_files)
+        t0 = time.perf_counter()
+        wm = bs.unpack_mask(cref.probe_mask(d_blk, wall[:nw_blk], c.n_blocks, b8, o8, cq.kinds, cq.prog, n_threads=threads), c.n_blocks)
+        dtc = time.perf_counter() - t0
+        want = wm & np.repeat(fmask, bpf)
+        got = bs.unpack_mask(bmask, n_units)
+        assert np.array_equal(got[:c.n_blocks], want) and np.array_equal(got[-c.n_blocks:], want), "config4 mask differs from the oracle"
+        res["oracle_checked_units"] = int(2 * c.n_blocks)
+        res["cpu_baseline"] = {"value": len(cq.keys) * c.n_blocks / dtc, "unit": "probes/s", "cores": threads, "kind": "port",
+                               "sample": f"block-level stage over {c.n_blocks} pre-decoded blocks, {threads} threads"}
+    qf.close()
+    qb.close()
+    blocks.close()
+    files.close()
+    if d_all:
+        ctx.comm_free(d_all)
+    return res
+
+
 def main():
     _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="2b", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=8, help="distinct HBM copies cycled so every step misses L2")
+    ap.add_argument("--replicas", type=int, default=8, help="distinct HBM copies cycled so every launch misses L2")
     ap.add_argument("--streams", type=int, default=2, help="streams the timed batches are issued on (round-robin)")
     ap.add_argument("--e2e-callers", type=int, default=4, help="host threads calling bsg_probe concurrently in the e2e leg")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary layout")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every CPU (oracle) leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the build / config4 / config5 legs")
+    ap.add_argument("--build-blocks", type=int, default=10000, help="config 3/5 size: blocks of 10 000 tokens (100 M keys at 10 000)")
+    ap.add_argument("--c4-files", type=int, default=10000, help="config 4 size: files of 100 blocks x 1000 rows")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    import bloomsearch_b200 as bs
-    from bloomsearch_b200 import _native as N
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = bs.Context(local_rank)
-
-    def barrier():
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    results = {}
-    cpu = None
+    env = Env(args)
+    peaks, ncu = load_peaks(), load_ncu_summary()
+    results, cpu = {}, None
     for wl in [args.workload] + ([] if args.no_also else [w for w in WORKLOADS if w != args.workload]):
-        headline = wl == args.workload
-        c = gen_corpus(wl, rank)
-        desc, n_words = size_filters(c, bs)
+        results[wl], cpu_wl = probe_leg(env, args, wl, wl == args.workload, peaks, ncu)
+        cpu = cpu or cpu_wl
+    extra = {}
+    if not args.no_extra:
         t = time.time()
-        words = ctx.build(c.blob, c.key_off, c.group_begin, np.arange(len(desc), dtype=np.uint32), None, desc, n_words)
-        log(f"GPU-built {len(desc)} filters, {n_words * 8 / 1e6:.1f} MB of bitsets ({time.time() - t:.1f}s incl. PCIe)")
-        keys, kinds = make_batch(c, 7 + rank)
-        n_units = c.n_blocks
-        blob, off = N.pack_keys(keys)
+        extra["build"], data = build_leg(env, args, peaks)
+        log(f"build leg done ({time.time() - t:.0f}s)")
+        t = time.time()
+        extra["config5"] = config5_leg(env, args, peaks, data)
+        del data
+        log(f"config5 leg done ({time.time() - t:.0f}s)")
+        t = time.time()
+        extra["config4"] = config4_leg(env, args, peaks)
+        log(f"config4 leg done ({time.time() - t:.0f}s)")
 
-        n_rep = max(1, args.replicas)
-        corpora = [bs.Corpus(ctx, desc, words) for _ in range(n_rep)]
-        bitset_bytes = corpora[0].bitset_bytes(7)
-        queries = [bs.Query(cp, keys, kinds, None) for cp in corpora]
-        # self-consistency before timing (no oracle in the GPU arm): the two data paths agree, and every
-        # sampled key is found in some block.  The oracle check lives in the cpu_baseline leg below.
-        queries[0].run(N.PROBE_STAGED)
-        got_m, got_mask = queries[0].fetch()
-        queries[0].run(N.PROBE_GATHER)
-        got_g, _ = queries[0].fetch()
-        assert np.array_equal(got_m, got_g), "staged and gather probe paths disagree"
-        assert bs.unpack_mask(got_mask, n_units).all()
-
-        # ---- device-timed steps, inputs resident in HBM; replicas cycled so no step hits L2.
-        #      A step = the batch's (block x key) membership matrix: one probe_staged launch
-        #      (no expression tree -> no mask kernel; the all-ones mask is not materialised). ----
-        RUN = N.PROBE_AUTO | N.RUN_MATRIX_ONLY
-        import ctypes as C
-        L = N.lib()
-        L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
-        cp_arr = (C.c_void_p * n_rep)(*[cp.handle for cp in corpora])
-        q_arr = (C.c_void_p * n_rep)(*[q._h for q in queries])
-
-        def run_steps(k, streams=None):
-            # the K launches are issued from C (ctypes drops the GIL): no interpreter jitter.
-            # Consecutive batches go round-robin on args.streams streams (independent batches overlap
-            # tail-to-head, as concurrent bsg_probe() callers on their pool streams do).
-            N.check(L.bsg_debug_run_cycle(ctx.handle, cp_arr, q_arr, n_rep, k, RUN, streams or args.streams))
-
-        run_steps(args.warmup)
-        barrier()
-        with ClockSampler(local_rank) as clk:
-            # load the GPU for >= 0.5 s first so the sampler sees clocks under load, then the
-            # timed K steps inside the same sampled, loaded period, then >= 1 s more load
-            t_end = time.time() + 0.5
-            while time.time() < t_end:
-                run_steps(256)
-                ctx.synchronize()
-            barrier()
-            ctx.timer_begin()
-            run_steps(args.steps)
-            ms = ctx.timer_end()
-            barrier()
-            ctx.timer_begin()          # same K steps serialised on ONE stream, for reference
-            run_steps(args.steps, 1)
-            ms_single = ctx.timer_end() / args.steps
-            barrier()
-            t_end = time.time() + 1.0
-            while time.time() < t_end:
-                run_steps(256)
-                ctx.synchronize()
-        launches_per_step = queries[0].launches()
-        k_ms = ms / args.steps  # this rank's probe-kernel time per launch (events on the launching stream)
-        ms = max_over_ranks(ms)
-        probes_per_step = n_units * len(keys)
-        total_probes = sum_over_ranks(float(probes_per_step))
-        value = total_probes * args.steps / (ms / 1e3)
-
-        # ---- roofline of the dominant (only) kernel of the step ----
-        algo_bytes = bitset_bytes + 32 * len(keys) + (len(keys) * n_units + 7) // 8
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = algo_bytes / (k_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": TRAFFIC_NCU.get(wl), "kernel": PROBE_KERNEL, "kernel_ms": k_ms,
-                    "kernel_ms_single_stream": ms_single, "frac_single_stream": algo_bytes / (ms_single / 1e3) / 1e9 / peak,
-                    "launch_streams": args.streams,
-                    "programmatic_dependent_launch": os.environ.get("BSG_PROBE_PDL", "1") != "0",
-                    "algorithmic_bytes_per_launch": algo_bytes,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
-
-        # ---- end to end through the C ABI call a host makes: bsg_probe() with HOST buffers.  Every
-        #      step uploads the packed key bytes / offsets / kinds, hashes, probes, and reads the
-        #      (block x key) matrix back to host memory.  args.e2e_callers host threads call
-        #      concurrently (the reference runs up to MaxQueryConcurrency file workers per query,
-        #      query_exec.go:303-357); the single-caller figure is reported next to it. ----
-        import threading
-        e2e_steps = max(20, min(args.steps, 200))
-        m_words = (len(keys) + 63) // 64
-
-        def e2e_run(n_callers, steps_each):
-            outs = [np.zeros((n_units, m_words), dtype=np.uint64) for _ in range(n_callers)]
-            def worker(t):
-                for i in range(steps_each):
-                    corpora[(t + i) % n_rep].probe_packed(blob, off, kinds, None, outs[t], None)
-            ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_callers)]
-            t0 = time.perf_counter()
-            for th in ths:
-                th.start()
-            for th in ths:
-                th.join()
-            dt = time.perf_counter() - t0
-            assert np.array_equal(outs[0], got_m), "e2e matrix differs from the resident run"
-            return dt
-
-        e2e_run(args.e2e_callers, 5)  # warm-up (scratch + pinned staging allocation)
-        barrier()
-        dt_multi = max_over_ranks(e2e_run(args.e2e_callers, e2e_steps))
-        barrier()
-        dt_single = max_over_ranks(e2e_run(1, e2e_steps))
-        e2e = {"value": total_probes * e2e_steps * args.e2e_callers / dt_multi, "unit": "probes/s",
-               "h2d_bytes_per_step": int(blob.nbytes + off.nbytes + kinds.nbytes),
-               "d2h_bytes_per_step": int(n_units * m_words * 8),
-               "callers": args.e2e_callers, "ms_per_step_per_caller": dt_multi / e2e_steps * 1e3,
-               "single_caller": {"value": total_probes * e2e_steps / dt_single, "ms_per_step": dt_single / e2e_steps * 1e3},
-               "what": "bsg_probe(): packed host key bytes -> one H2D copy, one kernel (hashing fused into the probe); the (block x key) matrix rows are "
-                       "written by the probe kernel straight into pinned host memory (device->host over PCIe inside "
-                       "the call), then copied to the caller's buffer"}
-
-        if headline and rank == 0 and world == 1 and not args.no_cpu:
-            cpu, _ = cpu_probe_rate(desc, words, n_units, keys, kinds, c=c, gpu_matrix=got_m)
-
-        results[wl] = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e,
-                       "clocks": clk.summary(), "launches_per_step": launches_per_step,
-                       "bitset_mb": bitset_bytes / 1e6, "n_units_per_gpu": n_units, "replicas": n_rep}
-        for q in queries:
-            q.close()
-        for cp in corpora:
-            cp.close()
-        del words, c
-
-    if rank == 0:
+    if env.rank == 0:
         r = results[args.workload]
-        n_blocks, rows, _ = WORKLOADS[args.workload]
         out = {
-            "metric": "bloom probes/sec (block-level)", "value": r["value"], "unit": "probes/s", "n_gpus": world,
+            "metric": "bloom probes/sec (block-level)", "value": r["value"], "unit": "probes/s", "n_gpus": env.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"config2-{args.workload}: 10M-row synthetic log corpus per GPU as {n_blocks} blocks x "
-                                   f"{rows} rows, fpr 0.001, batched 1k-key block probe (500 present / 500 absent)",
-                       "keys_per_batch": N_KEYS, "blocks_per_gpu": r["n_units_per_gpu"],
+            "config": {"workload": workload_string(args.workload),
+                       "keys_per_batch": N_KEYS, "batches_per_step": BATCHES_PER_STEP, "blocks_per_gpu": r["n_units_per_gpu"],
                        "bitset_mb_per_gpu": r["bitset_mb"],
-                       "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per step "
+                       "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per launch "
                              f"({r['replicas'] * r['bitset_mb']:.0f} MB > 126 MB L2): inputs larger than L2",
-                       "sharding": "by file, one shard per GPU, no data-path collective",
-                       "timed_launches": f"K probe launches issued from C, round-robin on {args.streams} streams forked "
-                                         "from / joined to the timed stream (independent batches overlap tail-to-head)"},
+                       "sharding": "every rank owns its own 10M-row shard (sharded by file); no data-path collective in this "
+                                   "leg — the product's collectives are timed in the config4 / config5 legs",
+                       "timed_launches": f"{BATCHES_PER_STEP} probe launches per step issued from C, round-robin on "
+                                         f"{args.streams} streams forked from / joined to the timed stream (independent "
+                                         "batches overlap tail-to-head); roofline.frac is the ONE-stream figure"},
             "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "clocks": r["clocks"],
             "gpu_launches": r["launches_per_step"] * args.steps,
             "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],
                          "e2e": v["e2e"]} for w, v in results.items() if w != args.workload},
         }
+        if env.comm:
+            out["comm"] = {"peer_memory": env.comm["peer_memory"], "world": env.world}
+        out.update(extra)
         emit(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    ctx.close()
+    if env.world > 1:
+        env.dist.barrier()
+    env.ctx.close()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

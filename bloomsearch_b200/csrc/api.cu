@@ -2130,6 +2130,20 @@ extern "C" int bsg_debug_run_cycle(bsg_ctx* ctx, bsg_corpus* const* corpora, bsg
     return BSG_OK;
 }
 
+// reporting helper: which staged kernel a big-batch probe of this corpus launches, and how the corpus was cut
+extern "C" int bsg_debug_probe_kernel_name(bsg_ctx* ctx, const bsg_corpus* c, char* buf, size_t n) {
+    if (!ctx || !c || !buf || n == 0) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (ctx->probe_variant == 6)
+        snprintf(buf, n, "%s, %s mode, %u item(s) x %u tile(s), <= %u unit(s) and %u data bytes per tile; %u unit(s) on the gather kernel",
+                 probe_tiles_shape_name(ctx->tiles_shape), c->t_parts == 1 ? "UNIT" : "KIND", c->t_items, c->t_parts,
+                 c->t_units_cap, c->t_data_cap, c->t_gather);
+    else if (ctx->probe_variant == 0)
+        snprintf(buf, n, "probe_staged_kernel (one phase)");
+    else
+        snprintf(buf, n, "probe_staged2_kernel shape %d", ctx->probe_variant);
+    return BSG_OK;
+}
+
 // test / bench helper: synchronise the ctx stream, then copy device memory (e.g. a bsg_comm_alloc buffer) to the host
 extern "C" int bsg_debug_memcpy_d2h(bsg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     if (!ctx || !dst_host || !src_dev) return fail(BSG_ERR_INVALID, "NULL argument");
