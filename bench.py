@@ -582,11 +582,6 @@ def build_leg(env, args, peaks):
                                    n_threads=1)
         assert np.array_equal(words[nb * wb:nb * wb + wf], wantf), "GPU file-level filter differs from the oracle"
         sample_blocks = min(nb, 200)
-        t0 = time.perf_counter()
-        cref.build_filters(blob, key_off, group_begin[:sample_blocks + 1], np.arange(sample_blocks, dtype=np.uint32),
-                           gf2[:sample_blocks] - nb + sample_blocks,
-                           np.concatenate([desc[:sample_blocks], desc[nb:nb + (sample_blocks + bpf - 1) // bpf]]),
-                           0, n_threads=threads) if False else None
         d_s = np.zeros(sample_blocks, dtype=N.DESC_DTYPE)
         d_s["m"], d_s["k"], d_s["word_off"] = mb, kb, np.arange(sample_blocks, dtype=np.uint64) * wb
         t0 = time.perf_counter()

@@ -1021,15 +1021,22 @@ int make_layout(const bsg_filter_desc* desc, uint64_t n_units, Layout& L) {
     return BSG_OK;
 }
 
+// Shared memory one CTA of the configured probe_tiles shape may use: 1024 / threads CTAs share an SM, each
+// pays 1 KB of system-reserved shared memory.
+uint64_t tiles_cta_smem(const bsg_ctx* ctx) {
+    const uint64_t per_sm = 1024 / static_cast<uint64_t>(probe_tiles_threads(ctx->tiles_shape));
+    const uint64_t sm_total = static_cast<uint64_t>(ctx->max_smem_optin) + 1024;   // 228 KB per SM, 227 KB opt-in per CTA
+    return std::min<uint64_t>(ctx->max_smem_optin, (sm_total / per_sm - 1024) & ~uint64_t(127));
+}
+
 // Cuts the corpus into tiles for probe_tiles_kernel (bsg_internal.h): decides UNIT vs KIND mode, groups
 // small units, and lists the units no tile can hold (they take the gather kernel).
 int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
     // ring budget for a full pass of keys: the fixed part grows with the units per tile (survivor lists, rows)
     const uint32_t group_cap = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
-    auto ring_budget = [&](uint32_t units_cap) {
-        return static_cast<uint64_t>(ctx->max_smem_optin) - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass);
-    };
+    const uint64_t cta_smem = tiles_cta_smem(ctx);
+    auto ring_budget = [&](uint32_t units_cap) { return cta_smem - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass); };
     const uint64_t min_stages = static_cast<uint64_t>(ctx->tile_min_stages);
     const uint64_t unit_limit = ring_budget(group_cap) / min_stages - tile_header_bytes(group_cap);  // UNIT mode
     const uint64_t part_limit = ring_budget(1) / 2 - tile_header_bytes(1);                            // KIND mode: >= 2 stages
@@ -1689,11 +1696,11 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
             if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
-            plan.n_stages = static_cast<int>(
-                std::min<uint64_t>(max_stages, (static_cast<uint64_t>(ctx->max_smem_optin) - fixed) / stage_bytes));
+            plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, (tiles_cta_smem(ctx) - fixed) / stage_bytes));
             if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: tile does not fit shared memory");
             plan.smem_bytes = fixed + plan.n_stages * stage_bytes;
-            plan.grid = static_cast<int>(std::min<uint64_t>(c->t_items, ctx->sm_count));
+            plan.grid = static_cast<int>(std::min<uint64_t>(
+                c->t_items, static_cast<uint64_t>(ctx->sm_count) * (1024 / probe_tiles_threads(plan.shape))));
             const TileRec* tiles = c->d_tiles;
             const uint32_t* d_n_items = nullptr;
             if (d_parent) {  // keep the tiles with a unit whose parent survived (compacted on the device)

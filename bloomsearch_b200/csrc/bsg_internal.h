@@ -158,6 +158,7 @@ struct ProbeTilesPlan {
 };
 cudaError_t probe_tiles_configure(int max_smem_optin);
 int probe_tiles_n_shapes();
+int probe_tiles_threads(int shape);        // threads per CTA of a compiled shape; 1024 / threads CTAs share an SM
 const char* probe_tiles_shape_name(int shape);
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
                                const uint32_t* d_n_items, const uint64_t* d_words, const uint64_t* d_hashes,

@@ -114,9 +114,10 @@ __device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uin
 // specialised A / B warps: the scheduler favoured the A warps and phase B ran 5-10x slower than its
 // instruction count), and the geometric tail of TestString is re-compacted twice instead of
 // idling lanes.
-template <int NT, bool TRACE>
-__global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesArgs a) {
-    static_assert(NT >= 1 && NT <= 4, "shape");
+template <int NT, int NTHR, bool TRACE>
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const ProbeTilesArgs a) {
+    static_assert(NT >= 1 && NT <= 4 && (NTHR == 1024 || NTHR == 512), "shape");
+    constexpr int KPT = static_cast<int>(kProbeMaxKeysPerPass) / NTHR;   // key slots per thread in round A
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + 128);          // cnt[0] = |L1|, cnt[1] = |L2|
@@ -202,21 +203,29 @@ __global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesAr
     __syncthreads();
     if (TRACE && tr && tid == 0) tr[1] = globaltimer_ns();
 
-    // ---- this thread's key for round A ----
-    uint64_t loc[NT];        // location(h, 0..NT-1) = h0, h1+h3, h0+2*h3, h1+3*h2
-    uint32_t koff = 0, kbit = 0;
+    // ---- this thread's keys for round A: sorted slots tid + j*NTHR ----
+    uint64_t loc[KPT][NT];   // location(h, 0..NT-1) = h0, h1+h3, h0+2*h3, h1+3*h2
+    uint32_t koff[KPT], kbit[KPT];
+    uint32_t warp_kinds = 0;
 #pragma unroll
-    for (int t = 0; t < NT; ++t) loc[t] = 0;
-    if (tid < a.n_keys) {
-        const ulonglong2 x = htab[2 * tid], y = htab[2 * tid + 1];
-        const uint64_t l4[4] = {x.x, x.y + y.y, x.x + 2 * y.y, x.y + 3 * y.x};
+    for (int j = 0; j < KPT; ++j) {
+        const uint32_t slot = tid + j * NTHR;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) loc[t] = l4[t];
-        const uint32_t kind = s_slot[tid] >> 14;
-        koff = kind * 16u;
-        kbit = 1u << kind;
+        for (int t = 0; t < NT; ++t) loc[j][t] = 0;
+        koff[j] = 0;
+        kbit[j] = 0;
+        if (slot < a.n_keys) {
+            const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
+            const uint64_t l4[4] = {x.x, x.y + y.y, x.x + 2 * y.y, x.y + 3 * y.x};
+#pragma unroll
+            for (int t = 0; t < NT; ++t) loc[j][t] = l4[t];
+            const uint32_t kind = s_slot[slot] >> 14;
+            koff[j] = kind * 16u;
+            kbit[j] = 1u << kind;
+        }
+        warp_kinds |= kbit[j];
     }
-    const uint32_t warp_kinds = __reduce_or_sync(0xffffffffu, kbit);
+    warp_kinds = __reduce_or_sync(0xffffffffu, warp_kinds);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t out_words = (a.n_keys + 31) >> 5;
     uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
@@ -231,41 +240,76 @@ __global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesAr
         const uint8_t* data = st + a.hdr_bytes;
         // ---------------------------------------------------------------- round A ---
         if (warp_kinds & head.y) {
-            const bool act = (kbit & head.y) != 0;
+            // the ballot words stay in registers (lane u keeps unit u's words) until the tile's units are done:
+            // no shared-memory traffic inside the loop, so consecutive keys / units overlap; then ONE atomic per
+            // warp per tile reserves the warp's range of L1
+            uint32_t my[KPT];
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) my[j] = 0;
             auto unit_loop = [&](auto small_k) {
                 constexpr bool SMALLK = decltype(small_k)::value;
-                const uint8_t* desc = st + kTileDescOff + koff;
+                const uint8_t* desc = st + kTileDescOff;
 #pragma unroll 2
                 for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
-                    uint4 f = make_uint4(0, 0, 0, 0);
-                    if (act) f = *reinterpret_cast<const uint4*>(desc);
-                    // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
-                    const bool test = act && f.x != 0;
-                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
-                    uint32_t bit[NT], wv[NT];
+                    bool pass[KPT];
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
+                    for (int j = 0; j < KPT; ++j) {
+                        const bool act = (kbit[j] & head.y) != 0;
+                        uint4 f = make_uint4(0, 0, 0, 0);
+                        if (act) f = *reinterpret_cast<const uint4*>(desc + koff[j]);
+                        // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
+                        const bool test = act && f.x != 0;
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                        uint32_t bit[NT], wv[NT];
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
-                    uint32_t p = 1u;
+                        for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f.x, f.y, f.z);
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
-                        if (SMALLK) b |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
-                        p &= b;
+                        for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
+                        uint32_t p = 1u;
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
+                            if (SMALLK) b |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
+                            p &= b;
+                        }
+                        pass[j] = act && (f.x == 0 || p != 0u);
                     }
-                    const bool pass = act && (f.x == 0 || p != 0u);
-                    const uint32_t bits = __ballot_sync(0xffffffffu, pass);
-                    if (bits) {  // warp-aggregated append
-                        uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&cnt[0], static_cast<uint32_t>(__popc(bits)));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (pass) L1[base + __popc(bits & lt_mask)] = static_cast<uint16_t>((u << 10) | tid);
+#pragma unroll
+                    for (int j = 0; j < KPT; ++j) {
+                        const uint32_t bits = __ballot_sync(0xffffffffu, pass[j]);
+                        if (lane == u) my[j] = bits;
                     }
                 }
             };
             if (head.z & kTileSmallK) unit_loop(std::true_type{});
             else unit_loop(std::false_type{});
+            // append: lane u knows how many of unit u's keys survived in this warp
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) mine += __popc(my[j]);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < static_cast<int>(kTileMaxUnits); d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= static_cast<uint32_t>(d)) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, kTileMaxUnits - 1);
+            if (total) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[0], total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t excl = base + incl - mine;
+                for (uint32_t u = 0; u < head.x; ++u) {
+                    uint32_t off_u = __shfl_sync(0xffffffffu, excl, u);
+#pragma unroll
+                    for (int j = 0; j < KPT; ++j) {
+                        const uint32_t w = __shfl_sync(0xffffffffu, my[j], u);
+                        if ((w >> lane) & 1u)
+                            L1[off_u + __popc(w & lt_mask)] = static_cast<uint16_t>((u << 10) | (tid + j * NTHR));
+                        off_u += __popc(w);
+                    }
+                }
+            }
         }
         __syncthreads();
         const uint32_t n1 = ld_volatile_shared_u32(&cnt[0]);
@@ -350,7 +394,8 @@ __global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesAr
                     for (int i = 0; i < static_cast<int>(kTileMaxUnits) * 3; ++i) nb16[i] = src16[i];
                 }
                 const bool has_next = nxt + S < my_tiles;
-                fence_proxy_async();
+                // no proxy fence: the stage was only READ through the generic proxy, and those reads are ordered
+                // before this point by the CTA barrier (write-after-read needs no cross-proxy fence)
                 fill_tile(st, &full[s], rec_of(nxt), has_next, has_next ? rec_of(nxt + S) : rec_of(nxt), a.words, f0, nb16,
                           a.kind_mask, a.hdr_bytes);
             }
@@ -360,19 +405,27 @@ __global__ void __launch_bounds__(1024, 1) probe_tiles_kernel(const ProbeTilesAr
     }
 }
 
-// ---- compiled shapes: <tests of round A> ----
-#define BSG_TILES_SHAPES(X) X(0, 3) X(1, 2) X(2, 4)
+// ---- compiled shapes: <tests of round A, threads per CTA> (1024 / threads CTAs share an SM) ----
+#define BSG_TILES_SHAPES(X) X(0, 3, 512) X(1, 3, 1024) X(2, 2, 512) X(3, 2, 1024) X(4, 4, 512)
 
 int probe_tiles_n_shapes() {
     int n = 0;
-#define X(id, nt) ++n;
+#define X(id, nt, thr) ++n;
     BSG_TILES_SHAPES(X)
 #undef X
     return n;
 }
+int probe_tiles_threads(int shape) {
+    switch (shape) {
+#define X(id, nt, thr) case id: return thr;
+        BSG_TILES_SHAPES(X)
+#undef X
+        default: return 1024;
+    }
+}
 const char* probe_tiles_shape_name(int shape) {
     switch (shape) {
-#define X(id, nt) case id: return "probe_tiles_kernel<NT=" #nt ">";
+#define X(id, nt, thr) case id: return "probe_tiles_kernel<NT=" #nt "," #thr " threads>";
         BSG_TILES_SHAPES(X)
 #undef X
         default: return "probe_tiles_kernel<?>";
@@ -381,21 +434,21 @@ const char* probe_tiles_shape_name(int shape) {
 
 cudaError_t probe_tiles_configure(int max_smem_optin) {
     cudaError_t e = cudaSuccess;
-#define X(id, nt)                                                                                                     \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin); \
-    if (e != cudaSuccess) return e;                                                                                   \
-    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);  \
+#define X(id, nt, thr)                                                                                                    \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, thr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin); \
+    if (e != cudaSuccess) return e;                                                                                       \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, thr, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);  \
     if (e != cudaSuccess) return e;
     BSG_TILES_SHAPES(X)
 #undef X
     return e;
 }
 
-template <int NT>
+template <int NT, int NTHR>
 static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs& args, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(NTHR);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -403,8 +456,8 @@ static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.pdl ? 1 : 0;
-    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, true>, args);
-    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, false>, args);
+    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, NTHR, true>, args);
+    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, NTHR, false>, args);
 }
 
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
@@ -436,7 +489,7 @@ cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tile
     a.trace = d_trace;
     a.trace_slots = d_trace ? trace_slots : 0;
     switch (plan.shape) {
-#define X(id, nt) case id: return tiles_launch<nt>(plan, a, s);
+#define X(id, nt, thr) case id: return tiles_launch<nt, thr>(plan, a, s);
         BSG_TILES_SHAPES(X)
 #undef X
         default: return cudaErrorInvalidValue;
