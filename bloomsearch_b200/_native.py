@@ -68,6 +68,9 @@ ABI_SYMBOLS = [
     "bsg_keyset_create", "bsg_keyset_count_distinct", "bsg_keyset_set_filters", "bsg_keyset_build", "bsg_keyset_fetch",
     "bsg_keyset_device_words", "bsg_keyset_free", "bsg_query_run_child", "bsg_query_device_mask", "bsg_comm_info",
     "bsg_comm_alloc", "bsg_comm_free", "bsg_or_reduce_device", "bsg_allgather_masks_device", "bsg_probe_hierarchical_gather",
+    "bsg_corpus_device_bytes", "bsg_cache_create", "bsg_cache_destroy", "bsg_cache_acquire", "bsg_cache_insert",
+    "bsg_cache_insert_sections", "bsg_cache_release", "bsg_cache_invalidate", "bsg_cache_stats",
+    "bsg_host_alloc", "bsg_host_free",
 ]
 
 
@@ -141,6 +144,20 @@ def lib():
     L.bsg_or_reduce_device.argtypes = [vp, vp, u64]
     L.bsg_allgather_masks_device.argtypes = [vp, vp, u64, vp]
     L.bsg_probe_hierarchical_gather.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, u32, u64, vp]
+    L.bsg_corpus_device_bytes.argtypes = [vp]
+    L.bsg_corpus_device_bytes.restype = u64
+    L.bsg_cache_create.argtypes = [vp, u64, C.POINTER(vp)]
+    L.bsg_cache_destroy.argtypes = [vp]
+    L.bsg_cache_destroy.restype = None
+    L.bsg_cache_acquire.argtypes = [vp, u64, C.POINTER(vp)]
+    L.bsg_cache_insert.argtypes = [vp, u64, vp, C.POINTER(vp)]
+    L.bsg_cache_insert_sections.argtypes = [vp, u64, vp, vp, u64, i32, vp, C.POINTER(u64), C.POINTER(vp)]
+    L.bsg_cache_release.argtypes = [vp, vp]
+    L.bsg_cache_release.restype = None
+    L.bsg_cache_invalidate.argtypes = [vp, u64]
+    L.bsg_cache_stats.argtypes = [vp] + [C.POINTER(u64)] * 6
+    L.bsg_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.bsg_host_free.argtypes = [vp, vp]
     _lib = L
     return L
 

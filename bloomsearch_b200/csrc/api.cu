@@ -88,9 +88,10 @@ struct bsg_ctx {
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
-    int probe_variant = 6; // BSG_PROBE_VARIANT: 6 = probe_tiles (default); 0 = probe_staged (one phase), 1..5 = shapes of probe_staged2
-    int tiles_shape = 0;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
-    int tile_bytes = 32 * 1024;  // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
+    int probe_variant = 7; // BSG_PROBE_VARIANT: 7 = per corpus (default, see staged_variant_for); 6 = probe_tiles; 0 = probe_staged
+                           // (one phase); 1..5 = shapes of probe_staged2
+    int tiles_shape = 1;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
+    int tile_bytes = 60000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
     int tile_min_stages = 3;  // BSG_TILE_MIN_STAGES: UNIT mode keeps units small enough for a ring of this many stages
@@ -98,6 +99,9 @@ struct bsg_ctx {
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
     int fuse_hash = 1;     // BSG_PROBE_FUSE_HASH: bsg_probe() hashes inside the staged probe kernel when it can
+    int spin_wait = 1;     // BSG_PROBE_SPIN: bsg_probe() polls the stream instead of blocking in cudaStreamSynchronize
+    std::mutex host_mu;
+    std::vector<std::pair<uint8_t*, size_t>> host_bufs;  // bsg_host_alloc: pinned + mapped caller buffers
     int zero_copy = 1;     // BSG_PROBE_ZEROCOPY: bsg_probe() matrix rows written straight to pinned host memory
     int pdl = 1;           // BSG_PROBE_PDL: programmatic dependent launch of the two-phase probe kernel
     int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
@@ -159,7 +163,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
-    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(6, std::max(0, atoi(w)));
+    if (const char* w = getenv("BSG_PROBE_VARIANT")) ctx->probe_variant = std::min(7, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_TILES_SHAPE")) ctx->tiles_shape = std::min(probe_tiles_n_shapes() - 1, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_TILE_BYTES")) ctx->tile_bytes = std::max(1024, atoi(w));
     if (const char* w = getenv("BSG_TILE_UNITS")) ctx->tile_units = std::min<int>(kTileMaxUnits, std::max(1, atoi(w)));
@@ -169,6 +173,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
     if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_ZEROCOPY")) ctx->zero_copy = atoi(w) != 0;
+    if (const char* w = getenv("BSG_PROBE_SPIN")) ctx->spin_wait = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
     return BSG_OK;
@@ -188,6 +193,7 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     if (ctx->comm) bsg_comm_destroy_internal(ctx->comm);  // also frees the symmetric buffers (d_gather)
     for (cudaStream_t s : ctx->stream_pool) cudaStreamDestroy(s);
     for (bsg_query* q : ctx->scratch_pool) bsg_query_free(q);
+    for (auto& hb : ctx->host_bufs) cudaFreeHost(hb.first);
     for (uint8_t* p : ctx->stage_pin) cudaFreeHost(p);
     for (cudaStream_t s : ctx->stage_streams) cudaStreamDestroy(s);
     for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
@@ -223,6 +229,62 @@ extern "C" int bsg_device_info(bsg_ctx* ctx, int* sm_count, size_t* smem_optin, 
     if (cc_major) *cc_major = ctx->cc_major;
     if (cc_minor) *cc_minor = ctx->cc_minor;
     return BSG_OK;
+}
+
+// Pinned, device-mapped host memory for result buffers: bsg_probe() lets its kernels write a matrix that lives
+// in such a buffer directly (no staging copy at the end of the call).
+extern "C" int bsg_host_alloc(bsg_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return fail(BSG_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CUDA_TRY(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, std::max<size_t>(bytes, 16));
+    std::lock_guard<std::mutex> lk(ctx->host_mu);
+    ctx->host_bufs.emplace_back(static_cast<uint8_t*>(p), std::max<size_t>(bytes, 16));
+    *out = p;
+    return BSG_OK;
+}
+
+extern "C" int bsg_host_free(bsg_ctx* ctx, void* ptr) {
+    if (!ctx) return fail(BSG_ERR_INVALID, "NULL argument");
+    if (!ptr) return BSG_OK;
+    std::lock_guard<std::mutex> lk(ctx->host_mu);
+    for (size_t i = 0; i < ctx->host_bufs.size(); ++i)
+        if (ctx->host_bufs[i].first == ptr) {
+            cudaFreeHost(ptr);
+            ctx->host_bufs.erase(ctx->host_bufs.begin() + i);
+            return BSG_OK;
+        }
+    return fail(BSG_ERR_INVALID, "bsg_host_free: not a bsg_host_alloc buffer");
+}
+
+static uint32_t* host_buf_device_ptr(bsg_ctx* ctx, const void* p, size_t bytes) {
+    const uint8_t* p8 = static_cast<const uint8_t*>(p);
+    {
+        std::lock_guard<std::mutex> lk(ctx->host_mu);
+        bool found = false;
+        for (auto& hb : ctx->host_bufs)
+            if (p8 >= hb.first && p8 + bytes <= hb.first + hb.second) { found = true; break; }
+        if (!found) return nullptr;
+    }
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return static_cast<uint32_t*>(d);
+}
+
+// wait for a stream without parking the thread in the driver (a 15-20 us kernel is over before a blocked
+// thread is rescheduled); falls back to the blocking call after ~2 ms
+static cudaError_t stream_wait(bsg_ctx* ctx, cudaStream_t s) {
+    if (ctx && ctx->spin_wait) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (uint32_t i = 0;; ++i) {
+            const cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            if ((i & 63u) == 63u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+        }
+    }
+    return cudaStreamSynchronize(s);
 }
 
 extern "C" int bsg_timer_begin(bsg_ctx* ctx) {
@@ -973,6 +1035,17 @@ extern "C" uint64_t bsg_corpus_bitset_bytes(const bsg_corpus* c, uint32_t kind_m
     return t;
 }
 
+// HBM held by a corpus: bitset words + descriptor / stage / tile tables + unit lists (the resident cache's unit of account)
+extern "C" uint64_t bsg_corpus_device_bytes(const bsg_corpus* c) {
+    if (!c) return 0;
+    uint64_t b = (c->total_words + 2) * 8 + c->n_units * 3 * sizeof(DevFilter);
+    b += static_cast<uint64_t>(c->n_staged) * sizeof(StageRow) + static_cast<uint64_t>(c->t_items) * c->t_parts * sizeof(TileRec);
+    b += 4ull * (c->d_staged_list ? c->n_staged : 0) + 4ull * c->n_gather + 4ull * (c->d_t_staged_list ? c->t_staged : 0) + 4ull * c->t_gather;
+    if (c->d_parent) b += c->n_units * 4;
+    if (c->d_bad32) b += (c->n_units + 31) / 32 * 4 + 8;
+    return b;
+}
+
 extern "C" int bsg_corpus_unit_desc(const bsg_corpus* c, uint64_t unit, bsg_filter_desc out_desc[3]) {
     if (!c || !out_desc || unit >= c->n_units) return fail(BSG_ERR_INVALID, "bad unit");
     for (int k = 0; k < 3; ++k) out_desc[k] = c->h_desc[unit * 3 + k];
@@ -1396,6 +1469,7 @@ struct bsg_query {
     uint64_t* d_hash_scratch = nullptr;
     size_t cap_hash_scratch = 0;
     uint32_t* k_matrix = nullptr;
+    bool direct_out = false;       // k_matrix points into a caller buffer from bsg_host_alloc
     uint32_t* h_out = nullptr;
     uint32_t* h_out_dev = nullptr;
     size_t cap_out = 0;
@@ -1595,6 +1669,7 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         q->hashed = true;
     }
     q->k_matrix = q->d_matrix32;
+    q->direct_out = false;
     return BSG_OK;
 }
 
@@ -1646,6 +1721,30 @@ extern "C" int bsg_query_create(bsg_ctx* ctx, const bsg_corpus* corpus, const ui
     return BSG_OK;
 }
 
+// Which staged kernel serves this corpus (measured on B200, profiles/r02_*): the tile ring wins on small units
+// (several units per stage: the flush-shaped 1 000-row blocks) and is the only staged path for units of
+// 75-190 KB (one stage per kind); the two-phase probe_staged2 kernel wins on units of 20-75 KB (merged
+// 10 000-row blocks), where one unit fills a stage.
+static int staged_variant_for(const bsg_ctx* ctx, const bsg_corpus* c) {
+    if (ctx->probe_variant != 7) return ctx->probe_variant;
+    if (c->n_staged == 0 || c->t_gather < c->n_gather) return 6;
+    uint64_t bytes = 0;
+    for (int k = 0; k < 3; ++k) bytes += c->staged_kind_bytes[k];
+    return bytes / c->n_staged < 20 * 1024 ? 6 : 3;
+}
+
+// BSG_PROBE_AUTO: stream the staged units' bitsets through shared memory, or gather single words?
+// staged traffic = every byte of the touched kinds; gather traffic ~ one 32 B sector per tested location
+// (~3 on average for an absent key, k for a present one) + the descriptor.
+static bool auto_uses_staged(const bsg_corpus* c, int variant, uint32_t kind_mask, uint32_t n_keys) {
+    const uint32_t n_st = variant == 6 ? c->t_staged : c->n_staged;
+    if (n_st == 0) return false;
+    uint64_t staged_bytes = 0;
+    for (int k = 0; k < 3; ++k)
+        if (kind_mask & (1u << k)) staged_bytes += variant == 6 ? c->t_staged_kind_bytes[k] : c->staged_kind_bytes[k];
+    return staged_bytes <= static_cast<uint64_t>(n_st) * n_keys * (4 * 32 + 32);
+}
+
 static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int path, int want_matrix, cudaStream_t s,
                         const uint32_t* d_parent_mask32 = nullptr) {
     // d_parent_mask32 != nullptr: hierarchical stage — unit u is probed only if bit c->d_parent[u] of
@@ -1661,19 +1760,12 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
     if (path != BSG_PROBE_AUTO && path != BSG_PROBE_STAGED && path != BSG_PROBE_GATHER)
         return fail(BSG_ERR_INVALID, "unknown path %d", path);
     int launches = 0;
-    if (q->n_keys && c->n_units && ctx->probe_variant == 6) {
+    const int variant = (ctx && c) ? staged_variant_for(ctx, c) : 3;
+    if (q->n_keys && c->n_units && variant == 6) {
         // ---- tile ring (probe_tiles_kernel) for the units a tile can hold, gather kernel for the rest ----
         bool use_staged = c->t_staged > 0;
         if (path == BSG_PROBE_GATHER) use_staged = false;
-        if (path == BSG_PROBE_AUTO && use_staged) {
-            // staged traffic = every byte of the touched kinds; gather traffic ~ one 32 B sector per
-            // tested location (~3 on average for an absent key, k for a present one) + the descriptor.
-            uint64_t staged_bytes = 0;
-            for (int k = 0; k < 3; ++k)
-                if (q->kind_mask & (1u << k)) staged_bytes += c->t_staged_kind_bytes[k];
-            const uint64_t gather_bytes = static_cast<uint64_t>(c->t_staged) * q->n_keys * (4 * 32 + 32);
-            use_staged = staged_bytes <= gather_bytes;
-        }
+        if (path == BSG_PROBE_AUTO && use_staged) use_staged = auto_uses_staged(c, 6, q->kind_mask, q->n_keys);
         // deferred hashing (bsg_probe path): every CTA of the tile kernel hashes the batch into its own shared
         // memory when that kernel is the only consumer of the hashes, else a hash_keys_kernel launch now
         const bool fuse = !q->hashed && use_staged && c->t_gather == 0;
@@ -1735,18 +1827,10 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         // --- choose the data path for the stageable units ---
         bool use_staged = c->n_staged > 0;
         if (path == BSG_PROBE_GATHER) use_staged = false;
-        if (path == BSG_PROBE_AUTO && use_staged) {
-            // staged traffic = every byte of the touched kinds; gather traffic ~ one 32 B sector per
-            // tested location (~3 on average for an absent key, k for a present one) + the descriptor.
-            uint64_t staged_bytes = 0;
-            for (int k = 0; k < 3; ++k)
-                if (q->kind_mask & (1u << k)) staged_bytes += c->staged_kind_bytes[k];
-            const uint64_t gather_bytes = static_cast<uint64_t>(c->n_staged) * q->n_keys * (4 * 32 + 32);
-            use_staged = staged_bytes <= gather_bytes;
-        }
+        if (path == BSG_PROBE_AUTO && use_staged) use_staged = auto_uses_staged(c, variant, q->kind_mask, q->n_keys);
         // deferred hashing (bsg_probe path): fused into the two-phase staged kernel when that kernel is
         // the only consumer of the hashes, else a hash_keys_kernel launch now
-        const bool fuse = !q->hashed && use_staged && c->n_gather == 0 && ctx->probe_variant != 0;
+        const bool fuse = !q->hashed && use_staged && c->n_gather == 0 && variant != 0;
         if (!q->hashed && !fuse) {
             CUDA_TRY(launch_hash_keys(q->k_keys, q->k_key_off, q->n_keys, q->d_hashes, s));
             q->hashed = true;
@@ -1754,7 +1838,7 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         }
         if (use_staged) {
             ProbeStagedPlan plan;
-            plan.variant = ctx->probe_variant;
+            plan.variant = variant;
             plan.relax_sleep_ns = static_cast<uint32_t>(ctx->relax_sleep_ns);
             plan.pdl = ctx->pdl;
             plan.fuse_keys = nullptr;
@@ -1841,14 +1925,14 @@ extern "C" int bsg_query_run(bsg_ctx* ctx, const bsg_corpus* corpus, bsg_query* 
 }
 
 // D2H through the query's pinned block (true async DMA), then memcpy into the caller's buffers.
-static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask, cudaStream_t s,
-                              std::chrono::steady_clock::time_point* t_synced = nullptr) {
+static int query_fetch_pinned(bsg_ctx* ctx, bsg_query* q, uint64_t n_units, uint64_t* out_matrix, uint64_t* out_mask,
+                              cudaStream_t s, std::chrono::steady_clock::time_point* t_synced = nullptr) {
     const size_t mbytes = (out_matrix && q->n_keys) ? n_units * q->row_words32 * 4 : 0;
     const size_t kbytes = out_mask ? ((n_units + 63) / 64) * 8 : 0;
     if (q->k_matrix != q->d_matrix32) {  // zero copy: the rows are already in pinned host memory
-        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(stream_wait(ctx, s));
         if (t_synced) *t_synced = std::chrono::steady_clock::now();
-        if (mbytes) memcpy(out_matrix, q->h_out, mbytes);
+        if (mbytes && !q->direct_out) memcpy(out_matrix, q->h_out, mbytes);
         return BSG_OK;
     }
     const size_t need = mbytes + kbytes + 16;
@@ -1865,7 +1949,7 @@ static int query_fetch_pinned(bsg_query* q, uint64_t n_units, uint64_t* out_matr
     }
     if (mbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin, q->d_matrix32, mbytes, cudaMemcpyDeviceToHost, s));
     if (kbytes) CUDA_TRY(cudaMemcpyAsync(q->h_pin + mbytes, q->d_mask32, kbytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(stream_wait(ctx, s));
     if (t_synced) *t_synced = std::chrono::steady_clock::now();
     if (mbytes) memcpy(out_matrix, q->h_pin, mbytes);
     if (kbytes) memcpy(out_mask, q->h_pin + mbytes, kbytes);
@@ -1909,15 +1993,24 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
     // instead hold the SMs at PCIe speed, so large outputs keep the copy-engine path (D2H after the kernel)
     constexpr uint64_t kZeroCopyMaxBytes = 8ull << 20;
     if (rc == BSG_OK && ctx->zero_copy && out_matrix && !out_mask && n_keys && corpus->n_units &&
-        corpus->n_units * q->row_words32 * 4ull <= kZeroCopyMaxBytes)
-        rc = query_use_host_matrix(q);
+        corpus->n_units * q->row_words32 * 4ull <= kZeroCopyMaxBytes) {
+        // a caller buffer from bsg_host_alloc takes the rows directly (the staged kernels write every word of a
+        // row, pad included; units on the gather kernel do not, so those corpora keep the staging block)
+        uint32_t* direct = nullptr;
+        const int v = staged_variant_for(ctx, corpus);
+        const bool all_staged = v == 6 ? (corpus->t_gather == 0 && corpus->t_staged > 0) : (corpus->n_gather == 0 && corpus->n_staged > 0);
+        if (all_staged && v != 0 && auto_uses_staged(corpus, v, q->kind_mask, n_keys))
+            direct = host_buf_device_ptr(ctx, out_matrix, corpus->n_units * q->row_words32 * 4ull);
+        if (direct) { q->k_matrix = direct; q->direct_out = true; }
+        else rc = query_use_host_matrix(q);
+    }
     const auto t1 = clk::now();
     // the mask kernel is skipped when the caller wants no mask
     const int path = BSG_PROBE_AUTO | (out_mask ? 0 : BSG_RUN_MATRIX_ONLY);
     if (rc == BSG_OK) rc = query_run_on(ctx, corpus, q, path, out_matrix != nullptr, s);
     const auto t2 = clk::now();
     clk::time_point t3 = t2;
-    if (rc == BSG_OK) rc = query_fetch_pinned(q, corpus->n_units, out_matrix, out_mask, s, ctx->timing ? &t3 : nullptr);
+    if (rc == BSG_OK) rc = query_fetch_pinned(ctx, q, corpus->n_units, out_matrix, out_mask, s, ctx->timing ? &t3 : nullptr);
     else cudaStreamSynchronize(s);
     if (ctx->timing) {
         const auto t4 = clk::now();
@@ -1988,7 +2081,7 @@ extern "C" int bsg_probe_hierarchical(bsg_ctx* ctx, const bsg_corpus* files, con
     if (rc == BSG_OK) rc = query_run_on(ctx, blocks, qb, BSG_PROBE_AUTO, 0, s, qf->d_mask32);
     if (rc == BSG_OK && out_file_mask)
         rc = query_fetch_on(qf, files->n_units, nullptr, out_file_mask, s);
-    if (rc == BSG_OK) rc = query_fetch_pinned(qb, blocks->n_units, nullptr, out_block_mask, s);
+    if (rc == BSG_OK) rc = query_fetch_pinned(ctx, qb, blocks->n_units, nullptr, out_block_mask, s);
     else cudaStreamSynchronize(s);
     scratch_put(ctx, qf);
     scratch_put(ctx, qb);
@@ -2140,14 +2233,15 @@ extern "C" int bsg_debug_run_cycle(bsg_ctx* ctx, bsg_corpus* const* corpora, bsg
 // reporting helper: which staged kernel a big-batch probe of this corpus launches, and how the corpus was cut
 extern "C" int bsg_debug_probe_kernel_name(bsg_ctx* ctx, const bsg_corpus* c, char* buf, size_t n) {
     if (!ctx || !c || !buf || n == 0) return fail(BSG_ERR_INVALID, "NULL argument");
-    if (ctx->probe_variant == 6)
+    const int variant = staged_variant_for(ctx, c);
+    if (variant == 6)
         snprintf(buf, n, "%s, %s mode, %u item(s) x %u tile(s), <= %u unit(s) and %u data bytes per tile; %u unit(s) on the gather kernel",
                  probe_tiles_shape_name(ctx->tiles_shape), c->t_parts == 1 ? "UNIT" : "KIND", c->t_items, c->t_parts,
                  c->t_units_cap, c->t_data_cap, c->t_gather);
-    else if (ctx->probe_variant == 0)
+    else if (variant == 0)
         snprintf(buf, n, "probe_staged_kernel (one phase)");
     else
-        snprintf(buf, n, "probe_staged2_kernel shape %d", ctx->probe_variant);
+        snprintf(buf, n, "probe_staged2_kernel shape %d (<16,2,3,16,4> by default; one team of 16 B warps when the ring has < 4 stages), %u staged unit(s), %u on the gather kernel", variant, c->n_staged, c->n_gather);
     return BSG_OK;
 }
 

@@ -463,7 +463,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
         // ------------------------------------------------------------ phase B ---
         const uint32_t wb = warp - NA;
         const uint32_t team = wb / T, member = wb % T;
-        const uint32_t out_words = (n_keys + 31) >> 5;
+        // every word of the row that belongs to this pass, pad word included (A warps without keys wrote zeros)
+        const uint32_t out_words = min(32u, row_words32 - (key_base >> 5));
         uint32_t* out_base = matrix32 + (key_base >> 5);
         s = team;
         while (s >= S) { s -= S; ph ^= 1u; }

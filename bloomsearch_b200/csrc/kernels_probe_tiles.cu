@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
     }
     warp_kinds = __reduce_or_sync(0xffffffffu, warp_kinds);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t out_words = (a.n_keys + 31) >> 5;
+    // every word of the row that belongs to this pass, pad word included (the smem rows are zero there)
+    const uint32_t out_words = min(32u, a.row_words32 - (a.key_base >> 5));
     uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
 
     uint32_t s = 0, ph = 0;

@@ -151,6 +151,24 @@ class Context:
         N.check(L.bsg_debug_memcpy_d2h(self._h, N.ptr(out), C.c_void_p(dev_ptr), int(n_words) * 8))
         return out[:int(n_words)]
 
+    def host_alloc(self, shape, dtype=np.uint64) -> np.ndarray:
+        """A numpy array over pinned, device-mapped host memory (bsg_host_alloc): pass it as out_matrix and the
+        probe kernel writes the rows straight into it.  Free with host_free(array)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        N.check(N.lib().bsg_host_alloc(self._h, n, C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        arr.flags.writeable = True
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = getattr(self, "_host_ptrs", {}).pop(arr.ctypes.data, None)
+        if p is not None:
+            N.check(N.lib().bsg_host_free(self._h, C.c_void_p(p)))
+
     def comm_info(self) -> dict:
         r, w, p, b = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
         N.check(N.lib().bsg_comm_info(self._h, C.byref(r), C.byref(w), C.byref(p), C.byref(b)))
@@ -345,9 +363,12 @@ class Corpus:
         return cls(ctx, desc, words)
 
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):   # a cache-owned corpus is released, not freed
             N.lib().bsg_corpus_free(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
+
+    def device_bytes(self) -> int:
+        return N.lib().bsg_corpus_device_bytes(self._h)
 
     def __del__(self):
         try:
@@ -393,6 +414,71 @@ class Corpus:
         cq = compile_bloom_query(query)
         _, mask = self.probe(cq.keys, cq.kinds, cq.prog, want_matrix=False)
         return unpack_mask(mask, self.n_units)
+
+
+class FilterCache:
+    """Resident filter cache (bsg_cache): corpora keyed by file id under a byte budget, LRU eviction, pinned
+    while in use, invalidated when a merge replaces the file or it is tombstoned (merge.go:529-536)."""
+
+    def __init__(self, ctx: Context, budget_bytes: int):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        N.check(N.lib().bsg_cache_create(ctx.handle, int(budget_bytes), C.byref(self._h)))
+
+    def _borrow(self, handle) -> "Corpus":
+        cp = Corpus.__new__(Corpus)
+        cp.ctx = self.ctx
+        cp._h = C.c_void_p(handle)
+        cp.n_units = N.lib().bsg_corpus_units(cp._h)
+        cp._borrowed = True
+        return cp
+
+    def acquire(self, file_id: int) -> Optional["Corpus"]:
+        out = C.c_void_p()
+        N.check(N.lib().bsg_cache_acquire(self._h, int(file_id), C.byref(out)))
+        return self._borrow(out.value) if out.value else None
+
+    def insert_sections(self, file_id: int, sections: np.ndarray, sec_off: np.ndarray, verify_crc: bool = True):
+        sections = np.ascontiguousarray(sections, dtype=np.uint8)
+        sec_off = np.ascontiguousarray(sec_off, dtype=np.uint64)
+        n_units = len(sec_off) - 1
+        status = np.zeros(max(n_units, 1), dtype=np.int32)
+        n_bad, out = C.c_uint64(), C.c_void_p()
+        N.check(N.lib().bsg_cache_insert_sections(self._h, int(file_id), N.ptr(sections) if len(sections) else None,
+                                                  N.ptr(sec_off), n_units, 1 if verify_crc else 0, N.ptr(status),
+                                                  C.byref(n_bad), C.byref(out)))
+        return self._borrow(out.value), status[:n_units]
+
+    def insert(self, file_id: int, corpus: "Corpus") -> "Corpus":
+        """Hands an already loaded corpus (e.g. a file-level one) to the cache; `corpus` must not be used afterwards."""
+        out = C.c_void_p()
+        N.check(N.lib().bsg_cache_insert(self._h, int(file_id), corpus._h, C.byref(out)))
+        corpus._h = C.c_void_p()
+        return self._borrow(out.value)
+
+    def release(self, corpus: "Corpus"):
+        if corpus._h:
+            N.lib().bsg_cache_release(self._h, corpus._h)
+            corpus._h = C.c_void_p()
+
+    def invalidate(self, file_id: int):
+        N.check(N.lib().bsg_cache_invalidate(self._h, int(file_id)))
+
+    def stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(6)]
+        N.check(N.lib().bsg_cache_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("used_bytes", "entries", "hits", "misses", "evictions", "invalidations"), (x.value for x in v)))
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_cache_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def probe_hierarchical(files: Corpus, blocks: Corpus, query: Optional[BloomQuery]):

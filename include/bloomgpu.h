@@ -55,6 +55,7 @@ typedef struct bsg_ctx bsg_ctx;
 typedef struct bsg_corpus bsg_corpus;
 typedef struct bsg_query bsg_query;
 typedef struct bsg_keyset bsg_keyset;
+typedef struct bsg_cache bsg_cache;
 
 /* One bloom filter: m bits, k hash functions, words start at word_off (in uint64
  * units) inside the accompanying words array.  m == 0 means "filter absent"
@@ -93,6 +94,12 @@ int bsg_synchronize(bsg_ctx *ctx);
 /* Device properties the host needs for planning / reporting. */
 int bsg_device_info(bsg_ctx *ctx, int *sm_count, size_t *smem_per_block_optin,
                     size_t *total_mem, int *cc_major, int *cc_minor);
+
+/* Pinned, device-mapped host memory for RESULT buffers (optional).  When out_matrix of bsg_probe() lies in
+ * such a buffer the probe kernel writes the rows straight into it and the call ends without a staging
+ * copy; any other host memory (e.g. the Go heap) works too, through a pinned staging block.  Zero-filled. */
+int bsg_host_alloc(bsg_ctx *ctx, size_t bytes, void **out);
+int bsg_host_free(bsg_ctx *ctx, void *ptr);
 
 /* ---- sizing helper (bloom.EstimateParameters + New's clamp) -------------- */
 void bsg_estimate(uint64_t n, double fpr, uint64_t *m, uint64_t *k);
@@ -189,8 +196,33 @@ uint64_t bsg_corpus_units(const bsg_corpus *corpus);
 /* Bytes of filter bitsets resident in HBM (Σ_b S_b of SURVEY.md §8d), optionally
  * only for the kinds in kind_mask (bit kind). */
 uint64_t bsg_corpus_bitset_bytes(const bsg_corpus *corpus, uint32_t kind_mask);
+/* HBM held by the corpus (bitsets + descriptor tables): the resident cache's unit of account. */
+uint64_t bsg_corpus_device_bytes(const bsg_corpus *corpus);
 /* Copy unit u's descriptors (3) and words back out (tests / round trips). */
 int bsg_corpus_unit_desc(const bsg_corpus *corpus, uint64_t unit, bsg_filter_desc out_desc[3]);
+
+/* ---- resident filter cache -------------------------------- *
+ * The reference decodes a file's filters per query and drops them (query_exec.go:399-412, :572-615); the
+ * GPU path keeps them in HBM.  Corpora are keyed by a caller-chosen file id (one id space per cache: use
+ * one cache for file-level corpora and one for block-level corpora, or distinct ids), held under a byte
+ * budget with least-recently-used eviction, and pinned while in use:
+ *   acquire   hit: pins and returns the corpus; miss: *out = NULL (the caller reads the sections and inserts)
+ *   insert*   takes ownership of / loads a corpus for file_id (replacing an older one), evicts unpinned
+ *             entries down to the budget, returns it pinned when out != NULL
+ *   release   unpins; an entry that was invalidated or evicted while pinned is freed on its last release
+ *   invalidate  the file was replaced by a merge (merge.go:529-536) or tombstoned: never served again
+ * Thread-safe.  A corpus obtained here must not be passed to bsg_corpus_free. */
+int bsg_cache_create(bsg_ctx *ctx, uint64_t budget_bytes, bsg_cache **out);
+void bsg_cache_destroy(bsg_cache *cache);
+int bsg_cache_acquire(bsg_cache *cache, uint64_t file_id, const bsg_corpus **out);
+int bsg_cache_insert(bsg_cache *cache, uint64_t file_id, bsg_corpus *corpus, const bsg_corpus **out);
+int bsg_cache_insert_sections(bsg_cache *cache, uint64_t file_id, const uint8_t *sections, const uint64_t *sec_off,
+                              uint64_t n_units, int verify_crc, int32_t *unit_status, uint64_t *n_bad,
+                              const bsg_corpus **out);
+void bsg_cache_release(bsg_cache *cache, const bsg_corpus *corpus);
+int bsg_cache_invalidate(bsg_cache *cache, uint64_t file_id);
+int bsg_cache_stats(bsg_cache *cache, uint64_t *used_bytes, uint64_t *entries, uint64_t *hits, uint64_t *misses,
+                    uint64_t *evictions, uint64_t *invalidations);
 
 /* ---- K4/K5: probe ----------------------------------------------------------- *
  * Tests n_keys keys against every unit of the corpus.

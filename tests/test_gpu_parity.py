@@ -978,3 +978,80 @@ def test_probe_units_beyond_the_old_75kb_limit(ctx, unit_kb):
         keys.append(b"absent%d" % i)
         kinds.append(i % 3)
     _probe_case(ctx, desc, words, keys, kinds)
+
+
+# ------------------------------------------------ resident filter cache (§8 f.4) ---
+def test_filter_cache_load_query_invalidate_evict(ctx):
+    """load -> query -> merge-invalidate -> query, LRU eviction under a byte budget, pins that outlive an
+    invalidation; every answer equals the oracle's for the file's CURRENT filters."""
+    rng = random.Random(88)
+
+    def make_file(seed, n_units):
+        r = random.Random(seed)
+        uk = [(rand_keys(r, 4, 2, 9), rand_keys(r, 80, 1, 14), rand_keys(r, 80, 4, 25)) for _ in range(n_units)]
+        d, w = oracle_units(uk, 0.001)
+        sec, so = cref.encode_sections(d, w, n_units)
+        return uk, d, w, sec, so
+    files = {fid: make_file(1000 + fid, 6) for fid in range(5)}
+    one = bs.Corpus.from_sections(ctx, files[0][3], files[0][4])[0]
+    per_file = one.device_bytes()
+    one.close()
+    cache = bs.FilterCache(ctx, int(per_file * 3.5))     # room for three files
+
+    def query_file(fid, version=None):
+        uk, d, w, sec, so = version or files[fid]
+        cp = cache.acquire(fid)
+        hit = cp is not None
+        if cp is None:                                    # miss: the host reads the sections and inserts them
+            cp, status = cache.insert_sections(fid, sec, so)
+            assert not status.any()
+        key = uk[2][1][3]
+        q = bs.BloomQuery(bs.Or(bs.Token(key), bs.Token(b"definitely-absent")))
+        got = cp.evaluate_bloom_filters(q)
+        cache.release(cp)
+        want, errs = cref.probe_sections(sec, so, to_oracle_tuple(q.Expression))
+        assert errs == 0 and np.array_equal(got, bs.unpack_mask(want, len(so) - 1)) and got[2]
+        return hit
+    assert [query_file(f) for f in (0, 1, 2)] == [False, False, False]
+    assert [query_file(f) for f in (0, 1, 2)] == [True, True, True]
+    st = cache.stats()
+    assert st["entries"] == 3 and st["hits"] == 3 and st["misses"] == 3 and st["evictions"] == 0
+    assert query_file(3) is False                         # over budget: the least recently used file (0) goes
+    st = cache.stats()
+    assert st["entries"] == 3 and st["evictions"] == 1 and st["used_bytes"] <= per_file * 3.5
+    assert query_file(1) is True and query_file(0) is False
+    # a merge rewrites file 1 (new filters under the same id): the old corpus must never be served again, but a
+    # query that still holds it may finish
+    held = cache.acquire(1)
+    cache.invalidate(1)
+    assert cache.acquire(1) is None
+    newer = make_file(2001, 6)
+    assert query_file(1, newer) is False                  # reload: answers come from the NEW filters
+    old_key = files[1][0][2][1][3]
+    got_old = held.evaluate_bloom_filters(bs.BloomQuery(bs.Token(old_key)))
+    assert got_old[2]                                     # the pinned old corpus is still intact
+    cache.release(held)
+    files[1] = newer
+    assert query_file(1) is True
+    assert cache.stats()["invalidations"] == 1
+    cache.close()
+
+
+def test_bsg_probe_into_pinned_caller_buffer(ctx):
+    """out_matrix in a bsg_host_alloc buffer: the kernels write the rows (pad words included) straight into it;
+    reusing the buffer with another key count must leave no stale bits."""
+    rng = random.Random(61)
+    unit_keys = [(rand_keys(rng, 5, 3, 8), rand_keys(rng, 900, 1, 10), rand_keys(rng, 900, 4, 20)) for _ in range(300)]
+    desc, words = oracle_units(unit_keys, 0.001)
+    corpus = bs.Corpus(ctx, desc, words)
+    buf = ctx.host_alloc((300, 16), np.uint64)
+    for n_keys in (1000, 930, 97, 1000):
+        keys, kinds = _mixed_keys(rng, unit_keys, n_keys // 2, n_keys - n_keys // 2)
+        blob, off = N.pack_keys(keys)
+        kinds = np.asarray(kinds, np.uint8)
+        want = cref.probe_matrix(desc, words, 300, blob, off, kinds)
+        out = buf[:, :(n_keys + 63) // 64] if (n_keys + 63) // 64 == 16 else np.zeros((300, (n_keys + 63) // 64), np.uint64)
+        corpus.probe_packed(blob, off, kinds, None, out, None)
+        assert np.array_equal(out, want), f"n_keys {n_keys}"
+    corpus.close()
+    ctx.host_free(buf)
