@@ -742,8 +742,8 @@ static int count_distinct_device(bsg_ctx* ctx, const uint8_t* d_keys, const uint
     if (e == cudaSuccess && group_parent) e = cudaMemsetAsync(d_pc.p, 0, std::max<uint32_t>(n_parents, 1) * 8, s);
     if (e == cudaSuccess && group_parent) e = cudaMemcpyAsync(d_gp.p, group_parent, n_groups * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess)
-        e = launch_count_distinct(d_keys, d_off, n_keys, d_gb, n_groups, group_parent ? d_gp.p : nullptr, d_em.p, d_gc.p,
-                                  group_parent ? d_pc.p : nullptr, s);
+        e = launch_count_distinct(d_keys, d_off, n_keys, d_gb, n_groups, group_parent ? d_gp.p : nullptr, n_parents, d_em.p,
+                                  d_gc.p, group_parent ? d_pc.p : nullptr, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_group_counts, d_gc.p, n_groups * 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && group_parent)
         e = cudaMemcpyAsync(out_parent_counts, d_pc.p, n_parents * 8, cudaMemcpyDeviceToHost, s);

@@ -203,7 +203,7 @@ cudaError_t launch_build_ft(const uint8_t* d_strings, const uint64_t* d_str_off,
 
 cudaError_t launch_count_distinct(const uint8_t* d_keys, const uint64_t* d_key_off, uint64_t n_keys,
                                   const uint64_t* d_group_begin, uint32_t n_groups, const uint32_t* d_group_parent,
-                                  void* d_emissions, unsigned long long* d_group_counts,
+                                  uint32_t n_parents, void* d_scratch, unsigned long long* d_group_counts,
                                   unsigned long long* d_parent_counts, cudaStream_t s);
 size_t count_distinct_scratch_bytes(uint64_t n_keys);
 

@@ -172,9 +172,11 @@ static void test_gpu(const std::string& golden_section_hex) {
     BloomQuery hit{FieldToken("service", "auth")}, miss{FieldToken("service", "billing")};
     EXPECT(c3->evaluateBloomFilters(&hit)[0]);
     EXPECT(!c3->evaluateBloomFilters(&miss)[0]);
-    sec[sec.size() / 2] ^= 0x08;  // corrupt: unit fails open, status says why (query_exec.go:580-590)
+    // corrupt: the block is an error, never a candidate (query_exec.go:580-590 records the error and continues
+    // without scanning the block); status says why
+    sec[sec.size() / 2] ^= 0x08;
     auto c4 = Corpus::fromSections(ctx, sec, {0, sec.size()}, true, &status);
-    EXPECT(status[0] == -2 && c4->evaluateBloomFilters(&miss)[0]);
+    EXPECT(status[0] == -2 && !c4->evaluateBloomFilters(&miss)[0] && !c4->evaluateBloomFilters(&hit)[0]);
 
     // ---- cross-language golden: same entries as tests/golden (oracle-generated) section ----
     BloomEntrySets g1, g2;

@@ -55,6 +55,9 @@ const (
 	OpFalse = C.BSG_OP_FALSE
 )
 
+// check turns a status into an error.  bsg_last_error() is a THREAD-LOCAL detail string, and a goroutine may
+// be rescheduled onto another OS thread between two cgo calls, so every entry point below pins its goroutine
+// with pin() for the duration of "call + check".
 func check(rc C.int) error {
 	if rc == C.BSG_OK {
 		return nil
@@ -62,10 +65,16 @@ func check(rc C.int) error {
 	return fmt.Errorf("bloomgpu: %s: %s", C.GoString(C.bsg_strerror(rc)), C.GoString(C.bsg_last_error()))
 }
 
+func pin() func() {
+	runtime.LockOSThread()
+	return runtime.UnlockOSThread
+}
+
 // Context owns one GPU (bsg_ctx).  Safe for concurrent use by many goroutines.
 type Context struct{ h *C.bsg_ctx }
 
 func NewContext(device int) (*Context, error) {
+	defer pin()()
 	var h *C.bsg_ctx
 	if err := check(C.bsg_create(C.int(device), &h)); err != nil {
 		return nil, err
@@ -131,10 +140,11 @@ type Corpus struct {
 
 // LoadSections uploads raw filter sections exactly as they sit in a file's block filter
 // region (file_format.go:343-385); framing, CRC32C and big-endian decode run on the GPU.
-// status[u] != 0 marks a section that failed to parse: that unit keeps no filters and is
-// never disqualified, which is the reference's per-block error isolation
-// (query_exec.go:580-590) — the caller still records the error for the block.
+// status[u] != 0 marks a section that failed to parse.  As in the reference (query_exec.go:580-590: the
+// error is recorded, the loop continues, the block is NOT scanned) such a unit never survives a probe —
+// its mask bit is always 0 — and the caller records status[u] as that block's error.
 func (c *Context) LoadSections(sections []byte, secOff []uint64, verifyCRC bool) (*Corpus, []int32, error) {
+	defer pin()()
 	n := uint64(len(secOff) - 1)
 	status := make([]int32, n+1)
 	var h *C.bsg_corpus
@@ -159,6 +169,7 @@ func (c *Context) LoadSections(sections []byte, secOff []uint64, verifyCRC bool)
 
 // Load uploads already-decoded filters (desc[3*u+kind], native-endian words).
 func (c *Context) Load(desc []FilterDesc, words []uint64) (*Corpus, error) {
+	defer pin()()
 	if len(desc)%3 != 0 {
 		return nil, errors.New("bloomgpu: desc must hold 3 slots per unit")
 	}
@@ -191,6 +202,7 @@ func (cp *Corpus) Close() {
 // survives, query_exec.go:81-83) folds the leaf bits into the candidate mask.
 // mask bit u = unit u survives; matrix (optional) row u, bit q = TestString(key q) on unit u.
 func (c *Context) Probe(cp *Corpus, keys PackedKeys, kinds []Kind, prog []Op, wantMatrix bool) (mask []uint64, matrix []uint64, err error) {
+	defer pin()()
 	n := uint32(len(keys.Off) - 1)
 	mask = make([]uint64, (cp.Units+63)/64+1)
 	var mp *C.uint64_t
@@ -216,6 +228,7 @@ func (c *Context) Probe(cp *Corpus, keys PackedKeys, kinds []Kind, prog []Op, wa
 // ProbeHierarchical then runs both pruning stages of Query (query_exec.go:399-406 and :572-615)
 // in one call, compacting the surviving blocks on the device between them.
 func (c *Context) SetParents(cp *Corpus, parent []uint32, nParentUnits uint64) error {
+	defer pin()()
 	if len(parent) == 0 {
 		return nil
 	}
@@ -224,6 +237,7 @@ func (c *Context) SetParents(cp *Corpus, parent []uint32, nParentUnits uint64) e
 }
 
 func (c *Context) ProbeHierarchical(files, blocks *Corpus, keys PackedKeys, kinds []Kind, prog []Op) (fileMask, blockMask []uint64, err error) {
+	defer pin()()
 	n := uint32(len(keys.Off) - 1)
 	fileMask = make([]uint64, (files.Units+63)/64+1)
 	blockMask = make([]uint64, (blocks.Units+63)/64+1)
@@ -246,6 +260,7 @@ func (c *Context) ProbeHierarchical(files, blocks *Corpus, keys PackedKeys, kind
 // per parent union of emissions that may repeat — the counts the maps of bloomEntrySets provide
 // (ingest.go:24-45,105-123), i.e. the n that sizes each filter (ingest.go:139-140).
 func (c *Context) CountDistinct(keys PackedKeys, groupBegin []uint64, groupParent []uint32, nParents int) (groups, parents []uint64, err error) {
+	defer pin()()
 	nGroups := len(groupBegin) - 1
 	groups = make([]uint64, nGroups+1)
 	if nGroups <= 0 {
@@ -291,4 +306,89 @@ func (c *Context) BuildFieldTokens(strings PackedKeys, pairPath, pairToken []uin
 		C.uint32_t(len(desc)), (*C.uint64_t)(unsafe.Pointer(&out[0])), C.uint64_t(nWords))
 	runtime.KeepAlive(strings)
 	return out[:nWords], check(rc)
+}
+
+// Cache is the resident filter cache (bsg_cache): corpora keyed by file id under a byte budget with
+// least-recently-used eviction, pinned while a query uses them, invalidated when a merge replaces the
+// file (merge.go:529-536) or it is tombstoned.  The reference decodes filters per query and drops them
+// (query_exec.go:399-412, :572-615); this is what lets the GPU path keep them in HBM instead.
+type Cache struct {
+	h *C.bsg_cache
+	c *Context
+}
+
+func (c *Context) NewCache(budgetBytes uint64) (*Cache, error) {
+	defer pin()()
+	var h *C.bsg_cache
+	if err := check(C.bsg_cache_create(c.h, C.uint64_t(budgetBytes), &h)); err != nil {
+		return nil, err
+	}
+	return &Cache{h, c}, nil
+}
+
+func (k *Cache) Close() {
+	if k.h != nil {
+		C.bsg_cache_destroy(k.h)
+		k.h = nil
+	}
+}
+
+// Acquire returns the pinned corpus of fileID, or nil on a miss.  Release it when the query is done with it;
+// never Close it.
+func (k *Cache) Acquire(fileID uint64) (*Corpus, error) {
+	defer pin()()
+	var h *C.bsg_corpus
+	if err := check(C.bsg_cache_acquire(k.h, C.uint64_t(fileID), &h)); err != nil || h == nil {
+		return nil, err
+	}
+	return &Corpus{h, uint64(C.bsg_corpus_units(h))}, nil
+}
+
+// InsertSections loads the file's raw filter sections (as LoadSections) into the cache and returns the pinned corpus.
+func (k *Cache) InsertSections(fileID uint64, sections []byte, secOff []uint64, verifyCRC bool) (*Corpus, []int32, error) {
+	defer pin()()
+	n := uint64(len(secOff) - 1)
+	status := make([]int32, n+1)
+	var h *C.bsg_corpus
+	var bad C.uint64_t
+	v := C.int(0)
+	if verifyCRC {
+		v = 1
+	}
+	var sp *C.uint8_t
+	if len(sections) > 0 {
+		sp = (*C.uint8_t)(unsafe.Pointer(&sections[0]))
+	}
+	rc := C.bsg_cache_insert_sections(k.h, C.uint64_t(fileID), sp, (*C.uint64_t)(unsafe.Pointer(&secOff[0])), C.uint64_t(n), v,
+		(*C.int32_t)(unsafe.Pointer(&status[0])), &bad, &h)
+	if err := check(rc); err != nil {
+		return nil, nil, err
+	}
+	return &Corpus{h, n}, status[:n], nil
+}
+
+// Insert hands an already loaded corpus (e.g. the file-level filters of one MetaStore generation) to the cache.
+func (k *Cache) Insert(id uint64, cp *Corpus) (*Corpus, error) {
+	defer pin()()
+	var h *C.bsg_corpus
+	if err := check(C.bsg_cache_insert(k.h, C.uint64_t(id), cp.h, &h)); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(cp, nil)
+	cp.h = nil // owned by the cache now
+	return &Corpus{h, uint64(C.bsg_corpus_units(h))}, nil
+}
+
+func (k *Cache) Release(cp *Corpus) {
+	if cp != nil && cp.h != nil {
+		C.bsg_cache_release(k.h, cp.h)
+		cp.h = nil
+	}
+}
+
+// Invalidate: the file was replaced by a merge or tombstoned; its filters are never served again (a query
+// that still holds them finishes on the old copy, which is freed on its last Release).
+func (k *Cache) Invalidate(fileID uint64) error {
+	defer pin()()
+	return check(C.bsg_cache_invalidate(k.h, C.uint64_t(fileID)))
 }

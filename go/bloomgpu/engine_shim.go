@@ -9,6 +9,7 @@
 package bloomsearch
 
 import (
+	"sync"
 	"github.com/bits-and-blooms/bloom/v3"
 
 	"github.com/danthegoodman1/bloomsearch/bloomgpu"
@@ -65,17 +66,46 @@ func buildFlushFiltersGPU(blocks []*bloomEntrySets, file *bloomEntrySets, fpr fl
 }
 
 // ---------------------------------------------------------------------------
-// PROBE — replaces the per-block loop of evaluateBlockFilters (query_exec.go:572-615):
-// the ≤4 MiB chunks the blockFilterCursor already reads (file_format.go:618-662) are
-// handed to the GPU as raw sections; parseFilterSection + evaluateBloomFilters for every
-// block of the file become one LoadSections + one Probe.
+// PROBE — replaces the per-block loop of evaluateBlockFilters (query_exec.go:572-615) and the file-level
+// test of the file stage (query_exec.go:399-406).  The reference decodes every filter per query and drops
+// it again; here both levels stay RESIDENT in HBM in two caches:
+//
+//	blockCache  file pointer id -> the file's block filters (loaded from the raw <= 4 MiB chunks the
+//	            blockFilterCursor already reads, file_format.go:618-662; parse + CRC + decode on the GPU)
+//	fileCache   MetaStore generation -> the file-level filters of every current file as one corpus
+//
+// A merge commit (merge.go:529-536: MetaStore.Update adds the merged file and tombstones its sources) and
+// DataStore.TombstoneFile call InvalidateFile for every retired file id and bump the generation.
 // ---------------------------------------------------------------------------
-func evaluateBlockFiltersGPU(sections []byte, secOff []uint64, q *BloomQuery) (keep []bool, perBlockErr []int32, err error) {
-	corpus, status, err := gpu.LoadSections(sections, secOff, true)
+var (
+	blockCache *bloomgpu.Cache // gpu.NewCache(budget) at engine start
+	fileCache  *bloomgpu.Cache
+	blockErrMu sync.Mutex
+	blockErr   = map[uint64][]int32{} // per-block parse status of the cached files (query_exec.go:580-590)
+)
+
+// evaluateBlockFiltersGPU: blocks of one file.  readSections is only called on a cache miss.
+// keep[u] = block u is a candidate; perBlockErr[u] != 0 = its filter section failed to parse: the caller records
+// the error for that block and does NOT scan it (keep[u] is false for such a block, as in the reference).
+func evaluateBlockFiltersGPU(fileID uint64, readSections func() ([]byte, []uint64, error), q *BloomQuery) (keep []bool, perBlockErr []int32, err error) {
+	corpus, err := blockCache.Acquire(fileID)
 	if err != nil {
 		return nil, nil, err
 	}
-	defer corpus.Close()
+	if corpus == nil { // miss: one read of the filter region, one upload; later queries of this file skip both
+		sections, secOff, rerr := readSections()
+		if rerr != nil {
+			return nil, nil, rerr
+		}
+		var status []int32
+		if corpus, status, err = blockCache.InsertSections(fileID, sections, secOff, true); err != nil {
+			return nil, nil, err
+		}
+		blockErrMu.Lock()
+		blockErr[fileID] = status
+		blockErrMu.Unlock()
+	}
+	defer blockCache.Release(corpus)
 	keys, kinds, prog := compileBloomQuery(q) // postfix lowering, see bloomsearch_b200/query.py:compile_bloom_query
 	mask, _, err := gpu.Probe(corpus, bloomgpu.Pack(keys), kinds, prog, false)
 	if err != nil {
@@ -85,7 +115,50 @@ func evaluateBlockFiltersGPU(sections []byte, secOff []uint64, q *BloomQuery) (k
 	for u := range keep {
 		keep[u] = mask[u/64]>>(uint(u)%64)&1 == 1 // BloomFilterSkipped = !keep[u] (query_exec.go:599-606)
 	}
-	return keep, status, nil
+	blockErrMu.Lock()
+	perBlockErr = blockErr[fileID]
+	blockErrMu.Unlock()
+	return keep, perBlockErr, nil
+}
+
+// evaluateFileFiltersGPU: the file stage's bloom test for every candidate file of one MetaStore generation in
+// one probe.  loadFiles is only called when that generation's file-level corpus is not resident yet.
+func evaluateFileFiltersGPU(generation uint64, loadFiles func() (desc []bloomgpu.FilterDesc, words []uint64), q *BloomQuery) ([]bool, error) {
+	corpus, err := fileCache.Acquire(generation)
+	if err != nil {
+		return nil, err
+	}
+	if corpus == nil {
+		desc, words := loadFiles()
+		fresh, lerr := gpu.Load(desc, words)
+		if lerr != nil {
+			return nil, lerr
+		}
+		if corpus, err = fileCache.Insert(generation, fresh); err != nil {
+			return nil, err
+		}
+	}
+	defer fileCache.Release(corpus)
+	keys, kinds, prog := compileBloomQuery(q)
+	mask, _, err := gpu.Probe(corpus, bloomgpu.Pack(keys), kinds, prog, false)
+	if err != nil {
+		return nil, err
+	}
+	keep := make([]bool, corpus.Units)
+	for u := range keep {
+		keep[u] = mask[u/64]>>(uint(u)%64)&1 == 1
+	}
+	return keep, nil
+}
+
+// InvalidateFile is called from the merge commit and from TombstoneFile for every retired file, with the
+// generation the file-level corpus was built for.
+func InvalidateFile(fileID, oldGeneration uint64) {
+	_ = blockCache.Invalidate(fileID)
+	_ = fileCache.Invalidate(oldGeneration)
+	blockErrMu.Lock()
+	delete(blockErr, fileID)
+	blockErrMu.Unlock()
 }
 
 // compileBloomQuery lowers a BloomExpression tree (query.go:505-509) to distinct leaf keys,

@@ -143,8 +143,10 @@ int bsg_build_fieldtokens(bsg_ctx *ctx, const uint8_t *strings, const uint64_t *
  * keys may repeat inside and across groups.  out_group_counts[g] = number of distinct keys of
  * group g; if group_parent != NULL, out_parent_counts[p] = number of distinct keys of the union
  * of all groups with group_parent[g] == p (the file-level union count, flush.go:221,253).
- * These are the n of NewWithEstimates(max(n,1), fpr) (ingest.go:139-140).  Two keys count as
- * equal when their 256 bits of base hashes agree. */
+ * These are the n of NewWithEstimates(max(n,1), fpr) (ingest.go:139-140).  Exact: emissions are
+ * ordered by (group, 64-bit hash) with a radix sort and neighbours with equal hashes are compared
+ * byte for byte (a hash collision between distinct keys is counted as two keys, and triggers a
+ * second pass ordered by 128 hash bits so that their repeats cannot interleave). */
 int bsg_count_distinct(bsg_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, uint64_t n_keys,
                        const uint64_t *group_begin, uint32_t n_groups, const uint32_t *group_parent,
                        uint32_t n_parents, uint64_t *out_group_counts, uint64_t *out_parent_counts);
