@@ -727,13 +727,19 @@ cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_word
 
 // -------------------------------------------------------------- tree eval ---
 // One thread per unit; evaluation stack is a 64-bit bit-stack (BSG_MAX_STACK).
+constexpr uint32_t kTreeSmemOps = 4096;   // 32 KB of dynamic shared memory (no opt-in needed)
 __global__ void __launch_bounds__(256)
 tree_eval_kernel(const uint32_t* __restrict__ matrix32, uint32_t row_words32, uint64_t n_units,
                  const bsg_expr_op* __restrict__ prog, uint32_t prog_len, uint32_t* __restrict__ mask32,
                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ parent_mask32) {
-    extern __shared__ bsg_expr_op sprog[];
-    for (uint32_t i = threadIdx.x; i < prog_len; i += blockDim.x) sprog[i] = prog[i];
-    __syncthreads();
+    extern __shared__ bsg_expr_op sprog_buf[];
+    // programs up to kTreeSmemOps ops are staged in shared memory, longer ones are read from global (L1/L2 cached)
+    const bsg_expr_op* sprog = prog;
+    if (prog_len <= kTreeSmemOps) {
+        for (uint32_t i = threadIdx.x; i < prog_len; i += blockDim.x) sprog_buf[i] = prog[i];
+        __syncthreads();
+        sprog = sprog_buf;
+    }
     const uint64_t unit = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool alive = false;
     bool parent_alive = true;
@@ -773,7 +779,7 @@ cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, u
     if (n_units == 0) return cudaSuccess;
     const uint64_t n_blocks = (n_units + 255) / 256;
     if (n_blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-    tree_eval_kernel<<<static_cast<uint32_t>(n_blocks), 256, prog_len * sizeof(bsg_expr_op), s>>>(
+    tree_eval_kernel<<<static_cast<uint32_t>(n_blocks), 256, (prog_len <= kTreeSmemOps ? prog_len : 0) * sizeof(bsg_expr_op), s>>>(
         d_matrix32, row_words32, n_units, d_prog, prog_len, d_mask32, d_parent, d_parent_mask32);
     return cudaGetLastError();
 }

@@ -200,12 +200,13 @@ CompiledQuery compileBloomQuery(const BloomQuery* q) {
             case BloomExpressionType::And:
             case BloomExpressionType::Or: {
                 const uint32_t op = e.ExpressionType == BloomExpressionType::And ? BSG_OP_AND : BSG_OP_OR;
-                uint32_t pending = 0;
+                // fold pairwise (child, child, op 2, child, op 2, ...): the stack grows by one per nesting level
+                uint32_t n = 0;
                 for (const auto& c : e.Children) {
                     (*this)(c);
-                    if (++pending == 32) { cq.prog.push_back({op, 32}); pending = 1; }  // stack stays shallow
+                    if (++n >= 2) cq.prog.push_back({op, 2});
                 }
-                cq.prog.push_back({op, pending});
+                if (n <= 1) cq.prog.push_back({op, n});
                 return;
             }
             default: cq.prog.push_back({BSG_OP_FALSE, 0}); return;

@@ -59,7 +59,8 @@ static void test_ast_and_lowering() {
     CompiledQuery cq = compileBloomQuery(&q);
     EXPECT(cq.kinds.size() == 3 && cq.kinds[0] == BSG_KIND_TOKEN && cq.kinds[1] == BSG_KIND_FIELD && cq.kinds[2] == BSG_KIND_FIELDTOKEN);
     EXPECT(std::string(cq.key_bytes.begin(), cq.key_bytes.end()) == "aaf::a");
-    EXPECT(cq.prog.size() == 6 && cq.prog.back().op == BSG_OP_AND && cq.prog.back().arg == 3);
+    // pairwise fold: a, b, x OR 2, [AND 2], a, AND 2  (And of three children -> two AND-2 ops)
+    EXPECT(cq.prog.size() == 7 && cq.prog.back().op == BSG_OP_AND && cq.prog.back().arg == 2);
     EXPECT(!compileBloomQuery(nullptr).has_program);
     BloomQuery nilcond;
     nilcond.Expression = BloomExpression{};  // Condition == nil -> TRUE (query_exec.go:97-100)

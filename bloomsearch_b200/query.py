@@ -227,19 +227,19 @@ def compile_bloom_query(query: Optional[BloomQuery]) -> CompiledQuery:
                 prog.append((N.OP_FALSE, 0))
         elif e.ExpressionType in (BloomExpressionAnd, BloomExpressionOr):
             op = N.OP_AND if e.ExpressionType == BloomExpressionAnd else N.OP_OR
-            # n-ary nodes are folded in chunks so the evaluation stack stays shallow
+            # n-ary nodes are folded pairwise (child, child, op 2, child, op 2, ...): a node never holds more
+            # than two values, so the evaluation stack grows by one per NESTING level, not per child
+            # (BSG_MAX_STACK = 64 then covers trees 63 levels deep, however wide)
             n = len(e.Children)
             if n == 0:
                 prog.append((op, 0))
                 return
-            pending = 0
-            for ch in e.Children:
+            for i, ch in enumerate(e.Children):
                 emit(ch)
-                pending += 1
-                if pending == 32:
-                    prog.append((op, 32))
-                    pending = 1
-            prog.append((op, pending))
+                if i >= 1:
+                    prog.append((op, 2))
+            if n == 1:
+                prog.append((op, 1))
         else:
             prog.append((N.OP_FALSE, 0))
 

@@ -204,15 +204,17 @@ func compileBloomQuery(q *BloomQuery) (keys []string, kinds []bloomgpu.Kind, pro
 			if e.ExpressionType == BloomExpressionOr {
 				op = bloomgpu.OpOr
 			}
-			pending := uint32(0)
+			// fold pairwise (child, child, op 2, child, op 2, ...): the stack grows by one per nesting level,
+			// not per child, so BSG_MAX_STACK = 64 covers any width
 			for i := range e.Children {
 				emit(&e.Children[i])
-				if pending++; pending == 32 { // fold wide nodes: evaluation stack stays <= 64
-					prog = append(prog, bloomgpu.Op{Op: op, Arg: 32})
-					pending = 1
+				if i >= 1 {
+					prog = append(prog, bloomgpu.Op{Op: op, Arg: 2})
 				}
 			}
-			prog = append(prog, bloomgpu.Op{Op: op, Arg: pending})
+			if len(e.Children) <= 1 {
+				prog = append(prog, bloomgpu.Op{Op: op, Arg: uint32(len(e.Children))})
+			}
 		default:
 			prog = append(prog, bloomgpu.Op{Op: bloomgpu.OpFalse})
 		}

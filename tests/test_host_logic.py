@@ -123,6 +123,7 @@ def test_wide_nodes_are_folded_to_bound_stack_depth():
         sp = sp + 1 if op in (N.OP_LEAF, N.OP_TRUE, N.OP_FALSE) else sp - arg + 1
         mx = max(mx, sp)
     assert sp == 1 and mx <= N.MAX_STACK
+
     for hit in (None, 0, 57, 199):
         bits = np.zeros(200, np.uint8)
         if hit is not None:
@@ -155,3 +156,20 @@ def test_mask_and_matrix_unpack():
     assert bits.shape == (2, 70)
     assert list(np.nonzero(bits[0])[0]) == [0, 1, 3] and list(np.nonzero(bits[1])[0]) == [63, 64]
     assert list(bs.unpack_mask(np.array([0b101], dtype=np.uint64), 3)) == [True, False, True]
+    # nested wide nodes: the stack grows by one per nesting level, not per child (pairwise fold)
+    inner = bs.And(*[bs.Token("a%d" % i) for i in range(40)])
+    mid = bs.Or(*([bs.Field("f%d" % i) for i in range(39)] + [inner]))
+    outer = bs.And(*([bs.Token("b%d" % i) for i in range(50)] + [mid]))
+    cq2 = bs.compile_bloom_query(bs.BloomQuery(outer))
+    sp = mx = 0
+    for op, arg in cq2.prog:
+        sp = sp + 1 if op in (N.OP_LEAF, N.OP_TRUE, N.OP_FALSE) else sp - arg + 1
+        mx = max(mx, sp)
+    assert sp == 1 and mx <= 4
+    bits = np.ones(len(cq2.keys), np.uint8)
+    assert cref.eval_postfix(cq2.prog, bits) == 1
+    bits[cq2.keys.index(b"a7")] = 0            # one inner AND leaf false, but the OR's fields are true
+    assert cref.eval_postfix(cq2.prog, bits) == 1
+    bits[:] = 1
+    bits[cq2.keys.index(b"b3")] = 0
+    assert cref.eval_postfix(cq2.prog, bits) == 0
