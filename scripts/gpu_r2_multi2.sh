@@ -1,0 +1,11 @@
+#!/bin/bash
+N=${1:-2}
+mkdir -p gpurun_out
+S=$(date +%s); timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; echo "bench N=$N rc=$? in $(( $(date +%s) - S )) s"; grep -E "Error|error|assert" gpurun_out/r2_bench_${N}gpu.err | head -5
+python - <<PY
+import json
+r=json.load(open('gpurun_out/r2_bench_${N}gpu.json'))
+print('value %.3e e2e %.3e' % (r['value'], r['e2e']['value']), r.get('comm'))
+for k in ('build','config5','config4'):
+    d=r[k]; print(k, {kk: d[kk] for kk in d if kk not in ('workload','roofline','what')})
+PY
