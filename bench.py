@@ -624,8 +624,7 @@ def config5_leg(env, args, peaks, data):
     desc = np.zeros(files_total, dtype=N.DESC_DTYPE)
     desc["m"], desc["k"], desc["word_off"] = mf, kf, np.arange(files_total, dtype=np.uint64) * wf_pad
     n_words = files_total * wf_pad
-    per_file = len(my_blocks) // files_total
-    gf = (np.arange(len(my_blocks), dtype=np.uint32) // per_file).astype(np.uint32)
+    gf = (np.array(my_blocks, dtype=np.int64) // bpf).astype(np.uint32)   # group (block) -> its file's filter
     ks = bs.KeySet(ctx, blob, key_off, group_begin)
     ks.set_filters(gf, None, desc, n_words)
     d_out = ctx.comm_alloc(n_words * 8) if W > 1 else None
