@@ -459,10 +459,20 @@ cudaError_t staged_copy(bsg_ctx* ctx, void* dev, void* host, size_t bytes, bool 
     return cudaSuccess;
 }
 
-// host -> device on stream s for small arrays, staged (and synchronous) for large ones
+bool is_pinned_caller_buffer(bsg_ctx* ctx, const void* p, size_t bytes) {
+    const uint8_t* p8 = static_cast<const uint8_t*>(p);
+    std::lock_guard<std::mutex> lk(ctx->host_mu);
+    for (auto& hb : ctx->host_bufs)
+        if (p8 >= hb.first && p8 + bytes <= hb.first + hb.second) return true;
+    return false;
+}
+
+// host -> device on stream s for small arrays and for pinned caller buffers (bsg_host_alloc: one DMA at PCIe
+// speed), staged through pinned double buffers (and synchronous) for large pageable ones
 cudaError_t upload(bsg_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t s) {
     if (bytes == 0) return cudaSuccess;
-    if (bytes < kStageThreshold) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s);
+    if (bytes < kStageThreshold || is_pinned_caller_buffer(ctx, host, bytes))
+        return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s);
     return staged_copy(ctx, dev, const_cast<void*>(host), bytes, true);
 }
 }  // namespace
