@@ -646,7 +646,7 @@ def test_invalid_arguments_are_rejected_with_codes(ctx):
 
 
 # ------------------------------------------------- committed golden fixtures ---
-def test_gpu_reproduces_committed_golden_fixtures(ctx):
+def test_gpu_reproduces_oracle_pin_fixtures(ctx):
     """tests/golden/bloom_golden.json (oracle-generated, see make_golden.py) and the public
     murmur3 vectors, reproduced by the CUDA path alone: hashes, filter words, WriteTo bytes,
     the encoded section (host codec over GPU-built filters) and its device-side decode."""

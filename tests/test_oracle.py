@@ -66,7 +66,7 @@ def test_crc32c_check_value():
         assert cref.crc32c(d) == py.crc32c(d)
 
 
-def test_golden_fixtures_still_hold():
+def test_oracle_pin_fixtures_still_hold():
     g = json.load(open(os.path.join(GOLDEN, "bloom_golden.json")))
     for e in g["base_hashes"]:
         kb = e["key"].encode("utf-8")
