@@ -173,21 +173,22 @@ __device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) 
     return r;
 }
 
-// Same reduction for m < 2^30, in 32-bit arithmetic only (12 instructions instead of
-// ~35 for the emulated 64x64 multiply-high): with I = inv = floor(2^64/m),
-//   step 1  t = hi32(x) mod m            (32-bit Barrett with hi32(I) = floor(2^32/m))
+// Same reduction for m < 2^30, in 32-bit arithmetic only (9 instructions instead of ~35 for the emulated
+// 64x64 multiply-high): with I = inv = floor(2^64/m) = Ih*2^32 + Il,
+//   step 1  t = hi32(x) mod m            (32-bit Barrett with Ih = floor(2^32/m))
 //   step 2  y = t*2^32 + lo32(x) < m*2^32, so floor(y/m) < 2^32 and
-//           q = t*Ih + hi32(t*Il) + hi32(xl*Ih) is floor(y/m) - {0,1,2,3};
-//           y - q*m < 4m < 2^32 is exact in 32-bit wraparound arithmetic.
-// (proof in DESIGN.md; m == 1 works through inv = 2^64-1.)
+//           q = t*Ih + floor((t*Il + xl*Ih) / 2^32) is floor(y/m) - {0,1,2}  (one 64-bit multiply-add:
+//           IMAD.WIDE x2, no zeroing moves); y - q*m < 3m < 2^32 is exact in 32-bit wraparound arithmetic.
+// (proof in DESIGN.md §5; m == 1 works through inv = 2^64-1.)
 __device__ __forceinline__ uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih, uint32_t il) {
     const uint32_t xh = static_cast<uint32_t>(x >> 32), xl = static_cast<uint32_t>(x);
     const uint32_t nm = 0u - m;
     // conditional subtraction as min(v, v - c): v - c wraps above v exactly when v < c
     uint32_t t = __umulhi(xh, ih) * nm + xh;  // xh - floor-ish(xh/m)*m, in [0, 2m)
     t = min(t, t - m);
-    const uint32_t q = __umulhi(xl, ih) + __umulhi(t, il) + t * ih;
-    uint32_t r = q * nm + xl;                 // y - q*m, in [0, 4m)
+    const uint64_t s = static_cast<uint64_t>(xl) * ih + static_cast<uint64_t>(t) * il;  // < 2^64 (see the proof)
+    const uint32_t q = static_cast<uint32_t>(s >> 32) + t * ih;
+    uint32_t r = q * nm + xl;                 // y - q*m, in [0, 3m)
     r = min(r, r - 2u * m);
     r = min(r, r - m);
     return r;

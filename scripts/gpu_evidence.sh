@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2 evidence on one GPU: ncu --set full of the kernels the bench launches, launch list, sanitizers, bench
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_all.log 2>&1; echo "pytest(all) rc=$?"; tail -4 gpurun_out/r02_pytest_all.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_staged2 -s 6 -c 1 -o gpurun_out/r02_ncu_2b -f python scripts/sweep_tiles.py 2b "BSG_PROBE_VARIANT=7" > gpurun_out/r02_ncu_2b.log 2>&1; echo "ncu 2b rc=$?"; tail -2 gpurun_out/r02_ncu_2b.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_tiles -s 6 -c 1 -o gpurun_out/r02_ncu_2a -f python scripts/sweep_tiles.py 2a "BSG_PROBE_VARIANT=7" > gpurun_out/r02_ncu_2a.log 2>&1; echo "ncu 2a rc=$?"; tail -2 gpurun_out/r02_ncu_2a.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:build_kernel -s 3 -c 1 -o gpurun_out/r02_ncu_build_file -f python scripts/run_build.py 2000 file > gpurun_out/r02_ncu_build_file.log 2>&1; echo "ncu build(file) rc=$?"; tail -2 gpurun_out/r02_ncu_build_file.log
