@@ -90,7 +90,7 @@ struct bsg_ctx {
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
     int probe_variant = 7; // BSG_PROBE_VARIANT: 7 = per corpus (default, see staged_variant_for); 6 = probe_tiles; 0 = probe_staged
                            // (one phase); 1..5 = shapes of probe_staged2
-    int tiles_shape = 1;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
+    int tiles_shape = 5;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
     int tile_bytes = 60000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
@@ -1116,13 +1116,34 @@ uint64_t tiles_cta_smem(const bsg_ctx* ctx) {
 // small units, and lists the units no tile can hold (they take the gather kernel).
 int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
-    // ring budget for a full pass of keys: the fixed part grows with the units per tile (survivor lists, rows)
-    const uint32_t group_cap = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
+    // ring budget for a full pass of keys: the fixed part grows with the units per tile (survivor lists, rows).
+    // The pipelined kernel holds a slot for three iterations after its round A: it wants a ring of >= 5 stages.
+    const bool pipe = probe_tiles_pipelined(ctx->tiles_shape) != 0;
+    const uint32_t group_cap_cfg = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
     const uint64_t cta_smem = tiles_cta_smem(ctx);
-    auto ring_budget = [&](uint32_t units_cap) { return cta_smem - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass); };
-    const uint64_t min_stages = static_cast<uint64_t>(ctx->tile_min_stages);
-    const uint64_t unit_limit = ring_budget(group_cap) / min_stages - tile_header_bytes(group_cap);  // UNIT mode
-    const uint64_t part_limit = ring_budget(1) / 2 - tile_header_bytes(1);                            // KIND mode: >= 2 stages
+    auto ring_budget = [&](uint32_t units_cap) {
+        return cta_smem - (pipe ? tiles_fixed_smem_pipe(units_cap, kProbeMaxKeysPerPass) : tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass));
+    };
+    const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), pipe ? 5 : 1);
+    auto tile_limit = [&](uint32_t g) { return ring_budget(g) / min_stages - tile_header_bytes(g); };
+    // units per tile: the g in 1..cfg that packs the most units of the typical size (more units per tile cost list space)
+    uint32_t group_cap = 1;
+    {
+        uint64_t sum = 0, cnt = 0;
+        for (uint64_t u = 0; u < n_units; ++u) {
+            const uint64_t b = static_cast<uint64_t>(L.utab[u].total) * 8;
+            if (b && b <= tile_limit(1)) { sum += b; ++cnt; }
+        }
+        const uint64_t typical = cnt ? std::max<uint64_t>(sum / cnt, 16) : 16;
+        uint64_t best = 0;
+        for (uint32_t g = 1; g <= group_cap_cfg; ++g) {
+            const uint64_t lim = std::min<uint64_t>(tile_limit(g), static_cast<uint64_t>(ctx->tile_bytes));
+            const uint64_t fit = std::min<uint64_t>(g, lim / typical);
+            if (fit > best) { best = fit; group_cap = g; }
+        }
+    }
+    const uint64_t unit_limit = tile_limit(group_cap);                         // UNIT mode: largest tile (and unit)
+    const uint64_t part_limit = ring_budget(1) / 2 - tile_header_bytes(1);     // KIND mode: >= 2 stages (lock-step kernel)
     auto part_bytes = [&](uint64_t u, int part) -> uint64_t {
         const UnitTab& t = L.utab[u];
         return part == 0 ? (static_cast<uint64_t>(t.nw[0]) + t.nw[1]) * 8 : static_cast<uint64_t>(t.nw[2]) * 8;
@@ -1793,12 +1814,18 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             plan.stage_data_bytes = c->t_data_cap;
             plan.fuse_keys = fuse ? q->k_keys : nullptr;
             plan.fuse_key_off = fuse ? q->k_key_off : nullptr;
-            const uint32_t fixed = tiles_fixed_smem(c->t_units_cap,
-                                                    std::min<uint32_t>(q->n_keys, kProbeMaxKeysPerPass));
+            const uint32_t nk = std::min<uint32_t>(q->n_keys, kProbeMaxKeysPerPass);
             const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
             if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
+            uint32_t fixed = probe_tiles_pipelined(plan.shape) ? tiles_fixed_smem_pipe(c->t_units_cap, nk) : tiles_fixed_smem(c->t_units_cap, nk);
             plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, (tiles_cta_smem(ctx) - fixed) / stage_bytes));
+            if (probe_tiles_pipelined(plan.shape) && plan.n_stages < 4) {
+                // the pipelined kernel needs a ring of >= 4 stages: large tiles take the lock-step kernel
+                plan.shape = 1;
+                fixed = tiles_fixed_smem(c->t_units_cap, nk);
+                plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, (tiles_cta_smem(ctx) - fixed) / stage_bytes));
+            }
             if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: tile does not fit shared memory");
             plan.smem_bytes = fixed + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(

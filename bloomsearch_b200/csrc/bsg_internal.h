@@ -143,6 +143,12 @@ inline uint32_t tiles_fixed_smem(uint32_t units_cap, uint32_t n_keys) {
     const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
     return kTilesPrefixBytes + kTilesSlotInfoBytes + units_cap * 128u + 2u * units_cap * 2u * kProbeMaxKeysPerPass + hash_bytes;
 }
+// probe_pipe_kernel: + unit-id table (8 tiles x 64 B), 8 row buffers, both survivor lists double buffered
+inline uint32_t tiles_fixed_smem_pipe(uint32_t units_cap, uint32_t n_keys) {
+    const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
+    return kTilesPrefixBytes + kTilesSlotInfoBytes + 8u * 64u + 8u * units_cap * 128u +
+           4u * units_cap * 2u * kProbeMaxKeysPerPass + hash_bytes;
+}
 
 struct ProbeTilesPlan {
     int n_stages;
@@ -159,6 +165,7 @@ struct ProbeTilesPlan {
 cudaError_t probe_tiles_configure(int max_smem_optin);
 int probe_tiles_n_shapes();
 int probe_tiles_threads(int shape);        // threads per CTA of a compiled shape; 1024 / threads CTAs share an SM
+int probe_tiles_pipelined(int shape);      // 1: probe_pipe_kernel (rounds software pipelined across tiles; ring of >= 4 stages)
 const char* probe_tiles_shape_name(int shape);
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
                                const uint32_t* d_n_items, const uint64_t* d_words, const uint64_t* d_hashes,

@@ -921,7 +921,7 @@ def _tiles_case(monkeypatch, env, n_units, key_kinds=(0, 1, 2), big=False, n_key
         c2.close()
 
 
-@pytest.mark.parametrize("shape", range(5))
+@pytest.mark.parametrize("shape", range(7))
 def test_probe_tiles_every_shape(shape, monkeypatch):
     _tiles_case(monkeypatch, {"BSG_TILES_SHAPE": shape}, 700)
 
@@ -936,6 +936,12 @@ def test_probe_tiles_every_shape(shape, monkeypatch):
     ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1, "BSG_TILE_MIN_STAGES": 2, "BSG_TILES_SHAPE": 2}, 300),
     ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 1}, 450),
     ({"BSG_PROBE_PDL": 0}, 300),
+    # the pipelined kernel (shapes 5, 6): ring of exactly 4 stages, long rings, KIND mode, one unit per tile
+    ({"BSG_TILES_SHAPE": 5, "BSG_PROBE_STAGES": 4}, 900),
+    ({"BSG_TILES_SHAPE": 5, "BSG_TILE_MODE": 2}, 700),
+    ({"BSG_TILES_SHAPE": 6, "BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 5}, 450),
+    ({"BSG_TILES_SHAPE": 5, "BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1}, 1300),
+    ({"BSG_TILES_SHAPE": 6, "BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 3, "BSG_TILE_BYTES": 9000}, 2000),
 ])
 def test_probe_tiles_modes_groupings_rings(env, n_units, monkeypatch):
     _tiles_case(monkeypatch, env, n_units)
@@ -944,6 +950,7 @@ def test_probe_tiles_modes_groupings_rings(env, n_units, monkeypatch):
 @pytest.mark.parametrize("env,key_kinds", [
     ({"BSG_TILE_MODE": 1}, (1,)), ({"BSG_TILE_MODE": 1}, (0, 2)), ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 5}, (2,)),
     ({"BSG_TILE_MODE": 2}, (1,)), ({"BSG_TILE_MODE": 2}, (2,)), ({"BSG_TILE_MODE": 2}, (0,)), ({"BSG_TILE_MODE": 2}, (0, 2)),
+    ({"BSG_TILE_MODE": 1, "BSG_TILES_SHAPE": 1}, (1,)), ({"BSG_TILE_MODE": 2, "BSG_TILES_SHAPE": 1}, (0, 2)),
 ])
 def test_probe_tiles_masked_fills(env, key_kinds, monkeypatch):
     """A batch that touches only some kinds copies only those filters into the stages."""
