@@ -293,6 +293,10 @@ constexpr uint32_t kStage2QueueOff = kStage2CntOff + 16;                   // 10
 static_assert(kStage2QueueOff + 2 * kProbeMaxKeysPerPass == kProbeStage2HeaderBytes, "stage2 header layout");
 static_assert(kProbeStage2HeaderBytes % 16 == 0, "bulk copies need 16-byte aligned destinations");
 
+// Every lane that published into the stage (result-row words, survivor queue entries) arrives on `aready` itself,
+// so the publication does not lean on the warp barrier's transitivity (racecheck reported that pair in round 1).
+constexpr bool kAllLanesArrive = true;
+
 template <int NA, int KPT, int NT, int NB, int T, bool TRACE>
 __global__ void __launch_bounds__((NA + NB) * 32, 1)
 probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, const uint32_t* __restrict__ n_list_dev,
@@ -328,7 +332,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&aready[s], NA);
+            mbar_init(&aready[s], kAllLanesArrive ? NA * 32 : NA);
             done[s] = 0;
             *reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(s) * stage_bytes + kStage2CntOff) = 0;
         }
@@ -454,7 +458,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             // (acquire.cta) -> its loads.  compute-sanitizer racecheck does not credit the warp barrier's
             // transitivity and reports the queue write/read pair; memcheck and synccheck are clean.
             __syncwarp();
-            if (lane == 0) mbar_arrive(&aready[s]);
+            if (kAllLanesArrive || lane == 0) mbar_arrive(&aready[s]);
             if (TRACE && tr && tid == 0 && 2 + 8 * it < trace_slots) tr[2 + 8 * it] = globaltimer_ns();
             st += stage_bytes;
             if (++s == S) { s = 0; ph ^= 1u; st = stages; }
