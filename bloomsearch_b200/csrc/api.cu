@@ -90,7 +90,7 @@ struct bsg_ctx {
     int max_stages = 0;    // BSG_PROBE_STAGES override (tuning)
     int probe_variant = 7; // BSG_PROBE_VARIANT: 7 = per corpus (default, see staged_variant_for); 6 = probe_tiles; 0 = probe_staged
                            // (one phase); 1..5 = shapes of probe_staged2
-    int tiles_shape = 5;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
+    int tiles_shape = 1;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
     int tile_bytes = 60000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
@@ -1151,7 +1151,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     auto filters_ok = [&](uint64_t u) {
         for (int k = 0; k < 3; ++k) {
             const DevFilter& d = L.udesc[u * 3 + k];
-            if (d.m && (d.m >= (1ull << 30) || d.k > 0xffffu)) return false;
+            if (d.m && (d.m >= (1ull << 30) || d.k > kTileMaxK)) return false;
         }
         return true;
     };
@@ -1172,9 +1172,9 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     uint64_t data_cap = 0;
     auto tile_filter = [&](uint64_t u, int k, uint64_t rel_bytes) {
         const DevFilter& d = L.udesc[u * 3 + k];
-        if (d.m == 0) return TileFilter{0, 0, 0, 0};
+        if (d.m == 0) return tile_filter_absent();
         return TileFilter{static_cast<uint32_t>(d.m), static_cast<uint32_t>(d.inv >> 32), static_cast<uint32_t>(d.inv),
-                          (d.k << 16) | static_cast<uint32_t>(rel_bytes >> 4)};
+                          (static_cast<uint32_t>(rel_bytes) << 8) | static_cast<uint32_t>(d.k)};
     };
     auto small_k = [&](uint64_t u, int k) { const DevFilter& d = L.udesc[u * 3 + k]; return d.m && d.k < 4; };
     if (kind_mode) {
@@ -1185,6 +1185,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
             for (int part = 0; part < 2; ++part) {
                 TileRec r;
                 memset(&r, 0, sizeof(r));
+                for (auto& fu : r.f) for (auto& fk : fu) fk = tile_filter_absent();
                 r.n_units = 1;
                 r.part_kinds = part == 0 ? 3u : 4u;
                 r.flags = part == 0 ? kTileFirstPart : kTileLastPart;
@@ -1235,6 +1236,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
                 close_tile();
             if (!open) {
                 memset(&r, 0, sizeof(r));
+                for (auto& fu : r.f) for (auto& fk : fu) fk = tile_filter_absent();
                 r.part_kinds = 7u;
                 r.flags = kTileFirstPart | kTileLastPart;
                 r.fill.word_base = t.word_base;

@@ -173,25 +173,39 @@ __device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) 
     return r;
 }
 
-// Same reduction for m < 2^30, in 32-bit arithmetic only (9 instructions instead of ~35 for the emulated
-// 64x64 multiply-high): with I = inv = floor(2^64/m) = Ih*2^32 + Il,
-//   step 1  t = hi32(x) mod m            (32-bit Barrett with Ih = floor(2^32/m))
-//   step 2  y = t*2^32 + lo32(x) < m*2^32, so floor(y/m) < 2^32 and
-//           q = t*Ih + floor((t*Il + xl*Ih) / 2^32) is floor(y/m) - {0,1,2}  (one 64-bit multiply-add:
-//           IMAD.WIDE x2, no zeroing moves); y - q*m < 3m < 2^32 is exact in 32-bit wraparound arithmetic.
-// (proof in DESIGN.md §5; m == 1 works through inv = 2^64-1.)
+// Same reduction for m < 2^30 in SIX 32-bit instructions (2 IMAD.WIDE, 2 IMAD, 2 VIADDMNMX) instead of ~35 for the
+// emulated 64x64 multiply-high.  With I = inv = floor(2^64/m) = Ih*2^32 + Il and x = xh*2^32 + xl:
+//   q_full = xh*Ih + floor((xh*Il + xl*Ih) / 2^32)  is floor(x/m) - {0,1,2}   (it drops two fractional parts of
+//   x*I/2^64, each < 1, and x/m - x*I/2^64 is in [0,1)), so x - q_full*m is in [0, 3m), below 2^32 for m < 2^30.
+// A value below 2^32 is determined by its residue mod 2^32, and that residue needs only q_full mod 2^32:
+//   q = lo32(xh*Ih) + hi32((xh*Il + xl*Ih) mod 2^64),   r = lo32(xl - q*m)  — exact, then two conditional
+// subtractions (2m, m), each min(v, v - c): v - c wraps above v exactly when v < c.
+// No quotient ever has to fit 32 bits, so there is no separate reduction of xh (rounds 1-2 spent 12 instructions
+// on a two-step form).  (proof in DESIGN.md §5; m == 1 works through inv = 2^64-1; checked against 128-bit
+// arithmetic by tests/test_host_logic.py::test_mod_m32_formula.)
 __device__ __forceinline__ uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih, uint32_t il) {
     const uint32_t xh = static_cast<uint32_t>(x >> 32), xl = static_cast<uint32_t>(x);
-    const uint32_t nm = 0u - m;
-    // conditional subtraction as min(v, v - c): v - c wraps above v exactly when v < c
-    uint32_t t = __umulhi(xh, ih) * nm + xh;  // xh - floor-ish(xh/m)*m, in [0, 2m)
-    t = min(t, t - m);
-    const uint64_t s = static_cast<uint64_t>(xl) * ih + static_cast<uint64_t>(t) * il;  // < 2^64 (see the proof)
-    const uint32_t q = static_cast<uint32_t>(s >> 32) + t * ih;
-    uint32_t r = q * nm + xl;                 // y - q*m, in [0, 3m)
+    uint32_t shi;
+    asm("{\n\t.reg .u64 s;\n\t.reg .u32 lo;\n\t"
+        "mul.wide.u32 s, %1, %2;\n\t"
+        "mad.wide.u32 s, %3, %4, s;\n\t"
+        "mov.b64 {lo, %0}, s;\n\t}"
+        : "=r"(shi)
+        : "r"(xl), "r"(ih), "r"(xh), "r"(il));
+    const uint32_t q = xh * ih + shi;
+    const uint32_t nm = 0u - m;               // one negation per filter (hoisted), not one per location: written as
+    uint32_t r;                               // C++, q * nm + xl is turned back into m * (-q) + xl
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(nm), "r"(xl));   // x - q_full*m, in [0, 3m)
     r = min(r, r - 2u * m);
     r = min(r, r - m);
     return r;
+}
+// Word index of a bit, opaque to the optimiser: `w32[bit >> 5]` is canonicalised to ((bit >> 3) & ~3) + base
+// (SHF, LOP3, IADD); with the shift hidden the address is formed as base + idx * 4 (SHF, LEA).
+__device__ __forceinline__ uint32_t word_index(uint32_t bit) {
+    uint32_t i;
+    asm("shr.u32 %0, %1, 5;" : "=r"(i) : "r"(bit));
+    return i;
 }
 constexpr uint64_t kSmallModLimit = 1ull << 30;
 

@@ -105,11 +105,24 @@ struct ProbeStagedPlan {
 // One 512-byte TileRec per tile, bulk-copied into the stage header; the 64-byte TileFill of the tile
 // that will occupy the same stage next travels with it, so a refill never waits on a global load.
 constexpr uint32_t kTileMaxUnits = 8;
-struct __align__(16) TileFilter {  // staged filters: m < 2^30, k < 2^16, at most 1 MB into the tile data
-    uint32_t m;        // bits; 0 = filter absent (cannot disqualify, query_exec.go:137-151)
+struct __align__(16) TileFilter {  // staged filters: m < 2^30, k < 2^8, at most 16 MB into the tile data
+    uint32_t m;        // bits
     uint32_t ih, il;   // hi / lo halves of floor(2^64/m), see mod_m32
-    uint32_t krel;     // k << 16 | (byte offset of the filter's words inside the tile data) >> 4
+    uint32_t krel;     // (byte offset of the filter's words inside the tile data) << 8 | k
 };
+// An ABSENT filter (Go nil: cannot disqualify, query_exec.go:137-151) is k = 0 and reads as a one-bit filter at
+// offset 0 (m = 1: every location reduces to bit 0 of the tile's first word), so the first tests of a key need
+// neither a predicate nor a zero-filled copy of the descriptor; the same record fills the kinds a KIND-mode tile
+// does not carry.
+constexpr uint32_t kTileMaxK = 255;
+#if defined(__CUDACC__)
+#define BSG_HD __host__ __device__
+#else
+#define BSG_HD
+#endif
+BSG_HD inline uint32_t tile_k(uint32_t krel) { return krel & 0xffu; }
+BSG_HD inline uint32_t tile_rel(uint32_t krel) { return krel >> 8; }
+inline TileFilter tile_filter_absent() { return TileFilter{1u, 0xffffffffu, 0xffffffffu, 0u}; }
 struct __align__(16) TileFill {    // what the thread that (re)fills a stage needs
     uint64_t word_base;            // first word of the tile's data in the corpus words array (even)
     uint32_t data_bytes;           // all filters of the tile, 16-byte multiple

@@ -85,17 +85,17 @@ __device__ __forceinline__ void fill_tile(uint8_t* st, uint64_t* bar, const Tile
 // only when t < k.
 template <int NT, bool SMALLK>
 __device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uint4 f, const uint8_t* data) {
-    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
     uint32_t bit[NT], wv[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) wv[t] = w32[bit[t] >> 5];
+    for (int t = 0; t < NT; ++t) wv[t] = w32[word_index(bit[t])];
     uint32_t pass = 1u;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
-        if (SMALLK) b |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
+        if (SMALLK) b |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
         pass &= b;
     }
     return pass != 0u;
@@ -255,25 +255,26 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
                     bool pass[KPT];
 #pragma unroll
                     for (int j = 0; j < KPT; ++j) {
+                        // a key slot of a kind this tile does not carry reads an all-zero descriptor (m == 0: nothing
+                        // is loaded) and is masked out below; no zero-filled copy of the descriptor is needed
                         const bool act = (kbit[j] & head.y) != 0;
-                        uint4 f = make_uint4(0, 0, 0, 0);
-                        if (act) f = *reinterpret_cast<const uint4*>(desc + koff[j]);
-                        // absent filter (m == 0): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
-                        const bool test = act && f.x != 0;
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                        const uint4 f = *reinterpret_cast<const uint4*>(desc + koff[j]);
+                        // absent filter (k == 0, encoded as m = 1 at offset 0 so that the loads below need no
+                        // predicate): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
                         uint32_t bit[NT], wv[NT];
 #pragma unroll
                         for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f.x, f.y, f.z);
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
+                        for (int t = 0; t < NT; ++t) wv[t] = w32[word_index(bit[t])];
                         uint32_t p = 1u;
 #pragma unroll
                         for (int t = 0; t < NT; ++t) {
                             uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
-                            if (SMALLK) b |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
+                            if (SMALLK) b |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
                             p &= b;
                         }
-                        pass[j] = act && (f.x == 0 || p != 0u);
+                        pass[j] = act && (tile_k(f.w) == 0u || p != 0u);
                     }
 #pragma unroll
                     for (int j = 0; j < KPT; ++j) {
@@ -325,11 +326,11 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
                 const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
                 const uint32_t si = s_slot[slot];
                 const uint4 f = *reinterpret_cast<const uint4*>(st + kTileDescOff + u * 48u + (si >> 14) * 16u);
-                const uint32_t k = f.w >> 16;
-                bool fin = f.x == 0 || k <= static_cast<uint32_t>(NT);   // absent filter, or every location already passed
+                const uint32_t k = tile_k(f.w);
+                bool fin = k <= static_cast<uint32_t>(NT);   // absent filter (k == 0), or every location already passed
                 if (!fin) {
                     const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
                     uint32_t ok = 1u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {   // locations NT..NT+3: i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
                         const uint64_t aa = (i & 1) ? x.y : x.x;
                         const uint64_t bb = (((i + (i & 1)) & 3) >> 1) ? y.y : y.x;
                         const uint32_t bit = mod_m32(aa + static_cast<uint64_t>(i) * bb, f.x, f.y, f.z);
-                        ok &= ((w32[bit >> 5] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
+                        ok &= ((w32[word_index(bit)] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
                     }
                     fin = ok != 0u && k <= static_cast<uint32_t>(NT + 4);
                     more = ok != 0u && !fin;
@@ -368,8 +369,8 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
             const uint32_t si = s_slot[slot];
             const uint4 f = *reinterpret_cast<const uint4*>(st + kTileDescOff + u * 48u + (si >> 14) * 16u);
             const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-            if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
-                                      reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4)))) {
+            if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, tile_k(f.w),
+                                      reinterpret_cast<const uint32_t*>(data + tile_rel(f.w)))) {
                 const uint32_t pos = si & 0x3ffu;
                 atomicOr(&rows[u * 32u + (pos >> 5)], 1u << (pos & 31u));
             }
@@ -588,8 +589,8 @@ __global__ void __launch_bounds__(1024, 1) probe_pipe_kernel(const ProbeTilesArg
                 const uint32_t si = s_slot[slot];
                 const uint4 f = *reinterpret_cast<const uint4*>(st2 + kTileDescOff + u * 48u + (si >> 14) * 16u);
                 const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, f.w >> 16,
-                                          reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4)))) {
+                if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, tile_k(f.w),
+                                          reinterpret_cast<const uint32_t*>(data + tile_rel(f.w)))) {
                     const uint32_t pos = si & 0x3ffu;
                     atomicOr(&r[u * 32u + (pos >> 5)], 1u << (pos & 31u));
                 }
@@ -618,11 +619,11 @@ __global__ void __launch_bounds__(1024, 1) probe_pipe_kernel(const ProbeTilesArg
                     const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
                     const uint32_t si = s_slot[slot];
                     const uint4 f = *reinterpret_cast<const uint4*>(st1 + kTileDescOff + u * 48u + (si >> 14) * 16u);
-                    const uint32_t k = f.w >> 16;
-                    bool fin = f.x == 0 || k <= static_cast<uint32_t>(NT);   // absent filter, or every location already passed
+                    const uint32_t k = tile_k(f.w);
+                    bool fin = k <= static_cast<uint32_t>(NT);   // absent filter (k == 0), or every location already passed
                     if (!fin) {
                         const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
                         uint32_t ok = 1u;
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {   // locations NT..NT+3
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(1024, 1) probe_pipe_kernel(const ProbeTilesArg
                             const uint64_t aa = (i & 1) ? x.y : x.x;
                             const uint64_t bb = (((i + (i & 1)) & 3) >> 1) ? y.y : y.x;
                             const uint32_t bit = mod_m32(aa + static_cast<uint64_t>(i) * bb, f.x, f.y, f.z);
-                            ok &= ((w32[bit >> 5] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
+                            ok &= ((w32[word_index(bit)] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
                         }
                         fin = ok != 0u && k <= static_cast<uint32_t>(NT + 4);
                         more = ok != 0u && !fin;
@@ -671,23 +672,21 @@ __global__ void __launch_bounds__(1024, 1) probe_pipe_kernel(const ProbeTilesArg
                     const uint8_t* desc = st + kTileDescOff + koff;
 #pragma unroll 2
                     for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
-                        uint4 f = make_uint4(0, 0, 0, 0);
-                        if (act) f = *reinterpret_cast<const uint4*>(desc);
-                        const bool test = act && f.x != 0;
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + ((f.w & 0xffffu) << 4));
+                        const uint4 f = *reinterpret_cast<const uint4*>(desc);
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
                         uint32_t bit[NT], wv[NT];
 #pragma unroll
                         for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) wv[t] = test ? w32[bit[t] >> 5] : 0u;
+                        for (int t = 0; t < NT; ++t) wv[t] = w32[word_index(bit[t])];
                         uint32_t p = 1u;
 #pragma unroll
                         for (int t = 0; t < NT; ++t) {
                             uint32_t bb = (wv[t] >> (bit[t] & 31u)) & 1u;
-                            if (SMALLK) bb |= static_cast<uint32_t>((f.w >> 16) <= static_cast<uint32_t>(t));
+                            if (SMALLK) bb |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
                             p &= bb;
                         }
-                        const bool pass = act && (f.x == 0 || p != 0u);   // absent filter: survives to round B1
+                        const bool pass = act && (tile_k(f.w) == 0u || p != 0u);   // absent filter: survives to round B1
                         const uint32_t bits = __ballot_sync(0xffffffffu, pass);
                         if (lane == u) my = bits;
                     }

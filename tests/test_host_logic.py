@@ -173,3 +173,18 @@ def test_mask_and_matrix_unpack():
     bits[:] = 1
     bits[cq2.keys.index(b"b3")] = 0
     assert cref.eval_postfix(cq2.prog, bits) == 0
+
+
+def test_mod_m32_formula(tmp_path):
+    """The exact 32-bit `location % m` of the kernels (bsg_device.cuh: mod_m32), same operations in
+    plain C, against 128-bit arithmetic on edge moduli and edge values (tools/mod32_check.c)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "mod32_check"
+    subprocess.run(["gcc", "-O2", "-o", str(exe), os.path.join(root, "tools", "mod32_check.c")], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip().endswith(", 0 bad"), out
+    # the C file must state the formula the device header uses (guards against the two drifting apart)
+    dev = open(os.path.join(root, "bloomsearch_b200", "csrc", "bsg_device.cuh")).read()
+    assert "mad.wide.u32 s, %3, %4, s" in dev and "xh * ih + shi" in dev
