@@ -484,6 +484,8 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
            "what": "bsg_probe(): packed host key bytes -> one H2D copy, one kernel (hashing fused into the probe), the "
                    "(block x key) matrix rows written by the kernel straight into the caller's result buffer (pinned, from "
                    "bsg_host_alloc); corpus resident in HBM (bytes per step = per call x batches per step)"}
+    if headline:
+        e2e["small_queries"] = small_query_rates(bs, ctx, corpora[0], c, n_units, env)
     out = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "e2e": e2e, "clocks": clocks,
            "launches_per_step": launches_per_batch * BATCHES_PER_STEP, "bitset_mb": bitset_bytes / 1e6,
            "n_units_per_gpu": n_units, "replicas": n_rep}
@@ -529,6 +531,52 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
     for cp in corpora:
         cp.close()
     return out, cpu
+
+
+def small_query_rates(bs, ctx, corpus, c, n_units, env, n_threads=32, calls_each=150):
+    """many concurrent SMALL queries (8 FieldToken/Token keys, And(Or(..), Or(..), k, k) — config 4's
+    shape) against the resident corpus, n_threads host threads (issued from C, bsg_debug_query_callers): each query
+    its own bsg_probe call vs. the same calls through bsg_batcher (concurrent callers merged into bsg_probe_multi
+    launches).  Masks are compared between the two arms."""
+    from bloomsearch_b200 import _native as N
+    rng = np.random.default_rng(11)
+    idx = rng.choice(c.n_keys, 4, replace=False)
+    group_of = np.searchsorted(c.group_begin, idx, side="right") - 1
+    keys = [c.key(int(i)) for i in idx] + [b"absent-q%d" % i for i in range(4)]
+    kinds = np.array([int(g % 3) for g in group_of] + [1, 2, 1, 2], dtype=np.uint8)
+    blob, off = N.pack_keys(keys)
+    OPL, AND, OR = N.OP_LEAF, N.OP_AND, N.OP_OR
+    prog = np.array([(OPL, 0), (OPL, 4), (OR, 2), (OPL, 1), (OPL, 5), (OR, 2), (AND, 2), (OPL, 2), (OPL, 3), (OR, 2), (AND, 2)],
+                    dtype=N.OP_DTYPE)
+    L = N.lib()
+    L.bsg_debug_query_callers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]
+    words = (n_units + 63) // 64
+
+    def run(batcher_handle, threads, calls):
+        mask = np.zeros(max(words, 1), np.uint64)
+        sec = C.c_double()
+        N.check(L.bsg_debug_query_callers(ctx.handle, corpus.handle, batcher_handle, threads, calls, N.ptr(blob), N.ptr(off),
+                                          len(keys), N.ptr(kinds), N.ptr(prog), len(prog), N.ptr(mask), C.byref(sec)))
+        return sec.value, mask
+    res = {"threads": n_threads, "keys_per_query": len(keys), "calls_per_thread": calls_each}
+    run(None, n_threads, 10)
+    dt, m_direct = run(None, n_threads, calls_each)
+    res["direct"] = {"queries_per_s": env.sum(n_threads * calls_each / env.max(dt)), "us_per_query_per_thread": dt / calls_each * 1e6}
+    dt1, _ = run(None, 1, calls_each)
+    res["single_caller_us_per_query"] = dt1 / calls_each * 1e6
+    b = bs.Batcher(corpus)
+    run(b._h, n_threads, 10)
+    dt, m_batched = run(b._h, n_threads, calls_each)
+    st = b.stats()
+    b.close()
+    assert np.array_equal(m_direct, m_batched), "batched mask differs from the direct call's"
+    res["batched"] = {"queries_per_s": env.sum(n_threads * calls_each / env.max(dt)), "us_per_query_per_thread": dt / calls_each * 1e6,
+                      "launches": st["launches"], "calls": st["calls"], "largest_batch": st["largest_batch"]}
+    res["probes_per_query"] = int(n_units * len(keys))
+    res["what"] = ("host threads issuing 8-key AND/OR queries concurrently: bsg_probe per query vs bsg_batcher_probe "
+                   "(group commit into bsg_probe_multi); masks identical")
+    return res
 
 
 def encode_sections_gpu_arm(desc, words, n_units):

@@ -8,7 +8,7 @@ operation raises.
 """
 from . import _native
 from ._native import BloomGpuError, build
-from .engine import (BloomEntrySets, BloomFilter, BloomFilters, Context, Corpus, FilterCache, KeySet, Query, build_filters_many,
+from .engine import (Batcher, BloomEntrySets, BloomFilter, BloomFilters, Context, Corpus, FilterCache, KeySet, Query, build_filters_many,
                      estimate_parameters, probe_hierarchical, probe_hierarchical_gather, unpack_mask, unpack_matrix)
 from .query import (And, AndBloomQueries, BloomCondition, BloomExpression, BloomQuery, Field, FieldRegex, FieldToken,
                     NewQuery, Or, RegexAnd, RegexFieldGuardBloomQuery, RegexOr, RegexQuery, Token,

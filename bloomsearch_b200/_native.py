@@ -71,6 +71,7 @@ ABI_SYMBOLS = [
     "bsg_corpus_device_bytes", "bsg_cache_create", "bsg_cache_destroy", "bsg_cache_acquire", "bsg_cache_insert",
     "bsg_cache_insert_sections", "bsg_cache_release", "bsg_cache_invalidate", "bsg_cache_stats",
     "bsg_host_alloc", "bsg_host_free",
+    "bsg_probe_multi", "bsg_batcher_create", "bsg_batcher_destroy", "bsg_batcher_probe", "bsg_batcher_stats",
 ]
 
 
@@ -158,6 +159,12 @@ def lib():
     L.bsg_cache_stats.argtypes = [vp] + [C.POINTER(u64)] * 6
     L.bsg_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.bsg_host_free.argtypes = [vp, vp]
+    L.bsg_probe_multi.argtypes = [vp, vp, vp, vp, u32, vp, u32, vp, vp, vp, vp]
+    L.bsg_batcher_create.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
+    L.bsg_batcher_destroy.argtypes = [vp]
+    L.bsg_batcher_destroy.restype = None
+    L.bsg_batcher_probe.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp]
+    L.bsg_batcher_stats.argtypes = [vp] + [C.POINTER(u64)] * 4
     _lib = L
     return L
 

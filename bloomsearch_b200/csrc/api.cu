@@ -1117,14 +1117,12 @@ uint64_t tiles_cta_smem(const bsg_ctx* ctx) {
 int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     const uint64_t n_units = c->n_units;
     // ring budget for a full pass of keys: the fixed part grows with the units per tile (survivor lists, rows).
-    // The pipelined kernel holds a slot for three iterations after its round A: it wants a ring of >= 5 stages.
-    const bool pipe = probe_tiles_pipelined(ctx->tiles_shape) != 0;
     const uint32_t group_cap_cfg = static_cast<uint32_t>(std::min<int>(ctx->tile_units, kTileMaxUnits));
     const uint64_t cta_smem = tiles_cta_smem(ctx);
     auto ring_budget = [&](uint32_t units_cap) {
-        return cta_smem - (pipe ? tiles_fixed_smem_pipe(units_cap, kProbeMaxKeysPerPass) : tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass));
+        return cta_smem - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass);
     };
-    const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), pipe ? 5 : 1);
+    const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), 1);
     auto tile_limit = [&](uint32_t g) { return ring_budget(g) / min_stages - tile_header_bytes(g); };
     // units per tile: the g in 1..cfg that packs the most units of the typical size (more units per tile cost list space)
     uint32_t group_cap = 1;
@@ -1527,6 +1525,8 @@ struct bsg_query {
     bsg_expr_op* d_prog = nullptr;
     uint32_t* d_matrix32 = nullptr;
     uint32_t* d_mask32 = nullptr;
+    uint32_t* d_multi_mask32 = nullptr;   // bsg_probe_multi: one candidate mask per query of the batch
+    size_t cap_multi_mask = 0;
     int last_launches = 0;
 };
 
@@ -1540,6 +1540,7 @@ extern "C" void bsg_query_free(bsg_query* q) {
     cudaFree(q->d_prog);
     cudaFree(q->d_matrix32);
     cudaFree(q->d_mask32);
+    cudaFree(q->d_multi_mask32);
     if (q->h_pin) cudaFreeHost(q->h_pin);
     if (q->h_out) cudaFreeHost(q->h_out);
     cudaFree(q->d_in);
@@ -1591,7 +1592,7 @@ static cudaError_t ensure_cap(T*& p, size_t& cap, size_t need_bytes) {
 // launches the hash kernel on stream s.  Buffers only grow.
 static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
                             uint32_t n_keys, const uint8_t* key_kind, const bsg_expr_op* prog, uint32_t prog_len,
-                            cudaStream_t s, bsg_query* q, bool use_pinned = false) {
+                            cudaStream_t s, bsg_query* q, bool use_pinned = false, bool prog_prevalidated = false) {
     if (!ctx || !corpus || !q || (n_keys && (!key_off || !key_kind)) || (prog_len && !prog))
         return fail(BSG_ERR_INVALID, "NULL argument");
     const uint64_t nbytes = n_keys ? key_off[n_keys] : 0;
@@ -1603,7 +1604,7 @@ static int query_prepare_on(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_
         if (key_kind[i] > 2) return fail(BSG_ERR_INVALID, "key %u: kind %u unknown", i, key_kind[i]);
         kind_mask |= 1u << key_kind[i];
     }
-    if (prog_len) {
+    if (prog_len && !prog_prevalidated) {
         int rc = validate_program(prog, prog_len, n_keys);
         if (rc) return rc;
     }
@@ -1820,14 +1821,8 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
             const uint64_t stage_bytes = tile_header_bytes(plan.units_cap) + plan.stage_data_bytes;
             int max_stages = kProbeMaxStages;
             if (ctx->max_stages > 0 && ctx->max_stages < max_stages) max_stages = ctx->max_stages;
-            uint32_t fixed = probe_tiles_pipelined(plan.shape) ? tiles_fixed_smem_pipe(c->t_units_cap, nk) : tiles_fixed_smem(c->t_units_cap, nk);
+            const uint32_t fixed = tiles_fixed_smem(c->t_units_cap, nk);
             plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, (tiles_cta_smem(ctx) - fixed) / stage_bytes));
-            if (probe_tiles_pipelined(plan.shape) && plan.n_stages < 4) {
-                // the pipelined kernel needs a ring of >= 4 stages: large tiles take the lock-step kernel
-                plan.shape = 1;
-                fixed = tiles_fixed_smem(c->t_units_cap, nk);
-                plan.n_stages = static_cast<int>(std::min<uint64_t>(max_stages, (tiles_cta_smem(ctx) - fixed) / stage_bytes));
-            }
             if (plan.n_stages < 1) return fail(BSG_ERR_INVALID, "internal: tile does not fit shared memory");
             plan.smem_bytes = fixed + plan.n_stages * stage_bytes;
             plan.grid = static_cast<int>(std::min<uint64_t>(
@@ -2059,6 +2054,87 @@ extern "C" int bsg_probe(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* 
         ctx->t_calls += 1; ctx->t_prepare += ns(t0, t1); ctx->t_run += ns(t1, t2); ctx->t_wait += ns(t2, t3);
         ctx->t_copyout += ns(t3, t4);
     }
+    if (q) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->scratch_pool.push_back(q);
+    }
+    pool_put(ctx, s);
+    return rc;
+}
+
+// Several queries in ONE pass over the corpus (concurrent queries merged into one launch).
+// The staged probe streams every filter byte of the corpus once per pass of up to 1 024 keys whatever the number
+// of keys, so the keys of many small queries (the reference's typical query has a handful of leaves) ride along
+// for free; each query keeps its own expression and gets its own candidate mask.
+extern "C" int bsg_probe_multi(bsg_ctx* ctx, const bsg_corpus* corpus, const uint8_t* keys, const uint64_t* key_off,
+                               uint32_t n_keys, const uint8_t* key_kind, uint32_t n_queries,
+                               const uint32_t* query_key_begin, const bsg_expr_op* progs, const uint32_t* prog_begin,
+                               uint64_t* out_masks) {
+    if (!ctx || !corpus || !query_key_begin || !prog_begin || !out_masks || n_queries == 0)
+        return fail(BSG_ERR_INVALID, "NULL argument");
+    if (n_queries > 65535u) return fail(BSG_ERR_INVALID, "at most 65535 queries per call");
+    if (query_key_begin[0] != 0 || query_key_begin[n_queries] != n_keys || prog_begin[0] != 0)
+        return fail(BSG_ERR_INVALID, "query_key_begin / prog_begin must be CSR arrays covering all keys / ops");
+    const uint32_t total_ops = prog_begin[n_queries];
+    if (total_ops && !progs) return fail(BSG_ERR_INVALID, "progs is NULL");
+    // leaves are query-local in the caller's programs and batch-global on the device; the CSR of the programs
+    // rides behind the ops in the same upload (two uint32 per pseudo-op)
+    const uint32_t tail_ops = (n_queries + 2u) / 2u;
+    std::vector<bsg_expr_op> gprog(static_cast<size_t>(total_ops) + tail_ops, bsg_expr_op{0u, 0u});
+    for (uint32_t j = 0; j < n_queries; ++j) {
+        const uint32_t kb = query_key_begin[j], ke = query_key_begin[j + 1], pb = prog_begin[j], pe = prog_begin[j + 1];
+        if (ke < kb || ke > n_keys || pe < pb || pe > total_ops)
+            return fail(BSG_ERR_INVALID, "query %u: key / op range not monotone", j);
+        if (pe > pb) {
+            int rc = validate_program(progs + pb, pe - pb, ke - kb);
+            if (rc) return rc;
+        }
+        for (uint32_t pc = pb; pc < pe; ++pc) {
+            gprog[pc] = progs[pc];
+            if (progs[pc].op == BSG_OP_LEAF) gprog[pc].arg += kb;
+        }
+    }
+    memcpy(gprog.data() + total_ops, prog_begin, (static_cast<size_t>(n_queries) + 1) * sizeof(uint32_t));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = pool_get(ctx);
+    if (!s) return fail(BSG_ERR_CUDA, "stream create failed");
+    bsg_query* q = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->scratch_pool.empty()) { q = ctx->scratch_pool.back(); ctx->scratch_pool.pop_back(); }
+    }
+    if (!q) q = new (std::nothrow) bsg_query();
+    int rc = q ? BSG_OK : fail(BSG_ERR_NOMEM, "query alloc");
+    if (rc == BSG_OK)
+        rc = query_prepare_on(ctx, corpus, keys, key_off, n_keys, key_kind, gprog.data(),
+                              static_cast<uint32_t>(gprog.size()), s, q, true, true);
+    const uint64_t n_units = corpus->n_units;
+    const uint64_t mask_words32 = 2 * ((n_units + 63) / 64);
+    const size_t out_bytes = static_cast<size_t>(n_queries) * mask_words32 * 4;
+    auto run = [&]() -> int {
+        int r = query_run_on(ctx, corpus, q, BSG_PROBE_AUTO | BSG_RUN_MATRIX_ONLY, 1, s);
+        if (r) return r;
+        if (n_units == 0) return BSG_OK;
+        CUDA_TRY(ensure_cap(q->d_multi_mask32, q->cap_multi_mask, std::max<size_t>(out_bytes, 16)));
+        CUDA_TRY(launch_tree_eval_multi(q->k_matrix, q->row_words32, n_units, q->k_prog,
+                                        reinterpret_cast<const uint32_t*>(q->k_prog + total_ops), n_queries,
+                                        q->d_multi_mask32, mask_words32, corpus->d_bad32, s));
+        q->last_launches += 1;
+        if (out_bytes + 16 > q->cap_pin) {  // the inputs in the pinned block must have been consumed first
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (q->h_pin) cudaFreeHost(q->h_pin);
+            q->h_pin = nullptr;
+            q->cap_pin = 0;
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&q->h_pin), (out_bytes + 16) * 2, cudaHostAllocDefault));
+            q->cap_pin = (out_bytes + 16) * 2;
+        }
+        CUDA_TRY(cudaMemcpyAsync(q->h_pin, q->d_multi_mask32, out_bytes, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(stream_wait(ctx, s));
+        memcpy(out_masks, q->h_pin, out_bytes);
+        return BSG_OK;
+    };
+    if (rc == BSG_OK) rc = run();
+    if (rc != BSG_OK) cudaStreamSynchronize(s);
     if (q) {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->scratch_pool.push_back(q);

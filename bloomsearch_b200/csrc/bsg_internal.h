@@ -156,12 +156,6 @@ inline uint32_t tiles_fixed_smem(uint32_t units_cap, uint32_t n_keys) {
     const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
     return kTilesPrefixBytes + kTilesSlotInfoBytes + units_cap * 128u + 2u * units_cap * 2u * kProbeMaxKeysPerPass + hash_bytes;
 }
-// probe_pipe_kernel: + unit-id table (8 tiles x 64 B), 8 row buffers, both survivor lists double buffered
-inline uint32_t tiles_fixed_smem_pipe(uint32_t units_cap, uint32_t n_keys) {
-    const uint32_t hash_bytes = ((n_keys + 31u) & ~31u) * 32u;
-    return kTilesPrefixBytes + kTilesSlotInfoBytes + 8u * 64u + 8u * units_cap * 128u +
-           4u * units_cap * 2u * kProbeMaxKeysPerPass + hash_bytes;
-}
 
 struct ProbeTilesPlan {
     int n_stages;
@@ -178,7 +172,6 @@ struct ProbeTilesPlan {
 cudaError_t probe_tiles_configure(int max_smem_optin);
 int probe_tiles_n_shapes();
 int probe_tiles_threads(int shape);        // threads per CTA of a compiled shape; 1024 / threads CTAs share an SM
-int probe_tiles_pipelined(int shape);      // 1: probe_pipe_kernel (rounds software pipelined across tiles; ring of >= 4 stages)
 const char* probe_tiles_shape_name(int shape);
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
                                const uint32_t* d_n_items, const uint64_t* d_words, const uint64_t* d_hashes,
@@ -202,6 +195,10 @@ cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_word
 cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
                              const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s,
                              const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr);
+cudaError_t launch_tree_eval_multi(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
+                                   const bsg_expr_op* d_prog, const uint32_t* d_prog_begin, uint32_t n_queries,
+                                   uint32_t* d_masks32, uint64_t mask_words32, const uint32_t* d_bad32,
+                                   cudaStream_t s);
 cudaError_t launch_parent_mask(uint32_t* d_mask32, uint64_t n_units, const uint32_t* d_parent,
                                const uint32_t* d_parent_mask32, cudaStream_t s);
 cudaError_t launch_compact_rows(const StageRow* d_stab, uint32_t n_rows, const uint32_t* d_parent,

@@ -788,6 +788,59 @@ cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, u
     return cudaGetLastError();
 }
 
+// Several queries that were probed as ONE batch (bsg_probe_multi: the keys of concurrent queries share a pass over
+// the corpus): blockIdx.y = query; its program is prog[prog_begin[q] .. prog_begin[q+1]) with leaf arguments that
+// already index the batch's key columns.  An empty program keeps every unit (query_exec.go:81-83).  Units whose
+// section failed to parse are cleared here (bad32, nullable) instead of by a second kernel.
+__global__ void __launch_bounds__(256)
+tree_eval_multi_kernel(const uint32_t* __restrict__ matrix32, uint32_t row_words32, uint64_t n_units,
+                       const bsg_expr_op* __restrict__ prog, const uint32_t* __restrict__ prog_begin,
+                       uint32_t* __restrict__ masks32, uint64_t mask_words32, const uint32_t* __restrict__ bad32) {
+    const uint32_t q = blockIdx.y;
+    const uint32_t pb = __ldg(&prog_begin[q]), pe = __ldg(&prog_begin[q + 1]);
+    const uint64_t unit = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (unit < n_units) {
+        const uint32_t* row = matrix32 + unit * row_words32;
+        uint64_t stack = 1ull;   // an empty program leaves "true"
+        for (uint32_t pc = pb; pc < pe; ++pc) {
+            const uint32_t op = __ldg(&prog[pc].op), arg = __ldg(&prog[pc].arg);
+            if (op == BSG_OP_LEAF) {
+                const uint32_t bit = (__ldg(&row[arg >> 5]) >> (arg & 31u)) & 1u;
+                stack = (stack << 1) | bit;
+            } else if (op == BSG_OP_TRUE) {
+                stack = (stack << 1) | 1ull;
+            } else if (op == BSG_OP_FALSE) {
+                stack = stack << 1;
+            } else {
+                const uint64_t msk = arg >= 64 ? ~0ull : ((1ull << arg) - 1ull);
+                const uint64_t top = stack & msk;
+                const uint64_t v = (op == BSG_OP_AND) ? (top == msk) : (top != 0);
+                stack = arg >= 64 ? 0ull : (stack >> arg);
+                stack = (stack << 1) | v;
+            }
+        }
+        alive = stack & 1ull;
+    }
+    uint32_t bits = __ballot_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && (unit - (threadIdx.x & 31)) < n_units) {
+        if (bad32) bits &= ~__ldg(&bad32[unit >> 5]);
+        masks32[static_cast<uint64_t>(q) * mask_words32 + (unit >> 5)] = bits;
+    }
+}
+
+cudaError_t launch_tree_eval_multi(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
+                                   const bsg_expr_op* d_prog, const uint32_t* d_prog_begin, uint32_t n_queries,
+                                   uint32_t* d_masks32, uint64_t mask_words32, const uint32_t* d_bad32,
+                                   cudaStream_t s) {
+    if (n_units == 0 || n_queries == 0) return cudaSuccess;
+    const uint64_t n_blocks = (n_units + 255) / 256;
+    if (n_blocks > 0x7fffffffull || n_queries > 65535u) return cudaErrorInvalidValue;
+    tree_eval_multi_kernel<<<dim3(static_cast<uint32_t>(n_blocks), n_queries), 256, 0, s>>>(
+        d_matrix32, row_words32, n_units, d_prog, d_prog_begin, d_masks32, mask_words32, d_bad32);
+    return cudaGetLastError();
+}
+
 __global__ void fill_mask_kernel(uint32_t* __restrict__ mask32, uint64_t n_units) {
     const uint64_t w = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t n_words = (n_units + 31) / 32;

@@ -241,23 +241,23 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
         const uint8_t* data = st + a.hdr_bytes;
         // ---------------------------------------------------------------- round A ---
         if (warp_kinds & head.y) {
-            // the ballot words stay in registers (lane u keeps unit u's words) until the tile's units are done:
-            // no shared-memory traffic inside the loop, so consecutive keys / units overlap; then ONE atomic per
-            // warp per tile reserves the warp's range of L1
-            uint32_t my[KPT];
+            // every thread keeps, per key slot, the set of units whose first tests its key passed (bit u = unit u of
+            // the tile): one predicated OR per (key, unit), no ballot, no shared-memory traffic inside the loop, so
+            // consecutive units overlap; then ONE warp scan + ONE atomic per warp per tile reserve the warp's range
+            // of L1 and every thread appends its own few survivors (L1's order is free)
+            uint32_t umask[KPT];
 #pragma unroll
-            for (int j = 0; j < KPT; ++j) my[j] = 0;
+            for (int j = 0; j < KPT; ++j) umask[j] = 0;
             auto unit_loop = [&](auto small_k) {
                 constexpr bool SMALLK = decltype(small_k)::value;
                 const uint8_t* desc = st + kTileDescOff;
+                uint32_t ubit = 1u;
 #pragma unroll 2
-                for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
-                    bool pass[KPT];
+                for (uint32_t u = 0; u < head.x; ++u, desc += 48, ubit <<= 1) {
 #pragma unroll
                     for (int j = 0; j < KPT; ++j) {
-                        // a key slot of a kind this tile does not carry reads an all-zero descriptor (m == 0: nothing
-                        // is loaded) and is masked out below; no zero-filled copy of the descriptor is needed
-                        const bool act = (kbit[j] & head.y) != 0;
+                        // a key slot of a kind this tile does not carry reads an absent-filter record (see
+                        // TileFilter) and is masked out after the loop
                         const uint4 f = *reinterpret_cast<const uint4*>(desc + koff[j]);
                         // absent filter (k == 0, encoded as m = 1 at offset 0 so that the loads below need no
                         // predicate): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
@@ -270,45 +270,40 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
                         uint32_t p = 1u;
 #pragma unroll
                         for (int t = 0; t < NT; ++t) {
-                            uint32_t b = (wv[t] >> (bit[t] & 31u)) & 1u;
+                            uint32_t b = wv[t] >> (bit[t] & 31u);
                             if (SMALLK) b |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
                             p &= b;
                         }
-                        pass[j] = act && (tile_k(f.w) == 0u || p != 0u);
-                    }
-#pragma unroll
-                    for (int j = 0; j < KPT; ++j) {
-                        const uint32_t bits = __ballot_sync(0xffffffffu, pass[j]);
-                        if (lane == u) my[j] = bits;
+                        if (tile_k(f.w) == 0u || (p & 1u) != 0u) umask[j] |= ubit;
                     }
                 }
             };
             if (head.z & kTileSmallK) unit_loop(std::true_type{});
             else unit_loop(std::false_type{});
-            // append: lane u knows how many of unit u's keys survived in this warp
             uint32_t mine = 0;
 #pragma unroll
-            for (int j = 0; j < KPT; ++j) mine += __popc(my[j]);
+            for (int j = 0; j < KPT; ++j) {
+                if ((kbit[j] & head.y) == 0) umask[j] = 0;   // not a key of this tile's kinds (or no key at all)
+                mine += __popc(umask[j]);
+            }
             uint32_t incl = mine;
 #pragma unroll
-            for (int d = 1; d < static_cast<int>(kTileMaxUnits); d <<= 1) {
+            for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= static_cast<uint32_t>(d)) incl += v;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, kTileMaxUnits - 1);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&cnt[0], total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const uint32_t excl = base + incl - mine;
-                for (uint32_t u = 0; u < head.x; ++u) {
-                    uint32_t off_u = __shfl_sync(0xffffffffu, excl, u);
+                uint32_t off = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
 #pragma unroll
-                    for (int j = 0; j < KPT; ++j) {
-                        const uint32_t w = __shfl_sync(0xffffffffu, my[j], u);
-                        if ((w >> lane) & 1u)
-                            L1[off_u + __popc(w & lt_mask)] = static_cast<uint16_t>((u << 10) | (tid + j * NTHR));
-                        off_u += __popc(w);
+                for (int j = 0; j < KPT; ++j) {
+                    uint32_t mk = umask[j];
+                    while (mk) {
+                        const uint32_t u = static_cast<uint32_t>(__ffs(static_cast<int>(mk))) - 1u;
+                        mk &= mk - 1u;
+                        L1[off++] = static_cast<uint16_t>((u << 10) | (tid + j * NTHR));
                     }
                 }
             }
@@ -407,382 +402,48 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same three rounds, SOFTWARE PIPELINED across tiles: in iteration j every warp runs
-//     OUT(j-3)  rows of tile j-3 to HBM, its ring slot refilled      (needs: round B2 of tile j-3 done by all)
-//     B2(j-2)   second survivor list of tile j-2                       (needs: round B1 of tile j-2 done by all)
-//     B1(j-1)   first survivor list of tile j-1                        (needs: round A  of tile j-1 done by all)
-//     A(j)      first NT tests of every key against tile j
-// and each "done by all" is an mbarrier (XA / XB / XC, one arrival per warp) whose phase completed an
-// iteration earlier, so a warp practically never waits for its siblings: the CTA barriers of the lock-step
-// kernel (25 % of all warp time on the flush-shaped layout) and its four serial latencies per tile (what kept it
-// above the HBM time per tile on the merged layout) are gone.  The survivor lists are double buffered with
-// counters that only grow (a warp learns a buffer's base when it consumes it two tiles earlier), the result
-// rows live in a ring of 8 buffers, a tile's unit ids are copied to a small table in round A because its ring
-// slot is refilled in OUT while other warps may still be writing rows.  Chunks of the lists are dealt to
-// the warps starting at warp (tile mod 32), so the sparse B rounds do not always land on the same warps.
-// Needs a ring of >= 4 stages (a slot is held for three iterations after its round A).
-constexpr uint32_t kPipeRowBufs = 8;
-constexpr uint32_t kPipeXOff = 128;      // XA, XB, XC mbarriers
-constexpr uint32_t kPipeCntOff = 192;    // cnt1[2], cnt2[2]
-
-template <int NT, bool TRACE>
-__global__ void __launch_bounds__(1024, 1) probe_pipe_kernel(const ProbeTilesArgs a) {
-    static_assert(NT >= 1 && NT <= 4, "shape");
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* XA = reinterpret_cast<uint64_t*>(smem + kPipeXOff);
-    uint64_t* XB = XA + 1;
-    uint64_t* XC = XA + 2;
-    uint32_t* cnt1 = reinterpret_cast<uint32_t*>(smem + kPipeCntOff);
-    uint32_t* cnt2 = cnt1 + 2;
-    uint16_t* s_slot = reinterpret_cast<uint16_t*>(smem + kTilesPrefixBytes);
-    uint32_t* meta = reinterpret_cast<uint32_t*>(smem + kTilesPrefixBytes + kTilesSlotInfoBytes);   // [8 tiles][16]
-    uint32_t* rows = meta + kPipeRowBufs * 16;                                                       // [8 tiles][units_cap * 32]
-    const uint32_t row_stride = a.units_cap * 32u;
-    const uint32_t list_cap = a.units_cap * kProbeMaxKeysPerPass;
-    uint16_t* L1 = reinterpret_cast<uint16_t*>(rows + kPipeRowBufs * row_stride);                    // [2][list_cap]
-    uint16_t* L2 = L1 + 2 * list_cap;                                                                // [2][list_cap]
-    ulonglong2* htab = reinterpret_cast<ulonglong2*>(L2 + 2 * list_cap);
-    const uint32_t hash_bytes = ((a.n_keys + 31u) & ~31u) * 32u;
-    uint8_t* stages = reinterpret_cast<uint8_t*>(htab) + hash_bytes;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31;
-    const uint32_t warp = tid >> 5;
-    const uint32_t G = gridDim.x;
-    const uint32_t S = a.n_stages;
-    const uint32_t P = a.parts;
-    uint64_t* tr = (TRACE && a.trace) ? a.trace + static_cast<size_t>(blockIdx.x) * a.trace_slots : nullptr;
-    if (TRACE && tr && tid == 0) tr[0] = globaltimer_ns();
-
-    if (tid == 0) {
-        for (uint32_t s = 0; s < S; ++s) mbar_init(&full[s], 1);
-        mbar_init(XA, 32);
-        mbar_init(XB, 32);
-        mbar_init(XC, 32);
-        cnt1[0] = cnt1[1] = cnt2[0] = cnt2[1] = 0;
-        fence_barrier_init();
-    }
-    for (uint32_t i = tid; i < kPipeRowBufs * row_stride; i += blockDim.x) rows[i] = 0;
-    __syncthreads();
-
-    if (a.n_items_dev) griddep_wait();
-    const uint32_t n_items = a.n_items_dev ? __ldg(a.n_items_dev) : a.n_items_host;
-    const uint32_t my_items = n_items > blockIdx.x ? (n_items - blockIdx.x + G - 1) / G : 0;
-    const uint32_t my_tiles = my_items * P;
-    auto rec_of = [&](uint32_t n) -> const TileRec* {
-        const uint32_t item = blockIdx.x + (P == 1 ? n : (n >> 1)) * G;
-        return a.tiles + (P == 1 ? item : item * 2u + (n & 1u));
-    };
-    if (warp == 0 && lane < S && lane < my_tiles) {  // prologue: lane l fills stage l with tile l
-        const TileRec* r = rec_of(lane);
-        const uint4* fp = reinterpret_cast<const uint4*>(&r->fill);
-        const uint4 f0 = __ldg(fp);
-        uint16_t nb16[kTileMaxUnits * 3] = {};
-        if (a.kind_mask != 7u) {
-            const uint4 q1 = __ldg(fp + 1), q2 = __ldg(fp + 2), q3 = __ldg(fp + 3);
-            const uint32_t w[12] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-#pragma unroll
-            for (int i = 0; i < 12; ++i) { nb16[2 * i] = static_cast<uint16_t>(w[i]); nb16[2 * i + 1] = static_cast<uint16_t>(w[i] >> 16); }
-        }
-        const bool has_next = lane + S < my_tiles;
-        fill_tile(stages + static_cast<size_t>(lane) * a.stage_bytes, &full[lane], r, has_next,
-                  has_next ? rec_of(lane + S) : r, a.words, f0, nb16, a.kind_mask, a.hdr_bytes);
-    }
-    griddep_launch_dependents();
-    if (!a.n_items_dev) griddep_wait();
-
-    for (uint32_t t = tid; t < a.n_keys; t += blockDim.x) {   // the batch: slot table + base hashes (sorted-slot order)
-        const uint32_t si = __ldg(&a.slotinfo[a.key_base + t]);
-        s_slot[t] = static_cast<uint16_t>(si);
-        const uint32_t q = a.key_base + (si & 0x3ffu);
-        ulonglong2 h01, h23;
-        if (a.hashes) {
-            const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(a.hashes + 4ull * q);
-            h01 = __ldg(hp);
-            h23 = __ldg(hp + 1);
-        } else {
-            const uint64_t b = __ldg(&a.key_off[q]), e = __ldg(&a.key_off[q + 1]);
-            uint64_t h[4];
-            base_hashes(a.key_bytes + b, static_cast<uint32_t>(e - b), h);
-            h01 = make_ulonglong2(h[0], h[1]);
-            h23 = make_ulonglong2(h[2], h[3]);
-        }
-        htab[2 * t] = h01;
-        htab[2 * t + 1] = h23;
-    }
-    __syncthreads();
-    if (TRACE && tr && tid == 0) tr[1] = globaltimer_ns();
-
-    uint64_t loc[NT];
-    uint32_t koff = 0, kbit = 0;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) loc[t] = 0;
-    if (tid < a.n_keys) {
-        const ulonglong2 x = htab[2 * tid], y = htab[2 * tid + 1];
-        const uint64_t l4[4] = {x.x, x.y + y.y, x.x + 2 * y.y, x.y + 3 * y.x};
-#pragma unroll
-        for (int t = 0; t < NT; ++t) loc[t] = l4[t];
-        const uint32_t kind = s_slot[tid] >> 14;
-        koff = kind * 16u;
-        kbit = 1u << kind;
-    }
-    const uint32_t warp_kinds = __reduce_or_sync(0xffffffffu, kbit);
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t out_words = min(32u, a.row_words32 - (a.key_base >> 5));
-    uint32_t* out_base = a.matrix32 + (a.key_base >> 5);
-
-    uint32_t base1_0 = 0, base1_1 = 0, base2_0 = 0, base2_1 = 0;   // list counters at the start of a buffer's current use
-    uint32_t sA = 0, phA = 0;                          // ring slot / fill parity of the tile of round A
-    uint32_t s1 = 0, s2 = 0, s3 = 0;                   // ring slots of tiles j-1, j-2, j-3
-    for (uint32_t j = 0; j < my_tiles + 3; ++j) {
-        // ------------------------------------------------------------------ OUT(j-3) ---
-        if (j >= 3 && j - 3 < my_tiles) {
-            const uint32_t t = j - 3;
-            mbar_wait(XC, t & 1u);                     // every warp is done with round B2 of tile t (and with its stage)
-            const uint32_t* mt = meta + (t & 7u) * 16u;
-            const uint32_t n_units = mt[0], flags = mt[1];
-            if ((flags & kTileLastPart) && warp < n_units) {
-                uint32_t* r = rows + (t & 7u) * row_stride + warp * 32u;
-                uint32_t v = r[lane];
-                r[lane] = 0;
-                if (!(flags & kTileFirstPart)) {       // KIND mode: the unit's first part was the previous tile
-                    uint32_t* r0 = rows + ((t - 1) & 7u) * row_stride + warp * 32u;
-                    v |= r0[lane];
-                    r0[lane] = 0;
-                }
-                if (lane < out_words) out_base[static_cast<size_t>(mt[2 + warp]) * a.row_words32 + lane] = v;
-            }
-            if (tid == 0) {                            // refill the slot with tile t + S
-                const uint32_t nxt = t + S;
-                if (nxt < my_tiles) {
-                    uint8_t* st3 = stages + static_cast<size_t>(s3) * a.stage_bytes;
-                    const uint4* fp = reinterpret_cast<const uint4*>(st3 + kTileNextFillOff);
-                    const uint4 f0 = fp[0];
-                    uint16_t nb16[kTileMaxUnits * 3] = {};
-                    if (a.kind_mask != 7u) {
-                        const uint16_t* src16 = reinterpret_cast<const uint16_t*>(st3 + kTileNextFillOff + 16);
-#pragma unroll
-                        for (int i = 0; i < static_cast<int>(kTileMaxUnits) * 3; ++i) nb16[i] = src16[i];
-                    }
-                    const bool has_next = nxt + S < my_tiles;
-                    fill_tile(st3, &full[s3], rec_of(nxt), has_next, has_next ? rec_of(nxt + S) : rec_of(nxt), a.words, f0,
-                              nb16, a.kind_mask, a.hdr_bytes);
-                }
-            }
-        }
-        // ------------------------------------------------------------------- B2(j-2) ---
-        if (j >= 2 && j - 2 < my_tiles) {
-            const uint32_t t = j - 2, b = t & 1u;
-            mbar_wait(XB, t & 1u);                     // every warp is done with round B1 of tile t: L2[b] is complete
-            const uint32_t c = ld_volatile_shared_u32(&cnt2[b]);
-            const uint32_t n2 = c - (b ? base2_1 : base2_0);
-            if (b) base2_1 = c; else base2_0 = c;
-            const uint8_t* st2 = stages + static_cast<size_t>(s2) * a.stage_bytes;
-            const uint8_t* data = st2 + a.hdr_bytes;
-            const uint16_t* l2 = L2 + b * list_cap;
-            uint32_t* r = rows + (t & 7u) * row_stride;
-            for (uint32_t e = (((warp + t) & 31u) << 5) + lane; e < n2; e += blockDim.x) {
-                const uint32_t entry = l2[e];
-                const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
-                const uint32_t si = s_slot[slot];
-                const uint4 f = *reinterpret_cast<const uint4*>(st2 + kTileDescOff + u * 48u + (si >> 14) * 16u);
-                const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, tile_k(f.w),
-                                          reinterpret_cast<const uint32_t*>(data + tile_rel(f.w)))) {
-                    const uint32_t pos = si & 0x3ffu;
-                    atomicOr(&r[u * 32u + (pos >> 5)], 1u << (pos & 31u));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(XC);
-        }
-        // ------------------------------------------------------------------- B1(j-1) ---
-        if (j >= 1 && j - 1 < my_tiles) {
-            const uint32_t t = j - 1, b = t & 1u;
-            mbar_wait(XA, t & 1u);                     // every warp is done with round A of tile t: L1[b] is complete
-            const uint32_t c = ld_volatile_shared_u32(&cnt1[b]);
-            const uint32_t n1 = c - (b ? base1_1 : base1_0);
-            if (b) base1_1 = c; else base1_0 = c;
-            const uint8_t* st1 = stages + static_cast<size_t>(s1) * a.stage_bytes;
-            const uint8_t* data = st1 + a.hdr_bytes;
-            const uint16_t* l1 = L1 + b * list_cap;
-            uint16_t* l2 = L2 + b * list_cap;
-            uint32_t* r = rows + (t & 7u) * row_stride;
-            for (uint32_t e0 = ((warp + t) & 31u) << 5; e0 < n1; e0 += blockDim.x) {
-                const uint32_t e = e0 + lane;
-                bool more = false;
-                uint32_t entry = 0;
-                if (e < n1) {
-                    entry = l1[e];
-                    const uint32_t u = entry >> 10, slot = entry & 0x3ffu;
-                    const uint32_t si = s_slot[slot];
-                    const uint4 f = *reinterpret_cast<const uint4*>(st1 + kTileDescOff + u * 48u + (si >> 14) * 16u);
-                    const uint32_t k = tile_k(f.w);
-                    bool fin = k <= static_cast<uint32_t>(NT);   // absent filter (k == 0), or every location already passed
-                    if (!fin) {
-                        const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
-                        uint32_t ok = 1u;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {   // locations NT..NT+3
-                            const int i = NT + jj;
-                            const uint64_t aa = (i & 1) ? x.y : x.x;
-                            const uint64_t bb = (((i + (i & 1)) & 3) >> 1) ? y.y : y.x;
-                            const uint32_t bit = mod_m32(aa + static_cast<uint64_t>(i) * bb, f.x, f.y, f.z);
-                            ok &= ((w32[word_index(bit)] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(static_cast<uint32_t>(i) >= k);
-                        }
-                        fin = ok != 0u && k <= static_cast<uint32_t>(NT + 4);
-                        more = ok != 0u && !fin;
-                    }
-                    if (fin) {
-                        const uint32_t pos = si & 0x3ffu;
-                        atomicOr(&r[u * 32u + (pos >> 5)], 1u << (pos & 31u));
-                    }
-                }
-                const uint32_t bits = __ballot_sync(0xffffffffu, more);
-                if (bits) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&cnt2[b], static_cast<uint32_t>(__popc(bits)));
-                    base = __shfl_sync(0xffffffffu, base, 0) - (b ? base2_1 : base2_0);
-                    if (more) l2[base + __popc(bits & lt_mask)] = static_cast<uint16_t>(entry);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(XB);
-        }
-        // --------------------------------------------------------------------- A(j) ---
-        if (j < my_tiles) {
-            uint8_t* st = stages + static_cast<size_t>(sA) * a.stage_bytes;
-            mbar_wait(&full[sA], phA);
-            if (TRACE && tr && tid == 0 && 2 + 4 * j + 3 < a.trace_slots) tr[2 + 4 * j] = globaltimer_ns();
-            const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
-            if (warp == 0 && lane < 2 + kTileMaxUnits) {             // what OUT needs after the slot was refilled
-                const uint32_t v = lane == 0 ? head.x : lane == 1 ? head.z : *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * (lane - 2));
-                meta[(j & 7u) * 16u + lane] = v;
-            }
-            const uint8_t* data = st + a.hdr_bytes;
-            const uint32_t b = j & 1u;
-            if (warp_kinds & head.y) {
-                const bool act = (kbit & head.y) != 0;
-                uint32_t my = 0;
-                auto unit_loop = [&](auto small_k) {
-                    constexpr bool SMALLK = decltype(small_k)::value;
-                    const uint8_t* desc = st + kTileDescOff + koff;
-#pragma unroll 2
-                    for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
-                        const uint4 f = *reinterpret_cast<const uint4*>(desc);
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
-                        uint32_t bit[NT], wv[NT];
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) wv[t] = w32[word_index(bit[t])];
-                        uint32_t p = 1u;
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            uint32_t bb = (wv[t] >> (bit[t] & 31u)) & 1u;
-                            if (SMALLK) bb |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
-                            p &= bb;
-                        }
-                        const bool pass = act && (tile_k(f.w) == 0u || p != 0u);   // absent filter: survives to round B1
-                        const uint32_t bits = __ballot_sync(0xffffffffu, pass);
-                        if (lane == u) my = bits;
-                    }
-                };
-                if (head.z & kTileSmallK) unit_loop(std::true_type{});
-                else unit_loop(std::false_type{});
-                const uint32_t mine = __popc(my);
-                uint32_t incl = mine;
-#pragma unroll
-                for (int d = 1; d < static_cast<int>(kTileMaxUnits); d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= static_cast<uint32_t>(d)) incl += v;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, kTileMaxUnits - 1);
-                if (total) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&cnt1[b], total);
-                    base = __shfl_sync(0xffffffffu, base, 0) - (b ? base1_1 : base1_0);
-                    const uint32_t excl = base + incl - mine;
-                    uint16_t* l1 = L1 + b * list_cap;
-                    for (uint32_t u = 0; u < head.x; ++u) {
-                        const uint32_t off_u = __shfl_sync(0xffffffffu, excl, u);
-                        const uint32_t w = __shfl_sync(0xffffffffu, my, u);
-                        if ((w >> lane) & 1u) l1[off_u + __popc(w & lt_mask)] = static_cast<uint16_t>((u << 10) | tid);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(XA);
-            if (TRACE && tr && tid == 0 && 2 + 4 * j + 3 < a.trace_slots) tr[3 + 4 * j] = globaltimer_ns();
-        }
-        s3 = s2;
-        s2 = s1;
-        s1 = sA;
-        if (++sA == S) { sA = 0; phA ^= 1u; }
-        if (TRACE && tr && tid == 0 && 2 + 4 * j + 3 < a.trace_slots) tr[4 + 4 * j] = globaltimer_ns();
-    }
-}
-
-// ---- compiled shapes: <tests of round A, threads per CTA (1024 / threads CTAs share an SM), pipelined> ----
-#define BSG_TILES_SHAPES(X) \
-    X(0, 3, 512, 0) X(1, 3, 1024, 0) X(2, 2, 512, 0) X(3, 2, 1024, 0) X(4, 4, 512, 0) X(5, 3, 1024, 1) X(6, 2, 1024, 1)
+// ---- compiled shapes: <tests of round A, threads per CTA> (1024 / threads CTAs share an SM) ----
+// (a software-pipelined variant of the same rounds — mbarrier hand-offs instead of CTA barriers, double-buffered
+// lists, ring of >= 5 stages — measured 16 % slower on both layouts and was removed; profiles/r02_kernel_experiments.txt)
+#define BSG_TILES_SHAPES(X) X(0, 3, 512) X(1, 3, 1024) X(2, 2, 512) X(3, 2, 1024) X(4, 4, 512)
 
 int probe_tiles_n_shapes() {
     int n = 0;
-#define X(id, nt, thr, pipe) ++n;
+#define X(id, nt, thr) ++n;
     BSG_TILES_SHAPES(X)
 #undef X
     return n;
 }
 int probe_tiles_threads(int shape) {
     switch (shape) {
-#define X(id, nt, thr, pipe) case id: return thr;
+#define X(id, nt, thr) case id: return thr;
         BSG_TILES_SHAPES(X)
 #undef X
         default: return 1024;
     }
 }
-int probe_tiles_pipelined(int shape) {
-    switch (shape) {
-#define X(id, nt, thr, pipe) case id: return pipe;
-        BSG_TILES_SHAPES(X)
-#undef X
-        default: return 0;
-    }
-}
 const char* probe_tiles_shape_name(int shape) {
     switch (shape) {
-#define X(id, nt, thr, pipe) case id: return pipe ? "probe_pipe_kernel<NT=" #nt ">" : "probe_tiles_kernel<NT=" #nt "," #thr " threads>";
+#define X(id, nt, thr) case id: return "probe_tiles_kernel<NT=" #nt "," #thr " threads>";
         BSG_TILES_SHAPES(X)
 #undef X
         default: return "probe_tiles_kernel<?>";
     }
 }
 
-template <int NT, int NTHR, int PIPE, bool TRACE>
-struct TilesKernel {
-    static auto get() {
-        if constexpr (PIPE) return probe_pipe_kernel<NT, TRACE>;
-        else return probe_tiles_kernel<NT, NTHR, TRACE>;
-    }
-};
-
 cudaError_t probe_tiles_configure(int max_smem_optin) {
     cudaError_t e = cudaSuccess;
-#define X(id, nt, thr, pipe)                                                                                              \
-    e = cudaFuncSetAttribute(TilesKernel<nt, thr, pipe, false>::get(), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin); \
+#define X(id, nt, thr)                                                                                              \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, thr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin); \
     if (e != cudaSuccess) return e;                                                                                       \
-    e = cudaFuncSetAttribute(TilesKernel<nt, thr, pipe, true>::get(), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);  \
+    e = cudaFuncSetAttribute(probe_tiles_kernel<nt, thr, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);  \
     if (e != cudaSuccess) return e;
     BSG_TILES_SHAPES(X)
 #undef X
     return e;
 }
 
-template <int NT, int NTHR, int PIPE>
+template <int NT, int NTHR>
 static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs& args, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
@@ -794,8 +455,8 @@ static cudaError_t tiles_launch(const ProbeTilesPlan& plan, const ProbeTilesArgs
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = plan.pdl ? 1 : 0;
-    if (args.trace) return cudaLaunchKernelEx(&cfg, TilesKernel<NT, NTHR, PIPE, true>::get(), args);
-    return cudaLaunchKernelEx(&cfg, TilesKernel<NT, NTHR, PIPE, false>::get(), args);
+    if (args.trace) return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, NTHR, true>, args);
+    return cudaLaunchKernelEx(&cfg, probe_tiles_kernel<NT, NTHR, false>, args);
 }
 
 cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tiles, uint32_t n_items,
@@ -827,7 +488,7 @@ cudaError_t launch_probe_tiles(const ProbeTilesPlan& plan, const TileRec* d_tile
     a.trace = d_trace;
     a.trace_slots = d_trace ? trace_slots : 0;
     switch (plan.shape) {
-#define X(id, nt, thr, pipe) case id: return tiles_launch<nt, thr, pipe>(plan, a, s);
+#define X(id, nt, thr) case id: return tiles_launch<nt, thr>(plan, a, s);
         BSG_TILES_SHAPES(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -404,6 +404,17 @@ class Corpus:
         N.check(N.lib().bsg_probe(self.ctx.handle, self._h, N.ptr(blob), N.ptr(off), len(off) - 1, N.ptr(kinds), pp, pl,
                                   N.ptr(out_matrix), N.ptr(out_mask)))
 
+    def probe_multi(self, queries: Sequence[Optional[BloomQuery]]) -> np.ndarray:
+        """bsg_probe_multi: several BloomQueries in one pass over the corpus -> bool[n_queries][n_units], row j
+        identical to evaluate_bloom_filters(queries[j])."""
+        cqs = [compile_bloom_query(q) for q in queries]
+        blob, off, kinds, qbegin, progs, pbegin = pack_queries(cqs)
+        words = (self.n_units + 63) // 64
+        out = np.zeros((len(cqs), max(words, 1)), dtype=np.uint64)
+        N.check(N.lib().bsg_probe_multi(self.ctx.handle, self._h, N.ptr(blob), N.ptr(off), len(off) - 1, N.ptr(kinds),
+                                        len(cqs), N.ptr(qbegin), N.ptr(progs), N.ptr(pbegin), N.ptr(out)))
+        return np.stack([unpack_mask(out[j], self.n_units) for j in range(len(cqs))]) if cqs else np.zeros((0, self.n_units), bool)
+
     def set_parents(self, parent: np.ndarray, n_parent_units: int) -> None:
         """Record, for every unit (block), the index of its parent unit (file) in another corpus."""
         parent = np.ascontiguousarray(parent, dtype=np.uint32)
@@ -414,6 +425,66 @@ class Corpus:
         cq = compile_bloom_query(query)
         _, mask = self.probe(cq.keys, cq.kinds, cq.prog, want_matrix=False)
         return unpack_mask(mask, self.n_units)
+
+
+def pack_queries(cqs):
+    """CompiledQuery list -> the packed arrays of bsg_probe_multi (keys of all queries back to back, CSR of keys and
+    of postfix ops per query; leaf arguments stay query-local)."""
+    keys, kinds, qbegin, pbegin, ops = [], [], [0], [0], []
+    for cq in cqs:
+        keys.extend(cq.keys)
+        kinds.extend(int(k) for k in cq.kinds)
+        qbegin.append(len(keys))
+        if cq.prog is not None:
+            ops.append(np.ascontiguousarray(cq.prog, N.OP_DTYPE))
+        pbegin.append(pbegin[-1] + (0 if cq.prog is None else len(cq.prog)))
+    blob, off = N.pack_keys(keys)
+    progs = np.concatenate(ops) if ops else np.zeros(1, N.OP_DTYPE)
+    return (blob, off, np.array(kinds if kinds else [0], dtype=np.uint8), np.array(qbegin, dtype=np.uint32),
+            np.ascontiguousarray(progs, N.OP_DTYPE), np.array(pbegin, dtype=np.uint32))
+
+
+class Batcher:
+    """bsg_batcher: merges concurrent evaluate() callers on one corpus into bsg_probe_multi launches (group commit).
+    Thread-safe; ctypes releases the GIL for the duration of the call, so Python threads really overlap."""
+
+    def __init__(self, corpus: "Corpus", max_keys: int = 0, max_queries: int = 0, window_us: int = 0):
+        self.corpus = corpus
+        h = C.c_void_p()
+        N.check(N.lib().bsg_batcher_create(corpus.ctx.handle, corpus.handle, max_keys, max_queries, window_us, C.byref(h)))
+        self._h = h
+
+    def evaluate_packed(self, blob, off, kinds, prog, out_mask) -> None:
+        pp, pl = (None, 0) if prog is None else (N.ptr(prog), len(prog))
+        N.check(N.lib().bsg_batcher_probe(self._h, N.ptr(blob), N.ptr(off), len(off) - 1, N.ptr(kinds), pp, pl,
+                                          N.ptr(out_mask)))
+
+    def evaluate(self, query: Optional[BloomQuery]) -> np.ndarray:
+        """evaluateBloomFilters (query_exec.go:75-87) for every unit -> bool[n_units]; may share its launch with
+        other threads' queries."""
+        cq = compile_bloom_query(query)
+        blob, off = N.pack_keys(list(cq.keys))
+        kinds = np.ascontiguousarray(cq.kinds if len(cq.keys) else [0], dtype=np.uint8)
+        prog = None if cq.prog is None else np.ascontiguousarray(cq.prog, N.OP_DTYPE)
+        mask = np.zeros(max((self.corpus.n_units + 63) // 64, 1), dtype=np.uint64)
+        self.evaluate_packed(blob, off, kinds, prog, mask)
+        return unpack_mask(mask, self.corpus.n_units)
+
+    def stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        N.check(N.lib().bsg_batcher_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("calls", "launches", "bypassed", "largest_batch"), (int(x.value) for x in v)))
+
+    def close(self):
+        if self._h:
+            N.lib().bsg_batcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class FilterCache:

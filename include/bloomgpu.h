@@ -244,6 +244,35 @@ int bsg_probe(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys, const
               uint32_t n_keys, const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len,
               uint64_t *out_matrix, uint64_t *out_mask);
 
+/* Several queries in one call.  The keys of all queries are packed as for bsg_probe;
+ * query j owns keys [query_key_begin[j], query_key_begin[j+1]) and the postfix program
+ * progs[prog_begin[j] .. prog_begin[j+1]), whose LEAF arguments index ITS OWN keys (0-based); an empty
+ * program keeps every unit (query_exec.go:81-83).  The corpus is probed ONCE for the union of the keys (one
+ * pass per 1 024 keys: the staged kernels stream every filter byte once per pass whatever the number of
+ * keys), then every query's expression is evaluated on its own columns.  out_masks: n_queries rows of
+ * ceil(n_units/64) words, bit u of row j = unit u survives query j — identical to n_queries separate
+ * bsg_probe calls.  Replaces n_queries executions of query_exec.go:572-615 over the same blocks. */
+int bsg_probe_multi(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys, const uint64_t *key_off,
+                    uint32_t n_keys, const uint8_t *key_kind, uint32_t n_queries,
+                    const uint32_t *query_key_begin, const bsg_expr_op *progs, const uint32_t *prog_begin,
+                    uint64_t *out_masks);
+
+/* Query batcher: merges CONCURRENT bsg_batcher_probe callers (one goroutine per query in the reference,
+ * query_exec.go:201-433) into bsg_probe_multi launches.  Group commit: a caller that finds no launch in
+ * flight launches at once; callers that arrive while one is running form the next batch (closed at max_keys
+ * keys / max_queries queries, 0 = defaults 1024 / 256; later arrivals open another), launched when the running
+ * one ends.  window_us > 0 additionally lets the first caller of a batch wait that long for company.  Blocking and
+ * thread-safe; each caller gets exactly the mask bsg_probe would have returned; a member whose program is
+ * malformed fails alone.  The corpus must outlive the batcher (pin it in the cache). */
+typedef struct bsg_batcher bsg_batcher;
+int bsg_batcher_create(bsg_ctx *ctx, const bsg_corpus *corpus, uint32_t max_keys, uint32_t max_queries,
+                       uint32_t window_us, bsg_batcher **out);
+void bsg_batcher_destroy(bsg_batcher *batcher);
+int bsg_batcher_probe(bsg_batcher *batcher, const uint8_t *keys, const uint64_t *key_off, uint32_t n_keys,
+                      const uint8_t *key_kind, const bsg_expr_op *prog, uint32_t prog_len, uint64_t *out_mask);
+int bsg_batcher_stats(bsg_batcher *batcher, uint64_t *calls, uint64_t *launches, uint64_t *bypassed,
+                      uint64_t *largest_batch);
+
 /* Hierarchical probe — the reference's two stages in one call: file-level filters first
  * (query_exec.go:399-406), then block-level filters only for blocks whose file survived
  * (query_exec.go:572-615); the surviving units are compacted on the device between the stages.

@@ -921,7 +921,7 @@ def _tiles_case(monkeypatch, env, n_units, key_kinds=(0, 1, 2), big=False, n_key
         c2.close()
 
 
-@pytest.mark.parametrize("shape", range(7))
+@pytest.mark.parametrize("shape", range(5))
 def test_probe_tiles_every_shape(shape, monkeypatch):
     _tiles_case(monkeypatch, {"BSG_TILES_SHAPE": shape}, 700)
 
@@ -936,12 +936,9 @@ def test_probe_tiles_every_shape(shape, monkeypatch):
     ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1, "BSG_TILE_MIN_STAGES": 2, "BSG_TILES_SHAPE": 2}, 300),
     ({"BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 1}, 450),
     ({"BSG_PROBE_PDL": 0}, 300),
-    # the pipelined kernel (shapes 5, 6): ring of exactly 4 stages, long rings, KIND mode, one unit per tile
-    ({"BSG_TILES_SHAPE": 5, "BSG_PROBE_STAGES": 4}, 900),
-    ({"BSG_TILES_SHAPE": 5, "BSG_TILE_MODE": 2}, 700),
-    ({"BSG_TILES_SHAPE": 6, "BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 5}, 450),
-    ({"BSG_TILES_SHAPE": 5, "BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 1}, 1300),
-    ({"BSG_TILES_SHAPE": 6, "BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 3, "BSG_TILE_BYTES": 9000}, 2000),
+    ({"BSG_TILES_SHAPE": 3, "BSG_PROBE_STAGES": 4}, 900),
+    ({"BSG_TILES_SHAPE": 0, "BSG_TILE_MODE": 2, "BSG_PROBE_STAGES": 5}, 450),
+    ({"BSG_TILES_SHAPE": 4, "BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 3, "BSG_TILE_BYTES": 9000}, 2000),
 ])
 def test_probe_tiles_modes_groupings_rings(env, n_units, monkeypatch):
     _tiles_case(monkeypatch, env, n_units)
@@ -1062,3 +1059,149 @@ def test_bsg_probe_into_pinned_caller_buffer(ctx):
         assert np.array_equal(out, want), f"n_keys {n_keys}"
     corpus.close()
     ctx.host_free(buf)
+
+
+# ------------------------------------------------- query batching (§8 f.4) ---
+def _random_queries(rng, unit_keys, n):
+    """Small BloomQueries in the shapes the reference's tests use (bloom_tree_engine_test.go:357-442): single
+    conditions, AND / OR of a few conditions with present and absent keys, nested, nil."""
+    def cond():
+        u = rng.randrange(len(unit_keys))
+        kind = rng.randrange(3)
+        pool = unit_keys[u][kind]
+        key = rng.choice(pool) if (pool and rng.random() < 0.6) else b"nope%d" % rng.randrange(1000)
+        if kind == 0:
+            return bs.Field(key)
+        if kind == 1:
+            return bs.Token(key)
+        f, _, t = key.partition(b"::")     # the fixture's fieldtoken keys are field + "::" + token (tokenizer.go:508-511)
+        return bs.FieldToken(f, t)
+    out = []
+    for i in range(n):
+        r = rng.random()
+        if r < 0.05:
+            out.append(None)
+        elif r < 0.3:
+            out.append(bs.BloomQuery(cond()))
+        elif r < 0.6:
+            out.append(bs.BloomQuery(bs.And(*[cond() for _ in range(rng.randint(2, 4))])))
+        elif r < 0.85:
+            out.append(bs.BloomQuery(bs.Or(*[cond() for _ in range(rng.randint(2, 5))])))
+        else:
+            out.append(bs.BloomQuery(bs.And(bs.Or(cond(), cond()), bs.Or(cond(), cond(), cond()), cond())))
+    return out
+
+
+def _multi_fixture(ctx, n_units=96, seed=31, corrupt=False):
+    rng = random.Random(seed)
+    unit_keys = [(rand_keys(rng, 5, 3, 8), rand_keys(rng, 120, 1, 10),
+                  sorted({a + b"::" + b for a, b in zip(rand_keys(rng, 110, 2, 8), rand_keys(rng, 110, 1, 9))}))
+                 for _ in range(n_units)]
+    desc, words = oracle_units(unit_keys, 0.01, absent={(3, 1), (7, 0), (7, 1), (7, 2)})
+    return rng, unit_keys, bs.Corpus(ctx, desc, words)
+
+
+def test_probe_multi_equals_separate_probes(ctx, monkeypatch):
+    """bsg_probe_multi: one pass for the union of the keys, one mask per query == n separate bsg_probe calls
+    (each of which is oracle-checked elsewhere), on both staged kernels and the gather path."""
+    for env in ({}, {"BSG_PROBE_VARIANT": "3"}, {"BSG_PROBE_VARIANT": "6"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c2 = bs.Context(0)
+        rng, unit_keys, corpus = _multi_fixture(c2)
+        for n in (1, 7, 130):   # 130 queries: > 1 024 keys in total -> two key passes
+            queries = _random_queries(rng, unit_keys, n)
+            got = corpus.probe_multi(queries)
+            want = np.stack([corpus.evaluate_bloom_filters(q) for q in queries])
+            assert got.shape == want.shape and np.array_equal(got, want), (env, n)
+        # only nil queries: no keys at all, every unit survives
+        assert corpus.probe_multi([None, None]).all()
+        corpus.close()
+        c2.close()
+        for k in env:
+            monkeypatch.delenv(k)
+
+
+def test_probe_multi_rejects_bad_programs(ctx):
+    rng, unit_keys, corpus = _multi_fixture(ctx, n_units=8)
+    blob, off = N.pack_keys([b"a", b"b"])
+    kinds = np.array([1, 1], np.uint8)
+    qbegin = np.array([0, 1, 2], np.uint32)
+    out = np.zeros((2, 1), np.uint64)
+    bad = np.array([(N.OP_LEAF, 0), (N.OP_LEAF, 1), (N.OP_AND, 2)], dtype=N.OP_DTYPE)   # query 0 has ONE key: leaf 1 is out of range
+    pbegin = np.array([0, 3, 3], np.uint32)
+    rc = N.lib().bsg_probe_multi(ctx.handle, corpus.handle, N.ptr(blob), N.ptr(off), 2, N.ptr(kinds), 2, N.ptr(qbegin),
+                                 N.ptr(bad), N.ptr(pbegin), N.ptr(out))
+    assert rc == N.ERR_INVALID
+    qbad = np.array([0, 2, 1], np.uint32)
+    rc = N.lib().bsg_probe_multi(ctx.handle, corpus.handle, N.ptr(blob), N.ptr(off), 2, N.ptr(kinds), 2, N.ptr(qbad),
+                                 N.ptr(bad), N.ptr(pbegin), N.ptr(out))
+    assert rc == N.ERR_INVALID
+    corpus.close()
+
+
+@pytest.mark.parametrize("window_us,max_keys", [(0, 0), (200, 0), (0, 16)])
+def test_batcher_concurrent_queries_share_launches(ctx, window_us, max_keys):
+    """bsg_batcher: 16 threads x 30 queries each; every caller gets exactly its own bsg_probe mask, and the
+    batcher needed fewer launches than calls (concurrent queries were merged)."""
+    import threading
+    rng, unit_keys, corpus = _multi_fixture(ctx, n_units=200, seed=5)
+    n_threads, per_thread = 16, 30
+    queries = [_random_queries(random.Random(100 + t), unit_keys, per_thread) for t in range(n_threads)]
+    want = [[corpus.evaluate_bloom_filters(q) for q in qs] for qs in queries]
+    batcher = bs.Batcher(corpus, max_keys=max_keys, window_us=window_us)
+    errors = []
+    barrier = threading.Barrier(n_threads)
+
+    def worker(t):
+        barrier.wait()
+        for i, q in enumerate(queries[t]):
+            got = batcher.evaluate(q)
+            if not np.array_equal(got, want[t][i]):
+                errors.append((t, i))
+                return
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    st = batcher.stats()
+    batcher.close()
+    corpus.close()
+    assert not errors, errors[:5]
+    assert st["calls"] == n_threads * per_thread
+    assert st["launches"] + st["bypassed"] <= st["calls"]
+    if max_keys == 0:
+        assert st["launches"] < st["calls"], st      # something was merged
+        assert st["largest_batch"] >= 2, st
+
+
+def test_batcher_bad_member_fails_alone(ctx):
+    import threading
+    rng, unit_keys, corpus = _multi_fixture(ctx, n_units=40, seed=9)
+    batcher = bs.Batcher(corpus, window_us=20000)     # a long window so the two callers share a batch
+    good = bs.BloomQuery(bs.Token(unit_keys[0][1][0]))
+    want = corpus.evaluate_bloom_filters(good)
+    res = {}
+
+    def ok():
+        res["good"] = batcher.evaluate(good)
+
+    def bad():
+        blob, off = N.pack_keys([b"x"])
+        prog = np.array([(N.OP_LEAF, 5)], dtype=N.OP_DTYPE)   # leaf out of range
+        try:
+            batcher.evaluate_packed(blob, off, np.array([1], np.uint8), prog, np.zeros(1, np.uint64))
+            res["bad"] = "no error"
+        except bs.BloomGpuError as e:
+            res["bad"] = e.code
+    ths = [threading.Thread(target=ok), threading.Thread(target=bad)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    batcher.close()
+    corpus.close()
+    assert res["bad"] == N.ERR_INVALID
+    assert np.array_equal(res["good"], want)
