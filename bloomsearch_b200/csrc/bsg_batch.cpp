@@ -17,6 +17,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bloomgpu.h"
@@ -40,6 +41,7 @@ struct Batch {
     std::vector<Req*> reqs;
     uint32_t n_keys = 0;
     bool closed = false;   // the leader took it: no more members
+    std::condition_variable done_cv;   // members sleep here: a finished launch wakes its own members only
 };
 }  // namespace
 
@@ -51,6 +53,7 @@ struct bsg_batcher {
     std::condition_variable cv;
     std::shared_ptr<Batch> open;   // the batch that accepts members (nullptr: none yet)
     uint32_t running = 0;          // launches in flight
+    uint32_t last_size = 1;        // members of the previous batch: how much company a leader may expect
     uint64_t n_calls = 0, n_launches = 0, n_bypass = 0, max_batch = 0;
     // leader scratch (one launch at a time touches it: guarded by `running`)
     std::vector<uint8_t> keys, kinds;
@@ -160,25 +163,41 @@ extern "C" int bsg_batcher_probe(bsg_batcher* b, const uint8_t* keys, const uint
     mine->reqs.push_back(&req);
     mine->n_keys += n_keys;
     if (!leader) {
-        if (mine->n_keys >= b->max_keys || mine->reqs.size() >= b->max_queries) b->cv.notify_all();  // full: wake the leader
-        b->cv.wait(lk, [&] { return req.done; });
+        if (b->window_us && (mine->n_keys >= b->max_keys || mine->reqs.size() >= b->max_queries)) b->cv.notify_all();  // full: wake the leader
+        mine->done_cv.wait(lk, [&] { return req.done; });
     } else {
         // group commit: launch when nothing is in flight; an optional window lets an idle system collect members
         auto full = [&] { return mine->n_keys >= b->max_keys || mine->reqs.size() >= b->max_queries; };
         if (b->window_us && !full())
             b->cv.wait_for(lk, std::chrono::microseconds(b->window_us), full);
         b->cv.wait(lk, [&] { return b->running == 0; });
+        // The members of the batch that just finished come back within microseconds of each other; the first one
+        // back would otherwise launch alone and make the rest wait a whole launch.  If the previous batch had
+        // company, give as many callers a few microseconds to arrive (bounded spin, lock released).
+        if (b->last_size > 1 && !full()) {
+            const uint32_t want = (b->last_size + 1) / 2;
+            const auto t0 = std::chrono::steady_clock::now();
+            while (mine->reqs.size() < want && !full() && b->running == 0 &&
+                   std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(25)) {
+                lk.unlock();
+                std::this_thread::yield();
+                lk.lock();
+            }
+            b->cv.wait(lk, [&] { return b->running == 0; });   // another leader may have slipped in meanwhile
+        }
         mine->closed = true;
         if (b->open == mine) b->open.reset();
         ++b->running;
         ++b->n_launches;
+        b->last_size = static_cast<uint32_t>(mine->reqs.size());
         if (mine->reqs.size() > b->max_batch) b->max_batch = mine->reqs.size();
         lk.unlock();
         run_batch(b, *mine);
         lk.lock();
         --b->running;
         for (Req* r : mine->reqs) r->done = true;
-        b->cv.notify_all();
+        mine->done_cv.notify_all();   // this batch's members
+        b->cv.notify_all();           // leaders waiting for the device (and bsg_batcher_destroy)
     }
     lk.unlock();
     if (req.rc != BSG_OK) return bsg_set_last_error_internal(req.rc, req.err.c_str());

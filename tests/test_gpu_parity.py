@@ -1172,8 +1172,8 @@ def test_batcher_concurrent_queries_share_launches(ctx, window_us, max_keys):
     assert not errors, errors[:5]
     assert st["calls"] == n_threads * per_thread
     assert st["launches"] + st["bypassed"] <= st["calls"]
-    if max_keys == 0:
-        assert st["launches"] < st["calls"], st      # something was merged
+    if window_us:   # with a window the callers certainly met (without one, short Python-driven calls may never overlap)
+        assert st["launches"] < st["calls"], st
         assert st["largest_batch"] >= 2, st
 
 
