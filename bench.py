@@ -446,25 +446,20 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
     e2e_calls = max(64, min(args.steps * 8, 400))
     m_words = (len(keys) + 63) // 64
 
-    pinned_outs = [ctx.host_alloc((n_units, m_words), np.uint64) for _ in range(args.e2e_callers)]
+    L.bsg_debug_probe_callers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
 
     def e2e_run(n_callers, calls_each, pinned=True):
-        # result buffers: pinned caller memory from bsg_host_alloc (the rows land in it directly), or plain
-        # pageable memory (one more 128 KB memcpy out of the library's pinned block)
-        outs = pinned_outs[:n_callers] if pinned else [np.zeros((n_units, m_words), dtype=np.uint64) for _ in range(n_callers)]
-
-        def worker(t):
-            for i in range(calls_each):
-                corpora[(t + i) % n_rep].probe_packed(blob, off, kinds, None, outs[t], None)
-        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_callers)]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        dt = time.perf_counter() - t0
-        assert np.array_equal(outs[0], got_m), "e2e matrix differs from the resident run"
-        return dt
+        # n_callers host threads (std::thread inside the library's measurement helper: what a Go host's goroutines
+        # produce, no interpreter lock between the calls), each calling bsg_probe() with host buffers into its own
+        # result buffer: pinned caller memory from bsg_host_alloc (the rows land in it directly) or plain pageable
+        # memory (one more 128 KB memcpy out of the library's pinned block)
+        outm = np.zeros((n_units, m_words), dtype=np.uint64)
+        sec = C.c_double()
+        N.check(L.bsg_debug_probe_callers(ctx.handle, cp_arr, n_rep, n_callers, calls_each, N.ptr(blob), N.ptr(off), len(keys),
+                                          N.ptr(kinds), 1 if pinned else 0, N.ptr(outm), C.byref(sec)))
+        assert np.array_equal(outm, got_m), "e2e matrix differs from the resident run"
+        return sec.value
 
     e2e_run(args.e2e_callers, 5)  # warm-up (scratch + pinned staging allocation)
     env.barrier()
@@ -472,8 +467,6 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
     env.barrier()
     dt_single = env.max(e2e_run(1, e2e_calls))
     dt_single_pageable = env.max(e2e_run(1, e2e_calls, pinned=False))
-    for b in pinned_outs:
-        ctx.host_free(b)
     per_call = env.sum(float(n_units * len(keys)))
     e2e = {"value": per_call * e2e_calls * args.e2e_callers / dt_multi, "unit": "probes/s",
            "h2d_bytes_per_step": int(blob.nbytes + off.nbytes + kinds.nbytes + 2 * len(keys)) * BATCHES_PER_STEP,

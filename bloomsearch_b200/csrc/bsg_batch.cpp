@@ -242,3 +242,51 @@ extern "C" int bsg_debug_query_callers(bsg_ctx* ctx, const bsg_corpus* corpus, b
     if (first_rc.load() != BSG_OK) return bsg_set_last_error_internal(first_rc.load(), "a caller thread failed");
     return BSG_OK;
 }
+
+// Same idea for the batch probe of the headline workload: n_threads host threads call bsg_probe(matrix out, no mask)
+// calls_each times, cycling over n_corpora resident replicas (so no call finds the filters in L2), each into its own
+// result buffer — pinned caller memory from bsg_host_alloc (pinned != 0) or plain pageable memory.  out_matrix
+// receives thread 0's last result.
+extern "C" int bsg_debug_probe_callers(bsg_ctx* ctx, const bsg_corpus* const* corpora, uint32_t n_corpora,
+                                       uint32_t n_threads, uint32_t calls_each, const uint8_t* keys,
+                                       const uint64_t* key_off, uint32_t n_keys, const uint8_t* kinds, int pinned,
+                                       uint64_t* out_matrix, double* seconds) {
+    if (!ctx || !corpora || n_corpora == 0 || !out_matrix || !seconds || n_threads == 0)
+        return bsg_set_last_error_internal(BSG_ERR_INVALID, "NULL argument");
+    const size_t words = static_cast<size_t>(bsg_corpus_units(corpora[0])) * ((n_keys + 63) / 64);
+    std::vector<uint64_t*> bufs(n_threads, nullptr);
+    std::vector<std::vector<uint64_t>> pageable;
+    if (pinned) {
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            void* p = nullptr;
+            const int rc = bsg_host_alloc(ctx, (words ? words : 1) * 8, &p);
+            if (rc != BSG_OK) { for (uint64_t* b : bufs) bsg_host_free(ctx, b); return rc; }
+            bufs[t] = static_cast<uint64_t*>(p);
+        }
+    } else {
+        pageable.assign(n_threads, std::vector<uint64_t>(words ? words : 1));
+        for (uint32_t t = 0; t < n_threads; ++t) bufs[t] = pageable[t].data();
+    }
+    std::atomic<uint32_t> ready{0};
+    std::atomic<bool> go{false};
+    std::atomic<int> first_rc{BSG_OK};
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t] {
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            for (uint32_t i = 0; i < calls_each; ++i) {
+                const int rc = bsg_probe(ctx, corpora[(t + i) % n_corpora], keys, key_off, n_keys, kinds, nullptr, 0, bufs[t], nullptr);
+                if (rc != BSG_OK) { int exp = BSG_OK; first_rc.compare_exchange_strong(exp, rc); return; }
+            }
+        });
+    while (ready.load() < n_threads) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto& x : th) x.join();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    memcpy(out_matrix, bufs[0], words * 8);
+    if (pinned) for (uint64_t* b : bufs) bsg_host_free(ctx, b);
+    if (first_rc.load() != BSG_OK) return bsg_set_last_error_internal(first_rc.load(), "a caller thread failed");
+    return BSG_OK;
+}
