@@ -91,10 +91,10 @@ struct bsg_ctx {
     int probe_variant = 7; // BSG_PROBE_VARIANT: 7 = per corpus (default, see staged_variant_for); 6 = probe_tiles; 0 = probe_staged
                            // (one phase); 1..5 = shapes of probe_staged2
     int tiles_shape = 1;   // BSG_TILES_SHAPE: compiled shape of probe_tiles_kernel (kernels_probe_tiles.cu)
-    int tile_bytes = 60000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
+    int tile_bytes = 80000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
-    int tile_min_stages = 3;  // BSG_TILE_MIN_STAGES: UNIT mode keeps units small enough for a ring of this many stages
+    int tile_min_stages = 2;  // BSG_TILE_MIN_STAGES: UNIT mode keeps units small enough for a ring of this many stages
     // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
 // ---- compiled shapes: <tests of round A, threads per CTA> (1024 / threads CTAs share an SM) ----
 // (a software-pipelined variant of the same rounds — mbarrier hand-offs instead of CTA barriers, double-buffered
 // lists, ring of >= 5 stages — measured 16 % slower on both layouts and was removed; profiles/r02_kernel_experiments.txt)
-#define BSG_TILES_SHAPES(X) X(0, 3, 512) X(1, 3, 1024) X(2, 2, 512) X(3, 2, 1024) X(4, 4, 512)
+#define BSG_TILES_SHAPES(X) X(0, 3, 512) X(1, 3, 1024) X(2, 2, 512) X(3, 2, 1024) X(4, 4, 512) X(5, 4, 1024)
 
 int probe_tiles_n_shapes() {
     int n = 0;

@@ -921,7 +921,7 @@ def _tiles_case(monkeypatch, env, n_units, key_kinds=(0, 1, 2), big=False, n_key
         c2.close()
 
 
-@pytest.mark.parametrize("shape", range(5))
+@pytest.mark.parametrize("shape", range(6))
 def test_probe_tiles_every_shape(shape, monkeypatch):
     _tiles_case(monkeypatch, {"BSG_TILES_SHAPE": shape}, 700)
 
