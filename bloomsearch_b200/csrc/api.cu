@@ -1122,8 +1122,12 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     auto ring_budget = [&](uint32_t units_cap) {
         return cta_smem - tiles_fixed_smem(units_cap, kProbeMaxKeysPerPass);
     };
-    const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), 1);
-    auto tile_limit = [&](uint32_t g) { return ring_budget(g) / min_stages - tile_header_bytes(g); };
+    // several small units per tile: two stages are enough (the kernel is instruction bound there and a larger tile
+    // amortises the per-tile rounds: 2a 53.2 -> 50.7 us); a tile that is one large unit keeps a ring of >= 3
+    auto tile_limit = [&](uint32_t g) {
+        const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), g > 1 ? 1 : 3);
+        return ring_budget(g) / min_stages - tile_header_bytes(g);
+    };
     // units per tile: the g in 1..cfg that packs the most units of the typical size (more units per tile cost list space)
     uint32_t group_cap = 1;
     {
