@@ -94,7 +94,7 @@ struct bsg_ctx {
     int tile_bytes = 80000;      // BSG_TILE_BYTES: UNIT mode, units are grouped into tiles of about this many bytes
     int tile_units = 8;    // BSG_TILE_UNITS: UNIT mode, at most this many units per tile (<= kTileMaxUnits)
     int tile_mode = 0;     // BSG_TILE_MODE: 0 = choose per corpus, 1 = force UNIT mode, 2 = force KIND mode
-    int tile_min_stages = 2;  // BSG_TILE_MIN_STAGES: UNIT mode keeps units small enough for a ring of this many stages
+    int tile_min_stages = 0;  // BSG_TILE_MIN_STAGES: UNIT mode keeps tiles small enough for a ring of this many stages (0 = 2 for grouped units, 3 for a single unit)
     // BSG_PROBE_TIMING=1: host-side phase times of bsg_probe() (ns sums), printed by bsg_destroy
     int timing = 0;
     std::atomic<uint64_t> t_calls{0}, t_prepare{0}, t_run{0}, t_wait{0}, t_copyout{0};
@@ -168,7 +168,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_TILE_BYTES")) ctx->tile_bytes = std::max(1024, atoi(w));
     if (const char* w = getenv("BSG_TILE_UNITS")) ctx->tile_units = std::min<int>(kTileMaxUnits, std::max(1, atoi(w)));
     if (const char* w = getenv("BSG_TILE_MODE")) ctx->tile_mode = std::min(2, std::max(0, atoi(w)));
-    if (const char* w = getenv("BSG_TILE_MIN_STAGES")) ctx->tile_min_stages = std::min(8, std::max(1, atoi(w)));
+    if (const char* w = getenv("BSG_TILE_MIN_STAGES")) ctx->tile_min_stages = std::min(8, std::max(0, atoi(w)));
     if (const char* w = getenv("BSG_PROBE_PDL")) ctx->pdl = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
     if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
@@ -1125,7 +1125,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     // several small units per tile: two stages are enough (the kernel is instruction bound there and a larger tile
     // amortises the per-tile rounds: 2a 53.2 -> 50.7 us); a tile that is one large unit keeps a ring of >= 3
     auto tile_limit = [&](uint32_t g) {
-        const uint64_t min_stages = std::max<uint64_t>(static_cast<uint64_t>(ctx->tile_min_stages), g > 1 ? 1 : 3);
+        const uint64_t min_stages = ctx->tile_min_stages > 0 ? static_cast<uint64_t>(ctx->tile_min_stages) : (g > 1 ? 2 : 3);
         return ring_budget(g) / min_stages - tile_header_bytes(g);
     };
     // units per tile: the g in 1..cfg that packs the most units of the typical size (more units per tile cost list space)
