@@ -222,7 +222,7 @@ __device__ __forceinline__ bool test_tail_s32(uint64_t h0, uint64_t h1, uint64_t
     static_assert(START >= 1 && START <= 4, "phase A runs 1..4 tests");
     auto probe = [&](uint64_t loc) -> uint32_t {
         const uint32_t bit = mod_m32(loc, m, ih, il);
-        return (w32[bit >> 5] >> (bit & 31u)) & 1u;
+        return (w32[word_index(bit)] >> (bit & 31u)) & 1u;
     };
     if (START < 4) {  // first group: locations START..3
         uint32_t ok = 1u;
@@ -267,7 +267,7 @@ __device__ __forceinline__ bool test_from_s32(uint64_t h0, uint64_t h1, uint64_t
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t bit = mod_m32(loc[j], m, ih, il);
-            ok &= ((w32[bit >> 5] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(i0 + j >= k);
+            ok &= ((w32[word_index(bit)] >> (bit & 31u)) & 1u) | static_cast<uint32_t>(i0 + j >= k);
             loc[j] += step[j];
         }
         if (!ok) return false;

@@ -944,6 +944,17 @@ def test_probe_tiles_modes_groupings_rings(env, n_units, monkeypatch):
     _tiles_case(monkeypatch, env, n_units)
 
 
+@pytest.mark.parametrize("env,cap", [
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 2}, 600),    # 600 keys present in both units of a tile: |L1| = 1200
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 3}, 400),    # 3 x 400 = 1200
+    ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 5, "BSG_TILES_SHAPE": 0}, 120),   # 512-thread shape: 600 = 512 + 88
+])
+def test_probe_tiles_survivor_list_just_above_a_full_pass(env, cap, monkeypatch):
+    """|L1| just above a multiple of the CTA size (a short, ragged last pass of round B1), with keys that pass
+    every location, absent filters and k = 1..30."""
+    _tiles_case(monkeypatch, env, 300, key_kinds=(1,), n_keys_cap=cap)
+
+
 @pytest.mark.parametrize("env,key_kinds", [
     ({"BSG_TILE_MODE": 1}, (1,)), ({"BSG_TILE_MODE": 1}, (0, 2)), ({"BSG_TILE_MODE": 1, "BSG_TILE_UNITS": 5}, (2,)),
     ({"BSG_TILE_MODE": 2}, (1,)), ({"BSG_TILE_MODE": 2}, (2,)), ({"BSG_TILE_MODE": 2}, (0,)), ({"BSG_TILE_MODE": 2}, (0, 2)),
