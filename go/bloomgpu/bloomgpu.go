@@ -224,6 +224,102 @@ func (c *Context) Probe(cp *Corpus, keys PackedKeys, kinds []Kind, prog []Op, wa
 	return mask[:(cp.Units+63)/64], matrix, check(rc)
 }
 
+// QuerySpec is one member of a ProbeMulti call: its keys (already packed), their kinds and its postfix
+// program, whose leaf arguments index ITS OWN keys.
+type QuerySpec struct {
+	Keys  []string
+	Kinds []Kind
+	Prog  []Op
+}
+
+// ProbeMulti is bsg_probe_multi: several queries in ONE pass over the corpus (the staged kernels stream every
+// filter byte once per pass of up to 1 024 keys, whatever the number of keys), one candidate mask per query —
+// identical to len(qs) Probe calls.  masks[j] bit u = unit u survives query j.
+func (c *Context) ProbeMulti(cp *Corpus, qs []QuerySpec) (masks [][]uint64, err error) {
+	defer pin()()
+	if len(qs) == 0 {
+		return nil, nil
+	}
+	var all []string
+	var kinds []Kind
+	var progs []Op
+	qBegin := make([]uint32, 1, len(qs)+1)
+	pBegin := make([]uint32, 1, len(qs)+1)
+	for _, q := range qs {
+		all = append(all, q.Keys...)
+		kinds = append(kinds, q.Kinds...)
+		progs = append(progs, q.Prog...)
+		qBegin = append(qBegin, uint32(len(all)))
+		pBegin = append(pBegin, uint32(len(progs)))
+	}
+	keys := Pack(all)
+	words := (cp.Units + 63) / 64
+	flat := make([]uint64, uint64(len(qs))*words+1)
+	var pp *C.bsg_expr_op
+	if len(progs) > 0 {
+		pp = (*C.bsg_expr_op)(unsafe.Pointer(&progs[0]))
+	}
+	var kp *C.uint8_t
+	if len(kinds) > 0 {
+		kp = (*C.uint8_t)(unsafe.Pointer(&kinds[0]))
+	}
+	rc := C.bsg_probe_multi(c.h, cp.h, (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0])), (*C.uint64_t)(unsafe.Pointer(&keys.Off[0])),
+		C.uint32_t(len(all)), kp, C.uint32_t(len(qs)), (*C.uint32_t)(unsafe.Pointer(&qBegin[0])), pp,
+		(*C.uint32_t)(unsafe.Pointer(&pBegin[0])), (*C.uint64_t)(unsafe.Pointer(&flat[0])))
+	runtime.KeepAlive(keys)
+	if err = check(rc); err != nil {
+		return nil, err
+	}
+	masks = make([][]uint64, len(qs))
+	for j := range qs {
+		masks[j] = flat[uint64(j)*words : uint64(j+1)*words]
+	}
+	return masks, nil
+}
+
+// Batcher is bsg_batcher: goroutines that query the same resident corpus at the same time (one goroutine per
+// query in the reference, query_exec.go:201-433) are merged into bsg_probe_multi launches by a group commit —
+// a caller that finds no launch in flight launches at once, callers that arrive meanwhile share the next one.
+type Batcher struct {
+	h  *C.bsg_batcher
+	cp *Corpus
+}
+
+func (c *Context) NewBatcher(cp *Corpus, maxKeys, maxQueries, windowMicros uint32) (*Batcher, error) {
+	defer pin()()
+	b := &Batcher{cp: cp}
+	if err := check(C.bsg_batcher_create(c.h, cp.h, C.uint32_t(maxKeys), C.uint32_t(maxQueries), C.uint32_t(windowMicros), &b.h)); err != nil {
+		return nil, err
+	}
+	return b, nil
+}
+
+func (b *Batcher) Close() {
+	if b.h != nil {
+		C.bsg_batcher_destroy(b.h)
+		b.h = nil
+	}
+}
+
+// Probe blocks until this query's candidate mask is ready; it may have shared its launch with other goroutines.
+func (b *Batcher) Probe(keys PackedKeys, kinds []Kind, prog []Op) (mask []uint64, err error) {
+	defer pin()()
+	n := uint32(len(keys.Off) - 1)
+	mask = make([]uint64, (b.cp.Units+63)/64+1)
+	var pp *C.bsg_expr_op
+	if len(prog) > 0 {
+		pp = (*C.bsg_expr_op)(unsafe.Pointer(&prog[0]))
+	}
+	var kp *C.uint8_t
+	if n > 0 {
+		kp = (*C.uint8_t)(unsafe.Pointer(&kinds[0]))
+	}
+	rc := C.bsg_batcher_probe(b.h, (*C.uint8_t)(unsafe.Pointer(&keys.Bytes[0])), (*C.uint64_t)(unsafe.Pointer(&keys.Off[0])),
+		C.uint32_t(n), kp, pp, C.uint32_t(len(prog)), (*C.uint64_t)(unsafe.Pointer(&mask[0])))
+	runtime.KeepAlive(keys)
+	return mask[:(b.cp.Units+63)/64], check(rc)
+}
+
 // SetParents records, for every unit (block) of cp, the index of its file in the files corpus;
 // ProbeHierarchical then runs both pruning stages of Query (query_exec.go:399-406 and :572-615)
 // in one call, compacting the surviving blocks on the device between them.

@@ -140,7 +140,9 @@ func evaluateFileFiltersGPU(generation uint64, loadFiles func() (desc []bloomgpu
 	}
 	defer fileCache.Release(corpus)
 	keys, kinds, prog := compileBloomQuery(q)
-	mask, _, err := gpu.Probe(corpus, bloomgpu.Pack(keys), kinds, prog, false)
+	// every concurrent Query() of this generation probes the SAME resident corpus: the batcher merges the ones
+	// that arrive together into one bsg_probe_multi launch (group commit; an idle engine adds no latency)
+	mask, err := fileBatcher(generation, corpus).Probe(bloomgpu.Pack(keys), kinds, prog)
 	if err != nil {
 		return nil, err
 	}
@@ -151,9 +153,39 @@ func evaluateFileFiltersGPU(generation uint64, loadFiles func() (desc []bloomgpu
 	return keep, nil
 }
 
+// One batcher per resident file-level corpus (= per MetaStore generation); it pins the corpus for its lifetime.
+var (
+	batcherMu   sync.Mutex
+	batchers    = map[uint64]*bloomgpu.Batcher{}
+	batcherPins = map[uint64]*bloomgpu.Corpus{}
+)
+
+func fileBatcher(generation uint64, corpus *bloomgpu.Corpus) *bloomgpu.Batcher {
+	batcherMu.Lock()
+	defer batcherMu.Unlock()
+	if b, ok := batchers[generation]; ok {
+		return b
+	}
+	pinned, _ := fileCache.Acquire(generation) // a second pin, held until the generation is retired
+	b, err := gpu.NewBatcher(corpus, 0, 0, 0)
+	if err != nil || pinned == nil {
+		panic("bloomgpu: batcher for a resident corpus") // both are programming errors: the caller holds a pin
+	}
+	batchers[generation], batcherPins[generation] = b, pinned
+	return b
+}
+
 // InvalidateFile is called from the merge commit and from TombstoneFile for every retired file, with the
 // generation the file-level corpus was built for.
 func InvalidateFile(fileID, oldGeneration uint64) {
+	batcherMu.Lock()
+	if b, ok := batchers[oldGeneration]; ok { // queries in flight finish first: Close waits for the running launch
+		b.Close()
+		fileCache.Release(batcherPins[oldGeneration])
+		delete(batchers, oldGeneration)
+		delete(batcherPins, oldGeneration)
+	}
+	batcherMu.Unlock()
 	_ = blockCache.Invalidate(fileID)
 	_ = fileCache.Invalidate(oldGeneration)
 	blockErrMu.Lock()

@@ -87,7 +87,7 @@ def test_go_shim_and_cpp_host_bind_only_declared_entry_points():
     nothing but what include/bloomgpu.h declares, and the shim must cover the whole hot path
     (build, fused field::token build, distinct counts, corpus loads, probe, hierarchical probe)."""
     declared = set(_declared_symbols())
-    types = {"bsg_ctx", "bsg_corpus", "bsg_query", "bsg_expr_op", "bsg_filter_desc", "bsg_cache", "bsg_keyset"}
+    types = {"bsg_ctx", "bsg_corpus", "bsg_query", "bsg_expr_op", "bsg_filter_desc", "bsg_cache", "bsg_keyset", "bsg_batcher"}
     go_calls = set()
     for fn in os.listdir(os.path.join(ROOT, "go", "bloomgpu")):
         if fn.endswith(".go"):
