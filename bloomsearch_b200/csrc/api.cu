@@ -84,6 +84,9 @@ struct bsg_ctx {
     std::vector<cudaEvent_t> aux_events;
     cudaEvent_t fork_event = nullptr;
     float last_build_kernel_ms = 0.f;  // profiling: device time of the last bsg_build's kernel
+    std::mutex distinct_mu;         // bsg_count_distinct: hash-set tables, grow-only
+    void* d_distinct = nullptr;
+    size_t distinct_cap = 0;
     uint64_t* d_trace = nullptr;  // profiling timeline (bsg_debug_trace_*), [n_ctas][slots]
     uint32_t trace_slots = 0;
     int probe_warps = 0;   // BSG_PROBE_WARPS override (tuning)
@@ -201,6 +204,7 @@ extern "C" void bsg_destroy(bsg_ctx* ctx) {
     for (cudaEvent_t e : ctx->aux_events) cudaEventDestroy(e);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_distinct);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -741,11 +745,21 @@ extern "C" int bsg_build_fieldtokens(bsg_ctx* ctx, const uint8_t* strings, const
 static int count_distinct_device(bsg_ctx* ctx, const uint8_t* d_keys, const uint64_t* d_off, uint64_t n_keys,
                                  const uint64_t* d_gb, uint32_t n_groups, const uint32_t* group_parent, uint32_t n_parents,
                                  uint64_t* out_group_counts, uint64_t* out_parent_counts, cudaStream_t s) {
-    (void)ctx;
-    DevBuf<uint8_t> d_em;
+    // the hash-set tables (GBs for a flush-sized batch) are kept by the ctx and only grow: allocating and freeing
+    // them per call cost more than the counting kernel; one count at a time per ctx (the flush worker's pace)
+    std::lock_guard<std::mutex> distinct_lk(ctx->distinct_mu);
+    const size_t need = count_distinct_scratch_bytes(n_keys);
+    if (need > ctx->distinct_cap) {
+        cudaFree(ctx->d_distinct);
+        ctx->d_distinct = nullptr;
+        ctx->distinct_cap = 0;
+        if (cudaMalloc(&ctx->d_distinct, need) != cudaSuccess) { cudaGetLastError(); return fail(BSG_ERR_NOMEM, "device alloc (%zu bytes of hash-set tables)", need); }
+        ctx->distinct_cap = need;
+    }
+    struct { void* p; } d_em{ctx->d_distinct};
     DevBuf<uint32_t> d_gp;
     DevBuf<unsigned long long> d_gc, d_pc;
-    if (d_gc.alloc(n_groups) != cudaSuccess || d_em.alloc(count_distinct_scratch_bytes(n_keys)) != cudaSuccess ||
+    if (d_gc.alloc(n_groups) != cudaSuccess ||
         (group_parent && (d_gp.alloc(n_groups) != cudaSuccess || d_pc.alloc(n_parents) != cudaSuccess)))
         return fail(BSG_ERR_NOMEM, "device alloc");
     cudaError_t e = cudaMemsetAsync(d_gc.p, 0, n_groups * 8, s);

@@ -3,19 +3,22 @@
 // (block x kind) and of every parent (file x kind) union, which is the `n` that sizes the filters
 // (ingest.go:139-140).  Emissions may repeat.
 //
-//   1. emit    one thread per emission: MurmurHash3_x64_128 of the key bytes -> (h0, h1), its group id
-//   2. sort    LSD radix sort (cub::DeviceRadixSort, library code like a plain cuBLAS GEMM) of
-//              (h0 -> emission index), then a stable sort of those indexes by group id: order (group, h0)
-//   3. count   an emission is a run head when its (group, h0) differs from its left neighbour's, OR when the
-//              KEY BYTES differ (the tie check of SURVEY §8f.3: equal 64-bit hashes are not taken as equal
-//              keys).  One atomic per (warp, group run).
-//   4. unions  the h0-sorted order is re-sorted by parent id and counted the same way.
-// A byte mismatch inside an equal-hash run means a real 64-bit collision between two distinct keys of one
-// group; their repeats could interleave, so the pass is repeated for that call with h1 as a third sort key
-// (order (group, h0, h1): equal keys are adjacent again).  BSG_DISTINCT_HASH_BITS=<n> keeps only n bits
-// of h0 to force that path in tests.
-#include <cub/device/device_radix_sort.cuh>
-
+// A Go map is a hash set, and so is this: one open-addressing table in HBM for all groups at once, one
+// thread per emission, no sort and no library call.
+//
+//   slot      one 64-bit word: 0 = empty, else (segment id << 32) | (emission index + 1).  Claimed with ONE
+//             atomicCAS, so a slot is never seen half written and no thread ever waits for another.
+//   home      MurmurHash3_x64_128 of the key bytes (h0, the hash the build kernel needs anyway) mixed with the
+//             segment id; linear probing; the table holds at least twice as many slots as emissions.
+//   equality  an occupied slot of the same segment is compared BYTE FOR BYTE with the emission (SURVEY §8f.3:
+//             equal hashes are never taken as equal keys): equal -> the emission is a repeat; different ->
+//             keep probing.  The count is therefore exact for any hash quality (BSG_DISTINCT_HASH_BITS=<n>
+//             keeps only n bits of h0 so that tests can force thousands of collisions).
+//   counts    an emission that claims a slot is the first of its key in its group: one atomicAdd per (warp,
+//             group) on the group's counter, and — file-level unions (flush.go:221,253) — the same insertion
+//             into a second table keyed by the group's parent, counted per parent.
+// Round 2 first ordered the emissions with cub::DeviceRadixSort (35 ms for 39 M emissions); the table needs
+// one pass over the keys and about two random 32-byte accesses per emission.
 #include <cstdlib>
 
 #include "bsg_device.cuh"
@@ -24,44 +27,6 @@
 namespace bsg {
 
 namespace {
-
-struct Scratch {
-    uint64_t *h0, *h1, *ka, *kb;
-    uint32_t *seg, *va, *vb, *sa, *sb;
-    unsigned long long* collisions;
-    void* temp;
-    size_t temp_bytes;
-};
-
-size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
-
-size_t temp_bytes_for(uint64_t n) {
-    size_t t64 = 0, t32 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t64, static_cast<const uint64_t*>(nullptr), static_cast<uint64_t*>(nullptr),
-                                    static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), n);
-    cub::DeviceRadixSort::SortPairs(nullptr, t32, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                    static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), n);
-    return std::max(t64, t32);
-}
-
-Scratch carve(void* base, uint64_t n) {
-    Scratch s;
-    uint8_t* p = static_cast<uint8_t*>(base);
-    auto take = [&](size_t bytes) { uint8_t* r = p; p += align_up(bytes); return r; };
-    s.h0 = reinterpret_cast<uint64_t*>(take(n * 8));
-    s.h1 = reinterpret_cast<uint64_t*>(take(n * 8));
-    s.ka = reinterpret_cast<uint64_t*>(take(n * 8));
-    s.kb = reinterpret_cast<uint64_t*>(take(n * 8));
-    s.seg = reinterpret_cast<uint32_t*>(take(n * 4));
-    s.va = reinterpret_cast<uint32_t*>(take(n * 4));
-    s.vb = reinterpret_cast<uint32_t*>(take(n * 4));
-    s.sa = reinterpret_cast<uint32_t*>(take(n * 4));
-    s.sb = reinterpret_cast<uint32_t*>(take(n * 4));
-    s.collisions = reinterpret_cast<unsigned long long*>(take(8));
-    s.temp_bytes = temp_bytes_for(n);
-    s.temp = take(s.temp_bytes);
-    return s;
-}
 
 // MurmurHash3_x64_128(key, seed 0): the first half of bloom/v3's baseHashes
 __device__ __forceinline__ void murmur128(const uint8_t* key, uint32_t len, uint64_t& o1, uint64_t& o2) {
@@ -78,45 +43,6 @@ __device__ __forceinline__ void murmur128(const uint8_t* key, uint32_t len, uint
         if (t > 8) k2 = rd.next() & low_bytes_mask(t - 8);
     }
     finalize(h1, h2, k1, k2, len, o1, o2);
-}
-
-// hash every key and tag it with its group (binary search of the CSR group_begin)
-__global__ void __launch_bounds__(256)
-emit_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off, uint64_t n_keys,
-            const uint64_t* __restrict__ group_begin, uint32_t n_groups, uint64_t h0_mask, uint64_t* __restrict__ h0,
-            uint64_t* __restrict__ h1, uint64_t* __restrict__ sort_key, uint32_t* __restrict__ idx,
-            uint32_t* __restrict__ seg) {
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_keys) return;
-    const uint64_t b = __ldg(&key_off[i]), e = __ldg(&key_off[i + 1]);
-    uint64_t a, c;
-    murmur128(keys + b, static_cast<uint32_t>(e - b), a, c);
-    a &= h0_mask;
-    uint32_t lo = 0, hi = n_groups;  // last g with group_begin[g] <= i
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&group_begin[mid]) <= i) lo = mid; else hi = mid;
-    }
-    h0[i] = a;
-    h1[i] = c;
-    sort_key[i] = a;
-    idx[i] = static_cast<uint32_t>(i);
-    seg[i] = lo;
-}
-
-// out[j] = table[in_idx[j]] (optionally mapped through `parent`)
-__global__ void __launch_bounds__(256)
-gather_seg_kernel(const uint32_t* __restrict__ order, uint64_t n, const uint32_t* __restrict__ seg,
-                  const uint32_t* __restrict__ parent, uint32_t* __restrict__ out) {
-    const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t g = seg[order[j]];
-    out[j] = parent ? __ldg(&parent[g]) : g;
-}
-__global__ void __launch_bounds__(256)
-gather_u64_kernel(const uint32_t* __restrict__ order, uint64_t n, const uint64_t* __restrict__ table, uint64_t* __restrict__ out) {
-    const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = table[order[j]];
 }
 
 __device__ __forceinline__ bool same_key_bytes(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off,
@@ -138,56 +64,85 @@ __device__ __forceinline__ bool same_key_bytes(const uint8_t* __restrict__ keys,
     return true;
 }
 
-// counts[seg] += run heads of the array sorted by (seg, h0[, h1]); one atomic per (warp, segment run)
-__global__ void __launch_bounds__(256)
-count_heads_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ segs, uint64_t n,
-                   const uint64_t* __restrict__ h0, const uint64_t* __restrict__ h1, int use_h1,
-                   const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off,
-                   unsigned long long* __restrict__ counts, unsigned long long* __restrict__ collisions) {
-    const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// true: emission i is the first of its key in segment `seg` (it now owns a slot); false: a repeat
+__device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ slots, uint64_t slot_mask, uint64_t h0, uint32_t seg,
+                                           uint32_t i, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off) {
+    uint64_t x = h0 ^ (static_cast<uint64_t>(seg) * 0x9E3779B97F4A7C15ull);
+    x ^= x >> 29;
+    uint64_t pos = x & slot_mask;
+    const unsigned long long mine = (static_cast<unsigned long long>(seg) << 32) | (static_cast<unsigned long long>(i) + 1ull);
+    for (;;) {
+        unsigned long long v = ld_relaxed_u64(&slots[pos]);
+        if (v == 0ull) {
+            v = atomicCAS(&slots[pos], 0ull, mine);
+            if (v == 0ull) return true;
+        }
+        if (static_cast<uint32_t>(v >> 32) == seg &&
+            same_key_bytes(keys, key_off, i, static_cast<uint32_t>(v) - 1u))
+            return false;
+        pos = (pos + 1) & slot_mask;
+    }
+}
+
+// counts[seg] += 1 for every lane with `add`, one atomic per distinct segment in the warp
+__device__ __forceinline__ void warp_count(unsigned long long* __restrict__ counts, uint32_t seg, bool add) {
     const uint32_t lane = threadIdx.x & 31;
-    bool head = false;
-    uint32_t seg = 0xffffffffu;
-    if (j < n) {
-        seg = segs[j];
-        head = true;
-        if (j > 0 && segs[j - 1] == seg) {
-            const uint32_t i = order[j], p = order[j - 1];
-            if (h0[i] == h0[p] && (!use_h1 || h1[i] == h1[p])) {
-                // tie check: equal hashes are not taken as equal keys
-                if (same_key_bytes(keys, key_off, i, p)) head = false;
-                else atomicAdd(collisions, 1ull);
+    const uint32_t key = add ? seg : 0xffffffffu;
+    const uint32_t same = __match_any_sync(0xffffffffu, key);
+    if (add && lane == static_cast<uint32_t>(__ffs(static_cast<int>(same)) - 1))
+        atomicAdd(&counts[seg], static_cast<unsigned long long>(__popc(same)));
+}
+
+__global__ void __launch_bounds__(256)
+distinct_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ key_off, uint64_t n_keys,
+                const uint64_t* __restrict__ group_begin, uint32_t n_groups, const uint32_t* __restrict__ group_parent,
+                uint64_t h0_mask, unsigned long long* __restrict__ tab_g, unsigned long long* __restrict__ tab_p,
+                uint64_t slot_mask, unsigned long long* __restrict__ group_counts,
+                unsigned long long* __restrict__ parent_counts) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool first_in_group = false, first_in_parent = false;
+    uint32_t g = 0, p = 0;
+    // the group of the warp's first emission by binary search (one lane), then every lane walks forward from it:
+    // emissions are grouped (CSR), so 32 consecutive ones rarely span more than two groups
+    {
+        const uint64_t i0 = i - (threadIdx.x & 31);
+        uint32_t lo = 0;
+        if ((threadIdx.x & 31) == 0 && i0 < n_keys) {
+            uint32_t hi = n_groups;  // last g with group_begin[g] <= i0
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&group_begin[mid]) <= i0) lo = mid; else hi = mid;
             }
         }
+        g = __shfl_sync(0xffffffffu, lo, 0);
     }
-    // lanes of one segment are contiguous (sorted): the first lane of each run adds the run's head count
-    const uint32_t same = __match_any_sync(0xffffffffu, seg);
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    if (j < n && lane == static_cast<uint32_t>(__ffs(same) - 1)) {
-        const uint32_t c = __popc(heads & same);
-        if (c) atomicAdd(&counts[seg], static_cast<unsigned long long>(c));
+    if (i < n_keys) {
+        while (g + 1 < n_groups && __ldg(&group_begin[g + 1]) <= i) ++g;   // also skips empty groups
+        const uint64_t b = __ldg(&key_off[i]), e = __ldg(&key_off[i + 1]);
+        uint64_t h0, h1;
+        murmur128(keys + b, static_cast<uint32_t>(e - b), h0, h1);
+        h0 &= h0_mask;
+        first_in_group = set_insert(tab_g, slot_mask, h0, g, static_cast<uint32_t>(i), keys, key_off);
+        if (first_in_group && tab_p) {
+            p = __ldg(&group_parent[g]);
+            // a different mix constant for the second table is not needed: it is a different table
+            first_in_parent = set_insert(tab_p, slot_mask, h0, p, static_cast<uint32_t>(i), keys, key_off);
+        }
     }
+    warp_count(group_counts, g, first_in_group);
+    if (tab_p) warp_count(parent_counts, p, first_in_parent);
 }
 
-int bits_for(uint32_t n) {
-    int b = 1;
-    while (b < 32 && (1ull << b) < n) ++b;
-    return b;
-}
-
-#define CUB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
-
-// order_h (indexes sorted by h0 [then h1]) -> stable sort by segment id -> count
-cudaError_t count_by_segment(const Scratch& S, uint64_t n, const uint32_t* order_h, const uint32_t* d_parent, uint32_t n_segments,
-                             int use_h1, const uint8_t* d_keys, const uint64_t* d_key_off, unsigned long long* d_counts,
-                             uint32_t* order_out, cudaStream_t s) {
-    const uint32_t blocks = static_cast<uint32_t>((n + 255) / 256);
-    gather_seg_kernel<<<blocks, 256, 0, s>>>(order_h, n, S.seg, d_parent, S.sa);
-    CUB_TRY(cudaGetLastError());
-    size_t tb = S.temp_bytes;
-    CUB_TRY(cub::DeviceRadixSort::SortPairs(S.temp, tb, S.sa, S.sb, order_h, order_out, n, 0, bits_for(n_segments), s));
-    count_heads_kernel<<<blocks, 256, 0, s>>>(order_out, S.sb, n, S.h0, S.h1, use_h1, d_keys, d_key_off, d_counts, S.collisions);
-    return cudaGetLastError();
+uint64_t table_slots(uint64_t n_keys) {   // power of two, >= 2 n (load factor <= 1/2)
+    uint64_t t = 1024;
+    while (t < 2 * n_keys) t <<= 1;
+    return t;
 }
 
 }  // namespace
@@ -196,53 +151,28 @@ cudaError_t launch_count_distinct(const uint8_t* d_keys, const uint64_t* d_key_o
                                   const uint64_t* d_group_begin, uint32_t n_groups, const uint32_t* d_group_parent,
                                   uint32_t n_parents, void* d_scratch, unsigned long long* d_group_counts,
                                   unsigned long long* d_parent_counts, cudaStream_t s) {
+    (void)n_parents;
     if (n_keys == 0 || n_groups == 0) return cudaSuccess;
     if (n_keys > 0xfffffff0ull) return cudaErrorInvalidValue;   // emission indexes are 32-bit
-    const Scratch S = carve(d_scratch, n_keys);
     uint64_t h0_mask = ~0ull;
     if (const char* w = getenv("BSG_DISTINCT_HASH_BITS")) {
         const int b = atoi(w);
         if (b > 0 && b < 64) h0_mask = (1ull << b) - 1ull;
     }
+    const uint64_t T = table_slots(n_keys);
+    const bool unions = d_group_parent && d_parent_counts;
+    unsigned long long* tab_g = static_cast<unsigned long long*>(d_scratch);
+    unsigned long long* tab_p = unions ? tab_g + T : nullptr;
+    cudaError_t e = cudaMemsetAsync(tab_g, 0, T * 8 * (unions ? 2 : 1), s);
+    if (e != cudaSuccess) return e;
     const uint32_t blocks = static_cast<uint32_t>((n_keys + 255) / 256);
-    CUB_TRY(cudaMemsetAsync(S.collisions, 0, 8, s));
-    emit_kernel<<<blocks, 256, 0, s>>>(d_keys, d_key_off, n_keys, d_group_begin, n_groups, h0_mask, S.h0, S.h1, S.ka, S.va, S.seg);
-    CUB_TRY(cudaGetLastError());
-    size_t tb = S.temp_bytes;
-    CUB_TRY(cub::DeviceRadixSort::SortPairs(S.temp, tb, S.ka, S.kb, S.va, S.vb, n_keys, 0, 64, s));   // S.vb: order by h0
-    for (int use_h1 = 0; use_h1 < 2; ++use_h1) {
-        if (use_h1) {
-            // a real 64-bit collision between distinct keys of one group: add h1 as a sort key so that repeats of
-            // equal keys are adjacent again.  LSD: h1 first, then h0 (both stable), then the segment ids.
-            CUB_TRY(cudaMemsetAsync(d_group_counts, 0, static_cast<size_t>(n_groups) * 8, s));
-            if (d_parent_counts) CUB_TRY(cudaMemsetAsync(d_parent_counts, 0, static_cast<size_t>(std::max<uint32_t>(n_parents, 1)) * 8, s));
-            CUB_TRY(cudaMemsetAsync(S.collisions, 0, 8, s));
-            emit_kernel<<<blocks, 256, 0, s>>>(d_keys, d_key_off, n_keys, d_group_begin, n_groups, h0_mask, S.h0, S.h1, S.ka, S.va, S.seg);
-            CUB_TRY(cudaGetLastError());
-            gather_u64_kernel<<<blocks, 256, 0, s>>>(S.va, n_keys, S.h1, S.ka);
-            CUB_TRY(cudaGetLastError());
-            tb = S.temp_bytes;
-            CUB_TRY(cub::DeviceRadixSort::SortPairs(S.temp, tb, S.ka, S.kb, S.va, S.vb, n_keys, 0, 64, s));   // by h1
-            gather_u64_kernel<<<blocks, 256, 0, s>>>(S.vb, n_keys, S.h0, S.ka);
-            CUB_TRY(cudaGetLastError());
-            tb = S.temp_bytes;
-            CUB_TRY(cub::DeviceRadixSort::SortPairs(S.temp, tb, S.ka, S.kb, S.vb, S.va, n_keys, 0, 64, s));   // by (h0, h1)
-            CUB_TRY(cudaMemcpyAsync(S.vb, S.va, n_keys * 4, cudaMemcpyDeviceToDevice, s));
-        }
-        CUB_TRY(count_by_segment(S, n_keys, S.vb, nullptr, n_groups, use_h1, d_keys, d_key_off, d_group_counts, S.va, s));
-        if (d_group_parent && d_parent_counts)
-            CUB_TRY(count_by_segment(S, n_keys, S.vb, d_group_parent, n_parents, use_h1, d_keys, d_key_off, d_parent_counts, S.va, s));
-        unsigned long long coll = 0;
-        CUB_TRY(cudaMemcpyAsync(&coll, S.collisions, 8, cudaMemcpyDeviceToHost, s));
-        CUB_TRY(cudaStreamSynchronize(s));
-        if (coll == 0) break;   // no equal-hash / different-bytes neighbours: the counts are exact
-    }
-    return cudaSuccess;
+    distinct_kernel<<<blocks, 256, 0, s>>>(d_keys, d_key_off, n_keys, d_group_begin, n_groups, d_group_parent, h0_mask, tab_g,
+                                           tab_p, T - 1, d_group_counts, d_parent_counts);
+    return cudaGetLastError();
 }
 
 size_t count_distinct_scratch_bytes(uint64_t n_keys) {
-    const uint64_t n = std::max<uint64_t>(n_keys, 1);
-    return 4 * align_up(n * 8) + 5 * align_up(n * 4) + align_up(8) + align_up(temp_bytes_for(n)) + 256;
+    return static_cast<size_t>(table_slots(std::max<uint64_t>(n_keys, 1))) * 8 * 2 + 256;
 }
 
 }  // namespace bsg
