@@ -838,6 +838,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=8, help="distinct HBM copies cycled so every launch misses L2")
     ap.add_argument("--streams", type=int, default=2, help="streams the timed batches are issued on (round-robin)")
     ap.add_argument("--e2e-callers", type=int, default=4, help="host threads calling bsg_probe concurrently in the e2e leg")
+    ap.add_argument("--leg", default="", choices=["", "config4"], help="run one extra leg alone and print only its result (profiling aid)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip every CPU (oracle) leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the build / config4 / config5 legs")
@@ -855,6 +856,12 @@ def main():
 
     env = Env(args)
     peaks, ncu = load_peaks(), load_ncu_summary()
+    if args.leg == "config4":   # development aid (profiling one leg under ncu): not the contract line
+        res = config4_leg(env, args, peaks)
+        if env.rank == 0:
+            print(json.dumps({"leg": "config4", **res}), flush=True)
+        env.ctx.close()
+        return
     results, cpu = {}, None
     for wl in [args.workload] + ([] if args.no_also else [w for w in WORKLOADS if w != args.workload]):
         results[wl], cpu_wl = probe_leg(env, args, wl, wl == args.workload, peaks, ncu)

@@ -105,6 +105,7 @@ struct bsg_ctx {
     int spin_wait = 1;     // BSG_PROBE_SPIN: bsg_probe() polls the stream instead of blocking in cudaStreamSynchronize
     std::mutex host_mu;
     std::vector<std::pair<uint8_t*, size_t>> host_bufs;  // bsg_host_alloc: pinned + mapped caller buffers
+    int short_circuit = 1; // BSG_PROBE_SHORT_CIRCUIT: mask-only small queries on the gather path stop testing a unit's keys once its expression is decided
     int zero_copy = 1;     // BSG_PROBE_ZEROCOPY: bsg_probe() matrix rows written straight to pinned host memory
     int pdl = 1;           // BSG_PROBE_PDL: programmatic dependent launch of the two-phase probe kernel
     int relax_sleep_ns = 0;  // BSG_PROBE_SLEEP: ns slept between polls of a phase-B warp (measured: no effect)
@@ -163,6 +164,12 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     CUDA_TRY(probe_tiles_configure(ctx->max_smem_optin));
     CUDA_TRY(build_configure(ctx->max_smem_optin));
     CUDA_TRY(sections_configure());
+    // BSG_L2_FETCH = 32 | 64 | 128: L2 fetch granularity hint (device-wide).  The gather kernel needs 4 bytes of every
+    // 32-byte sector it touches; a coarser fetch only multiplies its DRAM traffic.
+    if (const char* w = getenv("BSG_L2_FETCH")) {
+        const int g = atoi(w);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(g));
+    }
     if (const char* w = getenv("BSG_PROBE_WARPS")) ctx->probe_warps = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGES")) ctx->max_stages = atoi(w);
     if (const char* w = getenv("BSG_PROBE_STAGGER")) ctx->stagger_pct = atoi(w);
@@ -176,6 +183,7 @@ extern "C" int bsg_create(int device, bsg_ctx** out) {
     if (const char* w = getenv("BSG_PROBE_TIMING")) ctx->timing = atoi(w);
     if (const char* w = getenv("BSG_PROBE_FUSE_HASH")) ctx->fuse_hash = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_ZEROCOPY")) ctx->zero_copy = atoi(w) != 0;
+    if (const char* w = getenv("BSG_PROBE_SHORT_CIRCUIT")) ctx->short_circuit = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SPIN")) ctx->spin_wait = atoi(w) != 0;
     if (const char* w = getenv("BSG_PROBE_SLEEP")) ctx->relax_sleep_ns = std::max(0, atoi(w));
     *out = ctx;
@@ -1803,9 +1811,13 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
     // the mask is set; its result is forced to "disqualified" otherwise.
     const uint32_t* d_parent = d_parent_mask32 ? c->d_parent : nullptr;
     if (d_parent_mask32 && !d_parent) return fail(BSG_ERR_INVALID, "corpus has no parents (bsg_corpus_set_parents)");
-    (void)want_matrix;  // the matrix is always materialised (it is the tree kernel's input)
     if (!ctx || !c || !q) return fail(BSG_ERR_INVALID, "NULL argument");
     const bool matrix_only = (path & BSG_RUN_MATRIX_ONLY) != 0;
+    // the matrix is always materialised (it is the tree kernel's input); a caller that wants ONLY the mask of a small
+    // query lets the gather kernel short-circuit like evaluateBloomExpression does (the rows are then optimistic)
+    const bool sc = !want_matrix && !matrix_only && q->prog_len > 0 && q->n_keys <= 32 && ctx->short_circuit;
+    const bsg_expr_op* sc_prog = sc ? q->k_prog : nullptr;
+    const uint32_t sc_len = sc ? q->prog_len : 0;
     path &= 0xff;
     if (q->n_units != c->n_units) return fail(BSG_ERR_INVALID, "query was created for a corpus of %llu units",
                                               (unsigned long long)q->n_units);
@@ -1866,13 +1878,13 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         } else if (c->t_staged) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_t_staged_list, c->t_staged, q->d_hashes,
                                          q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
-                                         d_parent_mask32));
+                                         d_parent_mask32, sc_prog, sc_len));
             ++launches;
         }
         if (c->t_gather) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_t_gather_list, c->t_gather, q->d_hashes,
                                          q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
-                                         d_parent_mask32));
+                                         d_parent_mask32, sc_prog, sc_len));
             ++launches;
         }
     } else if (q->n_keys && c->n_units) {
@@ -1941,13 +1953,13 @@ static int query_run_on(bsg_ctx* ctx, const bsg_corpus* c, bsg_query* q, int pat
         } else if (c->n_staged) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_staged_list, c->n_staged, q->d_hashes,
                                          q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
-                                         d_parent_mask32));
+                                         d_parent_mask32, sc_prog, sc_len));
             ++launches;
         }
         if (c->n_gather) {
             CUDA_TRY(launch_probe_gather(c->d_udesc, c->d_words, c->d_gather_list, c->n_gather, q->d_hashes,
                                          q->k_kinds, q->n_keys, q->k_matrix, q->row_words32, s, d_parent,
-                                         d_parent_mask32));
+                                         d_parent_mask32, sc_prog, sc_len));
             ++launches;
         }
     }

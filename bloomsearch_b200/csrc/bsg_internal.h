@@ -191,7 +191,8 @@ cudaError_t launch_probe_staged(const ProbeStagedPlan& plan, const StageRow* d_s
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
                                 uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s,
-                                const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr);
+                                const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr,
+                                const bsg_expr_op* d_prog = nullptr, uint32_t prog_len = 0);   // prog: short-circuit form (mask-only callers)
 cudaError_t launch_tree_eval(const uint32_t* d_matrix32, uint32_t row_words32, uint64_t n_units,
                              const bsg_expr_op* d_prog, uint32_t prog_len, uint32_t* d_mask32, cudaStream_t s,
                              const uint32_t* d_parent = nullptr, const uint32_t* d_parent_mask32 = nullptr);

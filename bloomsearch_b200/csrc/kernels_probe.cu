@@ -704,11 +704,132 @@ probe_gather_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restr
     }
 }
 
+// The same probe for callers that want only the candidate mask of a SMALL query (<= 32 keys, one expression):
+// evaluateBloomExpression short-circuits (query_exec.go:105-119: an AND stops at its first failing child, an OR at
+// its first passing one), so in the reference a key whose sibling already decided the unit is never tested.  The
+// batched form of that: the G lanes of a unit test their keys in rounds (locations 0-2, 3-6, the rest); after each
+// round the expression is evaluated OPTIMISTICALLY on the unit's bits (a key that has not failed yet counts as
+// present).  Bloom tests and AND/OR trees are monotone, so an optimistic "false" is final: every lane of that unit
+// stops.  Present keys — the ones that cost all k locations — stop after 3 or 7 locations wherever another branch
+// has already disqualified the unit.  The row written is the optimistic one: the tree kernel derives exactly the
+// reference's mask from it, but it is not the membership matrix (callers that want the matrix take the plain kernel).
+constexpr uint32_t kGatherScMaxOps = 128;
+__global__ void __launch_bounds__(256)
+probe_gather_sc_kernel(const DevFilter* __restrict__ udesc, const uint64_t* __restrict__ words,
+                       const uint32_t* __restrict__ unit_list, uint32_t n_list, const uint64_t* __restrict__ hashes,
+                       const uint8_t* __restrict__ kinds, uint32_t n_keys, uint32_t g_log2,
+                       const bsg_expr_op* __restrict__ prog, uint32_t prog_len, uint32_t* __restrict__ matrix32,
+                       uint32_t row_words32, const uint32_t* __restrict__ parent, const uint32_t* __restrict__ parent_mask32) {
+    __shared__ bsg_expr_op sprog[kGatherScMaxOps];
+    for (uint32_t i = threadIdx.x; i < prog_len; i += blockDim.x) sprog[i] = prog[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gwarp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t G = 1u << g_log2;
+    const uint32_t per_warp = 32u >> g_log2;
+    const uint32_t grp = lane >> g_log2;
+    const uint32_t key = lane & (G - 1);
+    const uint64_t list_idx = gwarp * per_warp + grp;
+    const bool unit_ok = list_idx < n_list;
+    uint32_t unit = 0;
+    bool pass = false;           // this lane's key has not failed a location yet
+    uint32_t i = 0, k = 0;       // next location, number of locations
+    uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0, m = 0, inv = 0;
+    const uint32_t* w32 = nullptr;
+    if (unit_ok) {
+        unit = unit_list ? __ldg(&unit_list[list_idx]) : static_cast<uint32_t>(list_idx);
+        bool alive = true;
+        if (parent) {
+            const uint32_t f = __ldg(&parent[unit]);
+            alive = (__ldg(&parent_mask32[f >> 5]) >> (f & 31u)) & 1u;
+        }
+        if (alive && key < n_keys) {
+            const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hashes + 4ull * key);
+            const ulonglong2 a = __ldg(hp), b = __ldg(hp + 1);
+            h0 = a.x; h1 = a.y; h2 = b.x; h3 = b.y;
+            const uint32_t kd = __ldg(&kinds[key]);
+            const uint4* fp = reinterpret_cast<const uint4*>(&udesc[static_cast<size_t>(unit) * 3 + kd]);
+            const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+            m = (static_cast<uint64_t>(f0.w) << 32) | f0.z;
+            inv = (static_cast<uint64_t>(f1.y) << 32) | f1.x;
+            k = m ? f1.z : 0u;   // absent filter: passes, nothing to test
+            w32 = reinterpret_cast<const uint32_t*>(words + ((static_cast<uint64_t>(f0.y) << 32) | f0.x));
+            pass = true;
+        }
+    }
+    const uint32_t shift = grp << g_log2;
+    const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    uint32_t mine = 0;
+    for (uint32_t round = 0;; ++round) {
+        // the locations of a round are loaded TOGETHER (independent loads, no exit between them): every one of them is
+        // a DRAM round trip on a corpus of many GB, and a warp is as slow as its longest chain of dependent misses —
+        // a present key costs 3 round trips this way instead of k
+        const uint32_t upto = round == 0 ? 3u : round == 1 ? 7u : i + 4u;
+        if (pass && i < k) {
+            uint32_t wv[4], sh[4];
+#pragma unroll
+            for (uint32_t t = 0; t < 4; ++t) {
+                const uint32_t ii = i + t;
+                const bool on = ii < k && ii < upto;
+                const uint64_t a = (ii & 1u) ? h1 : h0;
+                const uint64_t b = (((ii + (ii & 1u)) & 3u) >> 1) ? h3 : h2;
+                const uint64_t loc = a + static_cast<uint64_t>(ii) * b;
+                uint64_t bit;
+                if (m < kSmallModLimit)
+                    bit = mod_m32(loc, static_cast<uint32_t>(m), static_cast<uint32_t>(inv >> 32), static_cast<uint32_t>(inv));
+                else
+                    bit = mod_m(loc, m, inv);
+                sh[t] = static_cast<uint32_t>(bit) & 31u;
+                wv[t] = on ? __ldg(w32 + (bit >> 5)) : 0xffffffffu;
+            }
+            uint32_t ok = 1u;
+#pragma unroll
+            for (uint32_t t = 0; t < 4; ++t) ok &= wv[t] >> sh[t];
+            pass = ok & 1u;
+            i = min(k, upto);
+        }
+        mine = (__ballot_sync(0xffffffffu, pass) >> shift) & gmask;
+        if (__ballot_sync(0xffffffffu, pass && i < k) == 0u) break;   // every key of the warp has failed or finished
+        // optimistic value of the expression on this unit's bits
+        uint64_t stack = 0;
+        for (uint32_t pc = 0; pc < prog_len; ++pc) {
+            const uint32_t op = sprog[pc].op, arg = sprog[pc].arg;
+            if (op == BSG_OP_LEAF) {
+                stack = (stack << 1) | ((mine >> arg) & 1u);
+            } else if (op == BSG_OP_TRUE) {
+                stack = (stack << 1) | 1ull;
+            } else if (op == BSG_OP_FALSE) {
+                stack = stack << 1;
+            } else {
+                const uint64_t msk = arg >= 64 ? ~0ull : ((1ull << arg) - 1ull);
+                const uint64_t top = stack & msk;
+                const uint64_t v = (op == BSG_OP_AND) ? (top == msk) : (top != 0);
+                stack = arg >= 64 ? 0ull : (stack >> arg);
+                stack = (stack << 1) | v;
+            }
+        }
+        if (!(stack & 1ull)) i = k;   // the unit is disqualified whatever the remaining locations say
+    }
+    if (unit_ok && key == 0) matrix32[static_cast<size_t>(unit) * row_words32] = mine;
+}
+
 cudaError_t launch_probe_gather(const DevFilter* d_udesc, const uint64_t* d_words, const uint32_t* d_unit_list,
                                 uint32_t n_list, const uint64_t* d_hashes, const uint8_t* d_kinds, uint32_t n_keys,
                                 uint32_t* d_matrix32, uint32_t row_words32, cudaStream_t s, const uint32_t* d_parent,
-                                const uint32_t* d_parent_mask32) {
+                                const uint32_t* d_parent_mask32, const bsg_expr_op* d_prog, uint32_t prog_len) {
     if (n_list == 0 || n_keys == 0) return cudaSuccess;
+    if (d_prog && prog_len && prog_len <= kGatherScMaxOps && n_keys <= 32) {   // mask-only small query: short-circuit form
+        uint32_t g_log2 = 0;
+        while ((1u << g_log2) < n_keys) ++g_log2;
+        const uint32_t per_warp = 32u >> g_log2;
+        const uint64_t n_warps = (static_cast<uint64_t>(n_list) + per_warp - 1) / per_warp;
+        const uint64_t n_blocks = (n_warps + 7) / 8;
+        if (n_blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+        probe_gather_sc_kernel<<<static_cast<uint32_t>(n_blocks), 256, 0, s>>>(
+            d_udesc, d_words, d_unit_list, n_list, d_hashes, d_kinds, n_keys, g_log2, d_prog, prog_len, d_matrix32,
+            row_words32, d_parent, d_parent_mask32);
+        return cudaGetLastError();
+    }
     uint32_t g_log2 = 5, chunks = 1;
     uint64_t n_warps;
     if (n_keys <= 32) {

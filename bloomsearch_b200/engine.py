@@ -646,9 +646,11 @@ class Query:
         N.check(N.lib().bsg_query_create(corpus.ctx.handle, corpus.handle, N.ptr(blob), N.ptr(off), self.n_keys,
                                          N.ptr(kinds), pp, pl, C.byref(self._h)))
 
-    def run(self, path: int = N.PROBE_AUTO, corpus: Optional[Corpus] = None):
+    def run(self, path: int = N.PROBE_AUTO, corpus: Optional[Corpus] = None, want_matrix: bool = True):
+        """want_matrix=False: only the candidate mask is wanted — a small query on the gather path then stops testing
+        a unit's keys as soon as its expression is decided (the fetched matrix is not the membership matrix)."""
         c = corpus or self.corpus
-        N.check(N.lib().bsg_query_run(c.ctx.handle, c.handle, self._h, path, 1))
+        N.check(N.lib().bsg_query_run(c.ctx.handle, c.handle, self._h, path, 1 if want_matrix else 0))
 
     def run_child(self, blocks: Corpus, parent: "Query", path: int = N.PROBE_AUTO):
         """Second stage of a hierarchical probe: only units of `blocks` whose parent survived `parent`'s run."""

@@ -295,6 +295,9 @@ enum { BSG_PROBE_AUTO = 0, BSG_PROBE_STAGED = 1, BSG_PROBE_GATHER = 2 };
 int bsg_query_create(bsg_ctx *ctx, const bsg_corpus *corpus, const uint8_t *keys,
                      const uint64_t *key_off, uint32_t n_keys, const uint8_t *key_kind,
                      const bsg_expr_op *prog, uint32_t prog_len, bsg_query **out);
+/* want_matrix == 0: the caller will fetch only the candidate mask.  A query of <= 32 keys on the gather path then
+ * short-circuits like evaluateBloomExpression (query_exec.go:105-119): a unit's keys stop being tested once its
+ * expression is decided, and the matrix rows are only an upper bound of the membership bits (the mask is exact). */
 int bsg_query_run(bsg_ctx *ctx, const bsg_corpus *corpus, bsg_query *q, int path, int want_matrix);
 int bsg_query_fetch(bsg_ctx *ctx, bsg_query *q, uint64_t n_units, uint64_t *out_matrix,
                     uint64_t *out_mask);

@@ -1216,3 +1216,39 @@ def test_batcher_bad_member_fails_alone(ctx):
     corpus.close()
     assert res["bad"] == N.ERR_INVALID
     assert np.array_equal(res["good"], want)
+
+
+def test_gather_short_circuit_mask_equals_oracle(ctx):
+    """Mask-only small queries on the gather path stop testing a unit's keys once its expression is decided (the
+    batched form of evaluateBloomExpression's short circuit, query_exec.go:105-119): the mask must still be exactly
+    the oracle's, for nested AND / OR trees, TRUE / FALSE ops, absent filters, 1..32 keys, with and without the
+    short circuit, and in the hierarchical call (pruned parents)."""
+    rng, unit_keys, corpus = _multi_fixture(ctx, n_units=300, seed=77)
+    # the oracle needs the fixture's descriptors and words: rebuild them the way the fixture did
+    desc2, words = oracle_units(unit_keys, 0.01, absent={(3, 1), (7, 0), (7, 1), (7, 2)})
+    queries = _random_queries(rng, unit_keys, 60)
+    # a wide one: 32 leaves under nested ORs inside an AND, plus constants
+    wide = bs.BloomQuery(bs.And(bs.Or(*[bs.Token(k) for k in unit_keys[0][1][:15]]),
+                                bs.Or(*[bs.Token(b"zz%d" % i) for i in range(10)], bs.Token(unit_keys[5][1][0])),
+                                bs.Or(*[bs.FieldToken(*k.split(b"::", 1)) for k in unit_keys[9][2][:6]])))
+    queries.append(wide)
+    n_sc = 0
+    for qy in queries:
+        cq = bs.compile_bloom_query(qy)
+        if cq.prog is None or len(cq.keys) == 0:
+            continue
+        blob, off = N.pack_keys(cq.keys)
+        want = cref.probe_mask(desc2, words, corpus.n_units, blob, off, np.asarray(cq.kinds, np.uint8), cq.prog)
+        q = bs.Query(corpus, cq.keys, cq.kinds, cq.prog)
+        for path in (N.PROBE_GATHER, N.PROBE_AUTO):
+            q.run(path, want_matrix=False)
+            _, mask = q.fetch(want_matrix=False)
+            assert np.array_equal(mask, want), (path, cq.keys[:3])
+        q.run(N.PROBE_GATHER, want_matrix=True)
+        m_exact, mask2 = q.fetch()
+        assert np.array_equal(mask2, want)
+        assert np.array_equal(m_exact, cref.probe_matrix(desc2, words, corpus.n_units, blob, off, np.asarray(cq.kinds, np.uint8)))
+        q.close()
+        n_sc += 1
+    assert n_sc >= 40
+    corpus.close()
