@@ -503,13 +503,15 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
                 cp.probe_packed(blob, off, kinds, None, outm, None)
                 cp.close()
 
-            def time_cold(src, n_cold=10):
+            def time_cold(src, n_cold=11):
                 cold(src)
                 assert np.array_equal(outm, got_m), "cold path matrix differs"
-                t0 = time.perf_counter()
+                ts = []
                 for _ in range(n_cold):
+                    t0 = time.perf_counter()
                     cold(src)
-                return (time.perf_counter() - t0) / n_cold
+                    ts.append(time.perf_counter() - t0)
+                return float(np.median(ts))   # host-timed on a shared host: the median call
             dt = time_cold(sec_pinned)
             dt_pageable = time_cold(sec)
             ctx.host_free(sec_pinned)
@@ -518,7 +520,7 @@ def probe_leg(env, args, wl, headline, peaks, ncu):
                                   "h2d_bytes_per_query": int(sec.nbytes + sec_off.nbytes + blob.nbytes + off.nbytes),
                                   "what": "bsg_corpus_load_sections (raw sections in pinned host memory from bsg_host_alloc, "
                                           "one DMA; CRC32C + framing + BE decode on the device) + bsg_probe + free, per 1k-key "
-                                          "batch: the reference's per-query work (decode, then probe)"}
+                                          "batch: the reference's per-query work (decode, then probe); median of 11 calls"}
     for q in queries:
         q.close()
     for cp in corpora:
@@ -621,12 +623,16 @@ def build_leg(env, args, peaks):
                         "note": "key bytes + 8 B offsets + one write of every output word; the scattered atomics are "
                                 "implementation traffic; the kernel is bound by integer issue + shared/L2 atomics, not HBM"}}
     # end to end: host buffers in, host bitsets out (the flush worker's call)
-    t0 = time.perf_counter()
-    w2 = ctx.build(blob, key_off, group_begin, gf, gf2, desc, n_words)
-    dt = env.max(time.perf_counter() - t0)
+    dts = []
+    for _ in range(2):   # host-timed: the faster of two calls (the GPU boxes are shared hosts; a stalled call says nothing)
+        t0 = time.perf_counter()
+        w2 = ctx.build(blob, key_off, group_begin, gf, gf2, desc, n_words)
+        dts.append(time.perf_counter() - t0)
+    dt = env.max(min(dts))
     assert np.array_equal(w2, words), "bsg_build and bsg_keyset_build disagree"
-    res["e2e"] = {"value": total_keys / dt, "unit": "keys/s", "ms": dt * 1e3, "h2d_bytes": int(blob.nbytes + key_off.nbytes),
-                  "d2h_bytes": int(n_words * 8), "what": "bsg_build(): pageable host keys -> staged H2D -> kernel -> staged D2H"}
+    res["e2e"] = {"value": total_keys / dt, "unit": "keys/s", "ms": dt * 1e3, "ms_each_call": [x * 1e3 for x in dts],
+                  "h2d_bytes": int(blob.nbytes + key_off.nbytes), "d2h_bytes": int(n_words * 8),
+                  "what": "bsg_build(): pageable host keys -> staged H2D -> kernel -> staged D2H (faster of two calls)"}
     if env.rank == 0 and not args.no_cpu:
         from oracle import cref
         threads = os.cpu_count() or 1
@@ -792,16 +798,18 @@ def config4_leg(env, args, peaks):
     out = bs.probe_hierarchical_gather(files, blocks, q, mw, W) if W > 1 else None
     n_e2e = 20
     env.barrier()
-    t0 = time.perf_counter()
+    ts = []
     for _ in range(n_e2e):
+        t0 = time.perf_counter()
         if W > 1:
             out = bs.probe_hierarchical_gather(files, blocks, q, mw, W)
         else:
             fm, bm = bs.probe_hierarchical(files, blocks, q)
-    dt = env.max(time.perf_counter() - t0) / n_e2e
-    res["e2e"] = {"value": probes / dt, "unit": "probes/s", "ms_per_query": dt * 1e3,
-                  "what": "bsg_probe_hierarchical_gather (host keys in, every rank's block mask out)" if W > 1
-                  else "bsg_probe_hierarchical (host keys in, file + block masks out)"}
+        ts.append(time.perf_counter() - t0)
+    dt = env.max(float(np.median(ts)))   # host-timed on a shared host: the median call, max over ranks
+    res["e2e"] = {"value": probes / dt, "unit": "probes/s", "ms_per_query": dt * 1e3, "ms_per_query_mean": float(np.mean(ts)) * 1e3,
+                  "what": ("bsg_probe_hierarchical_gather (host keys in, every rank's block mask out)" if W > 1
+                           else "bsg_probe_hierarchical (host keys in, file + block masks out)") + "; median of 20 calls"}
     if W > 1:
         assert np.array_equal(out[r][:len(bmask)], bmask)
     if r == 0 and not args.no_cpu:

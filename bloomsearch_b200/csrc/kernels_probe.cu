@@ -19,6 +19,8 @@
 //             words gathered straight from L2/HBM (the sparse 8*k bytes/probe bound).
 // tree_eval turns the (unit x key) bit matrix into the candidate mask with the
 // query's AND/OR tree (query_exec.go:89-125) in postfix form.
+#include <cstddef>
+
 #include "bsg_device.cuh"
 #include "bsg_internal.h"
 
@@ -288,8 +290,11 @@ probe_staged_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, con
 // Same bits as probe_staged (TestString is an AND over the k locations; the order in which clear
 // bits are discovered does not matter).
 constexpr uint32_t kStage2RowBitsOff = kProbeStageHeaderBytes;             // 32 x u32 result row
-constexpr uint32_t kStage2CntOff = kStage2RowBitsOff + 128;                // u32 survivors in queue
-constexpr uint32_t kStage2QueueOff = kStage2CntOff + 16;                   // 1024 x u16 key indexes
+// u32 survivors in queue: lives in StageRow::pad (always 0 in the row table), so every (re)fill of the stage zeroes it
+// through the bulk copy itself — no thread ever has to reset it (racecheck used to report the reset / next-read pair)
+constexpr uint32_t kStage2CntOff = 28;
+static_assert(offsetof(StageRow, pad) == kStage2CntOff, "the survivor count aliases StageRow::pad");
+constexpr uint32_t kStage2QueueOff = kStage2RowBitsOff + 128 + 16;         // 1024 x u16 key indexes
 static_assert(kStage2QueueOff + 2 * kProbeMaxKeysPerPass == kProbeStage2HeaderBytes, "stage2 header layout");
 static_assert(kProbeStage2HeaderBytes % 16 == 0, "bulk copies need 16-byte aligned destinations");
 
@@ -334,7 +339,6 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             mbar_init(&full[s], 1);
             mbar_init(&aready[s], kAllLanesArrive ? NA * 32 : NA);
             done[s] = 0;
-            *reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(s) * stage_bytes + kStage2CntOff) = 0;
         }
         fence_barrier_init();
     }
@@ -516,7 +520,6 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                 if (lane == 0) {
                     if (TRACE && tr && 4 + 8 * it < trace_slots) tr[4 + 8 * it] = globaltimer_ns();
                     done[s] = 0;
-                    *reinterpret_cast<uint32_t*>(st + kStage2CntOff) = 0;
                     const uint32_t nxt = it + S;
                     if (nxt < my_count) {
                         const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
