@@ -320,7 +320,8 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* aready = full + kProbeMaxStages;
-    uint32_t* done = reinterpret_cast<uint32_t*>(aready + kProbeMaxStages);
+    uint64_t* bdone = aready + kProbeMaxStages;   // every lane of the team's B warps is done reading the stage
+    static_assert(3 * kProbeMaxStages * 8 <= kProbe2SmemPrefixBytes, "prefix holds the three mbarrier arrays");
     uint8_t* stages = smem + kProbe2SmemPrefixBytes;
 
     const uint32_t tid = threadIdx.x;
@@ -338,7 +339,7 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&aready[s], kAllLanesArrive ? NA * 32 : NA);
-            done[s] = 0;
+            mbar_init(&bdone[s], T * 32);
         }
         fence_barrier_init();
     }
@@ -482,7 +483,11 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
             // every A warp has published its row words and survivors (usually the long wait of a B warp)
             mbar_wait_relaxed(&aready[s], ph, 1000u, relax_sleep_ns);
             if (TRACE && tr && member == 0 && lane == 0 && 3 + 8 * it < trace_slots) tr[3 + 8 * it] = globaltimer_ns();
-            const uint32_t n = ld_volatile_shared_u32(st + kStage2CntOff);
+            // the count was built with shared-memory atomics by the A warps; it is read the same way (one lane, then a
+            // shuffle) so that the tools see an atomic / atomic pair on this word
+            uint32_t n = 0;
+            if (lane == 0) n = atomicAdd(reinterpret_cast<uint32_t*>(st + kStage2CntOff), 0u);
+            n = __shfl_sync(0xffffffffu, n, 0);
             const uint32_t n_chunks = (n + 31) >> 5;
             const uint16_t* queue = reinterpret_cast<const uint16_t*>(st + kStage2QueueOff);
             // rotate the first chunk over the team's warps from unit to unit (even load per warp)
@@ -505,13 +510,14 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                 __syncwarp();
                 if (TRACE && tr && c == 0 && lane == 0 && 6 + 8 * it < trace_slots) tr[6 + 8 * it] = globaltimer_ns();  // chunk 0 tested
             }
-            __syncwarp();
-            uint32_t last = 0;
-            if (lane == 0) last = atom_add_acq_rel_shared(&done[s], 1u) == T - 1;
-            __syncwarp();  // reconverge before the shuffle
+            // hand-off of the stage: every lane that read it arrives on bdone[s]; the team's first warp waits for the
+            // whole team (an mbarrier phase per use of the stage: same parity as full[s]), then emits the row and refills.
+            // (Rounds 1-2 elected the last arriver with an acq_rel counter: same order, but a hand-off that
+            // compute-sanitizer racecheck does not model — it reported the refill against the team's reads.)
+            mbar_arrive(&bdone[s]);
             if (TRACE && tr && member == 0 && lane == 0 && 7 + 8 * it < trace_slots) tr[7 + 8 * it] = globaltimer_ns();
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {  // every warp of the team is done with this stage: emit the row, reset, refill
+            if (member == 0) {
+                mbar_wait(&bdone[s], ph);
                 const uint32_t unit = *reinterpret_cast<const uint32_t*>(st);
                 if (lane < out_words)
                     out_base[static_cast<size_t>(unit) * row_words32 + lane] =
@@ -519,7 +525,6 @@ probe_staged2_kernel(const StageRow* __restrict__ stab, uint32_t n_list_host, co
                 __syncwarp();
                 if (lane == 0) {
                     if (TRACE && tr && 4 + 8 * it < trace_slots) tr[4 + 8 * it] = globaltimer_ns();
-                    done[s] = 0;
                     const uint32_t nxt = it + S;
                     if (nxt < my_count) {
                         const uint4 a = *reinterpret_cast<const uint4*>(st + kStageRowBytes);
