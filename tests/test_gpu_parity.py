@@ -11,6 +11,7 @@ import bloomsearch_b200 as bs
 from bloomsearch_b200 import _native as N
 from oracle import bloomref as pyref
 from oracle import cref
+from oracle import murmur_canonical as canon
 from synth.corpus import SynthCorpus
 from tests.helpers import oracle_units, rand_keys, to_oracle_tuple
 
@@ -27,6 +28,20 @@ def test_hash_keys_matches_oracle_all_lengths(ctx):
     assert np.array_equal(got, want)
     # public MurmurHash3_x64_128 vectors (h0,h1 are murmur(key, seed 0))
     assert tuple(int(x) for x in got[keys.index(b"hello")][:2]) == (0xCBD8A7B341BD9B02, 0x5B1E906A48AE1D19)
+
+
+@pytest.mark.skipif(not canon.available(), reason="scikit-learn's copy of MurmurHash3.cpp is absent")
+def test_hash_keys_match_canonical_murmurhash3(ctx):
+    """THIRD-PARTY PIN: the device hash (csrc/bsg_device.cuh StreamHasher / base_hashes) against Austin Appleby's
+    MurmurHash3.cpp compiled unmodified (oracle/_ref, oracle/murmur_canonical.py): h0,h1 = murmur(key),
+    h2,h3 = murmur(key || 0x01) — what bloom/v3's sum256 documents — for every length 0..300, the virtual 0x01
+    byte at tail offsets 0 / 8 / 15 after many blocks, and long keys."""
+    rng = random.Random(77)
+    lens = list(range(0, 301)) + [1000, 4096, 4097, 70001] + [16 * b + t for b in (7, 40, 200) for t in (0, 8, 15)]
+    keys = [bytes(rng.randrange(256) for _ in range(L)) for L in lens for _ in range(2)] + [b"\x00" * 31, b"\xff" * 47, b"\x01"]
+    got = ctx.hash_keys(keys)
+    want = np.array([canon.base_hashes(k) for k in keys], dtype=np.uint64)
+    assert np.array_equal(got, want)
 
 
 def test_hash_keys_long_and_empty(ctx):

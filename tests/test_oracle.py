@@ -11,6 +11,7 @@ import pytest
 
 from oracle import bloomref as py
 from oracle import cref
+from oracle import murmur_canonical as canon
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -36,6 +37,45 @@ def test_base_hashes_second_half_is_murmur_of_data_plus_one():
         assert h[:2] == cref.murmur3_x64_128(d)
         assert h[2:] == cref.murmur3_x64_128(d + b"\x01")
         assert h == py.base_hashes(d)
+
+
+def _tail_shape_keys(seed):
+    """Every length 0..300 (all 16 tail shapes, several block counts), a few long keys, and the
+    tail lengths ADVICE r1 singles out (len % 16 in {0, 8, 15}) at several sizes."""
+    rng = random.Random(seed)
+    lens = list(range(0, 301)) + [1000, 4096, 4097, 70001] + [16 * b + t for b in (7, 40, 200) for t in (0, 8, 15)]
+    return [bytes(rng.randrange(256) for _ in range(L)) for L in lens for _ in range(3)] + [b"\x00" * 31, b"\xff" * 47, b"\x01"]
+
+
+@pytest.mark.skipif(not canon.available(), reason="scikit-learn's copy of MurmurHash3.cpp is absent")
+def test_hash_core_matches_canonical_murmurhash3():
+    """THIRD-PARTY PIN.  oracle/_ref/libmurmur3_canonical.so is Austin Appleby's MurmurHash3.cpp compiled
+    unmodified (oracle/Makefile `ref`); bloom/v3's sum256 documents strict equivalence with
+    MurmurHash3_x64_128(data) and MurmurHash3_x64_128(data || 0x01).  Both restatements must agree with it
+    for every tail shape, including the virtual 0x01 byte landing at tail offsets 0, 8 and 15."""
+    assert canon.murmur3_x64_128(b"hello") == (0xCBD8A7B341BD9B02, 0x5B1E906A48AE1D19)
+    vec = json.load(open(os.path.join(GOLDEN, "murmur3_x64_128.json")))["vectors"]
+    for v in vec:   # the canonical code reproduces the published known answers
+        assert canon.murmur3_x64_128(v["data"].encode()) == (int(v["h1"], 16), int(v["h2"], 16))
+    for d in _tail_shape_keys(11):
+        want = canon.base_hashes(d)
+        assert tuple(cref.base_hashes(d)) == want, len(d)
+        if len(d) <= 4097:
+            assert tuple(py.base_hashes(d)) == want, len(d)
+    for seed in (1, 0x9747B28C, 0xFFFFFFFF):   # the seeded core too (bloom/v3 uses seed 0 only)
+        for d in (b"", b"a", b"0123456789abcdef", b"0123456789abcdefg" * 3):
+            assert cref.murmur3_x64_128(d, seed) == canon.murmur3_x64_128(d, seed)
+
+
+@pytest.mark.skipif(not canon.available(), reason="scikit-learn's copy of MurmurHash3.cpp is absent")
+def test_fixture_base_hashes_match_canonical_murmurhash3():
+    """The committed oracle-pin fixtures (tests/golden/bloom_golden.json) carry the base hashes of 19 keys:
+    every one of them equals the canonical code's output, so the fixtures are not merely self-consistent."""
+    g = json.load(open(os.path.join(GOLDEN, "bloom_golden.json")))
+    assert len(g["base_hashes"]) >= 19
+    for e in g["base_hashes"]:
+        key = e["key"].encode("utf-8")
+        assert tuple(int(x, 16) for x in e["h"]) == canon.base_hashes(key), e["key"]
 
 
 def test_location_pattern():
