@@ -283,6 +283,19 @@ def _capture_stdout():
         os.dup2(2, 1)
 
 
+_PENDING = None   # rank 0: the headline line, complete before the extra legs start (see _emit_pending)
+
+
+def _emit_pending(reason: str):
+    """The headline measurements must not be lost because a LATER leg failed (or a peer rank died and the launcher
+    is tearing the job down): print the line that was ready, with the failure named in it."""
+    global _PENDING
+    if _PENDING is not None:
+        out, _PENDING = _PENDING, None
+        out["extra_legs_error"] = reason
+        emit(out)
+
+
 def emit(obj):
     line = (json.dumps(obj) + "\n").encode()
     if _JSON_FD is None:
@@ -835,7 +848,34 @@ def config4_leg(env, args, peaks):
     return res
 
 
+def headline_line(env, args, results, cpu):
+    r = results[args.workload]
+    out = {
+        "metric": "bloom probes/sec (block-level)", "value": r["value"], "unit": "probes/s", "n_gpus": env.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_string(args.workload),
+                   "keys_per_batch": N_KEYS, "batches_per_step": BATCHES_PER_STEP, "blocks_per_gpu": r["n_units_per_gpu"],
+                   "bitset_mb_per_gpu": r["bitset_mb"],
+                   "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per launch "
+                         f"({r['replicas'] * r['bitset_mb']:.0f} MB > 126 MB L2): inputs larger than L2",
+                   "sharding": "every rank owns its own 10M-row shard (sharded by file); no data-path collective in this "
+                               "leg — the product's collectives are timed in the config4 / config5 legs",
+                   "timed_launches": f"{BATCHES_PER_STEP} probe launches per step issued from C, round-robin on "
+                                     f"{args.streams} streams forked from / joined to the timed stream (independent "
+                                     "batches overlap tail-to-head); roofline.frac is the ONE-stream figure"},
+        "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "clocks": r["clocks"],
+        "gpu_launches": r["launches_per_step"] * args.steps,
+        "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],
+                     "e2e": v["e2e"]} for w, v in results.items() if w != args.workload},
+    }
+    if env.comm:
+        out["comm"] = {"peer_memory": env.comm["peer_memory"], "world": env.world}
+    return out
+
+
 def main():
+    global _PENDING
     _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -874,43 +914,24 @@ def main():
     for wl in [args.workload] + ([] if args.no_also else [w for w in WORKLOADS if w != args.workload]):
         results[wl], cpu_wl = probe_leg(env, args, wl, wl == args.workload, peaks, ncu)
         cpu = cpu or cpu_wl
-    extra = {}
+    # the headline line is complete here; it is kept pending (and printed by the failure handlers below main) while
+    # the extra legs run, each of which adds its block to it as it finishes
+    out = headline_line(env, args, results, cpu) if env.rank == 0 else {}
     if not args.no_extra:
+        _PENDING = out if env.rank == 0 else None
         t = time.time()
-        extra["build"], data = build_leg(env, args, peaks)
+        out["build"], data = build_leg(env, args, peaks)
         log(f"build leg done ({time.time() - t:.0f}s)")
         t = time.time()
-        extra["config5"] = config5_leg(env, args, peaks, data)
+        out["config5"] = config5_leg(env, args, peaks, data)
         del data
         log(f"config5 leg done ({time.time() - t:.0f}s)")
         t = time.time()
-        extra["config4"] = config4_leg(env, args, peaks)
+        out["config4"] = config4_leg(env, args, peaks)
         log(f"config4 leg done ({time.time() - t:.0f}s)")
 
     if env.rank == 0:
-        r = results[args.workload]
-        out = {
-            "metric": "bloom probes/sec (block-level)", "value": r["value"], "unit": "probes/s", "n_gpus": env.world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_string(args.workload),
-                       "keys_per_batch": N_KEYS, "batches_per_step": BATCHES_PER_STEP, "blocks_per_gpu": r["n_units_per_gpu"],
-                       "bitset_mb_per_gpu": r["bitset_mb"],
-                       "l2": f"{r['replicas']} distinct HBM replicas of the corpus cycled per launch "
-                             f"({r['replicas'] * r['bitset_mb']:.0f} MB > 126 MB L2): inputs larger than L2",
-                       "sharding": "every rank owns its own 10M-row shard (sharded by file); no data-path collective in this "
-                                   "leg — the product's collectives are timed in the config4 / config5 legs",
-                       "timed_launches": f"{BATCHES_PER_STEP} probe launches per step issued from C, round-robin on "
-                                         f"{args.streams} streams forked from / joined to the timed stream (independent "
-                                         "batches overlap tail-to-head); roofline.frac is the ONE-stream figure"},
-            "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"], "clocks": r["clocks"],
-            "gpu_launches": r["launches_per_step"] * args.steps,
-            "also": {w: {"probes_per_s": v["value"], "ms_per_step": v["ms_per_step"], "roofline": v["roofline"],
-                         "e2e": v["e2e"]} for w, v in results.items() if w != args.workload},
-        }
-        if env.comm:
-            out["comm"] = {"peer_memory": env.comm["peer_memory"], "world": env.world}
-        out.update(extra)
+        _PENDING = None
         emit(out)
     if env.world > 1:
         env.dist.barrier()
@@ -920,10 +941,17 @@ def main():
 
 
 if __name__ == "__main__":
+    import signal
+
+    def _on_term(signum, frame):   # the launcher tears the job down because a peer rank failed
+        _emit_pending(f"terminated by signal {signum} during the extra legs (a peer rank failed?)")
+        os._exit(1)
+    signal.signal(signal.SIGTERM, _on_term)
     try:
         main()
-    except BaseException:  # a failed rank must not leave its peers waiting in a collective until the watchdog fires
+    except BaseException as e:  # a failed rank must not leave its peers waiting in a collective until the watchdog fires
         import traceback
         traceback.print_exc()
         sys.stderr.flush()
+        _emit_pending(f"{type(e).__name__}: {e}"[:400])
         os._exit(1)

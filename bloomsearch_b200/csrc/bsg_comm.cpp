@@ -110,6 +110,7 @@ struct Comm {
     uint8_t* d_xchg = nullptr;      // 64 B x world: IPC handle exchange
     std::mutex mu;
     uint64_t nvlink_bytes = 0;      // bytes this rank moved over NVLink in the last collective (reporting)
+    uint64_t timeout_ns = 120ull * 1000000000ull;  // BSG_COMM_TIMEOUT_S: longest a collective kernel waits for a peer
 };
 
 }  // namespace
@@ -146,6 +147,7 @@ struct PeerPtrs { uint8_t* p[kMaxPeers]; };
 struct Sig {
     Ctl* mine;                 // this rank's control block
     Ctl* peer[kMaxPeers];      // every rank's control block as mapped here (peer[rank] == mine)
+    uint64_t timeout_ns;       // a flag wait longer than this traps the kernel (0 = wait for ever)
     uint32_t epoch;
     int rank, world;
 };
@@ -165,6 +167,24 @@ __device__ __forceinline__ uint4 ld_peer_u4(const uint4* p) {
     return v;
 }
 
+__device__ __forceinline__ uint64_t comm_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spins until *flag has reached `epoch`.  A peer that never arrives (its process died, its stream is stuck)
+// must not leave this GPU spinning for ever: after timeout_ns the kernel traps, the context reports a launch
+// failure at the next CUDA call and the caller fails loudly instead of hanging (BSG_COMM_TIMEOUT_S, default 120).
+__device__ __forceinline__ void comm_wait_flag(const uint32_t* flag, uint32_t epoch, uint64_t timeout_ns) {
+    if (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) >= 0) return;
+    const uint64_t t0 = comm_timer_ns();
+    uint32_t polls = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) < 0) {
+        if ((++polls & 0xfffu) == 0 && timeout_ns && comm_timer_ns() - t0 > timeout_ns) asm volatile("trap;");
+    }
+}
+
 // "my input is ready / my output may be overwritten": announce to every peer, then wait for all of them.
 // Executed by every CTA (the announcement by CTA 0 only); ends with a CTA barrier.
 __device__ __forceinline__ void comm_ready_barrier(const Sig& s) {
@@ -172,9 +192,7 @@ __device__ __forceinline__ void comm_ready_barrier(const Sig& s) {
         __threadfence_system();
         st_release_sys(&s.peer[threadIdx.x]->ready[s.rank], s.epoch);
     }
-    if (threadIdx.x < static_cast<uint32_t>(s.world))
-        while (static_cast<int32_t>(ld_acquire_sys(&s.mine->ready[threadIdx.x]) - s.epoch) < 0) {
-        }
+    if (threadIdx.x < static_cast<uint32_t>(s.world)) comm_wait_flag(&s.mine->ready[threadIdx.x], s.epoch, s.timeout_ns);
     __syncthreads();
 }
 
@@ -191,8 +209,7 @@ __device__ __forceinline__ void comm_done_barrier(const Sig& s) {
     if (threadIdx.x < static_cast<uint32_t>(s.world)) {
         __threadfence_system();
         st_release_sys(&s.peer[threadIdx.x]->done[s.rank], s.epoch);
-        while (static_cast<int32_t>(ld_acquire_sys(&s.mine->done[threadIdx.x]) - s.epoch) < 0) {
-        }
+        comm_wait_flag(&s.mine->done[threadIdx.x], s.epoch, s.timeout_ns);
     }
     __syncthreads();
 }
@@ -340,6 +357,7 @@ extern "C" int bsg_comm_init(bsg_ctx* ctx, int rank, int world, const uint8_t nc
     Comm* c = new Comm();
     c->rank = rank;
     c->world = world;
+    if (const char* t = getenv("BSG_COMM_TIMEOUT_S")) c->timeout_ns = static_cast<uint64_t>(std::max(0.0, atof(t)) * 1e9);
     c->device = bsg_ctx_device_internal(ctx);
     auto body = [&]() -> int {
         CU_TRY(cudaSetDevice(c->device));
@@ -452,6 +470,7 @@ static Sig make_sig(Comm* c) {
     s.mine = reinterpret_cast<Ctl*>(c->ctl.local);
     for (int p = 0; p < kMaxPeers; ++p) s.peer[p] = p < c->world ? reinterpret_cast<Ctl*>(c->ctl.peer[p]) : nullptr;
     s.epoch = ++c->epoch;
+    s.timeout_ns = c->timeout_ns;
     s.rank = c->rank;
     s.world = c->world;
     return s;

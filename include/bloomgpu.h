@@ -317,7 +317,11 @@ int bsg_timer_end(bsg_ctx *ctx, float *elapsed_ms); /* records, synchronises, re
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------- *
  * nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 (bsg_comm_unique_id)
- * and distributed by the host (the Go side would ship it over its own RPC). */
+ * and distributed by the host (the Go side would ship it over its own RPC).
+ * Environment, read at bsg_comm_init: BSG_COMM_P2P=0 forces the NCCL path; BSG_COMM_TIMEOUT_S (default
+ * 120, 0 = wait for ever) bounds how long a peer-memory collective kernel waits for a peer's flag — a
+ * peer that never arrives traps the kernel, and the next call on this ctx returns BSG_ERR_CUDA
+ * instead of the GPU spinning for ever. */
 int bsg_comm_unique_id(uint8_t out_id[128]);
 int bsg_comm_init(bsg_ctx *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
 /* rank / world of the communicator; *peer_memory = 1 when the collectives run as single kernels over
