@@ -20,9 +20,15 @@
  *
  * PARITY STATUS: "parity unpinned" at the bit level.  No Go toolchain exists in
  * the build container and the reference's tests hold no golden bitsets
- * (SURVEY.md §8c).  What IS pinned: the murmur3 core against the public
- * MurmurHash3_x64_128 vectors (the same ones spaolacci/murmur3's test-suite
- * uses, which bloom/v3 documents strict equivalence with), CRC32C against its
+ * (SURVEY.md §8c).  What IS pinned: the murmur3 core — bref_base_hashes for
+ * every key length and tail shape — against Austin Appleby's canonical
+ * MurmurHash3.cpp, compiled unmodified out of scikit-learn's tree into
+ * oracle/_ref (oracle/Makefile `ref`, oracle/murmur_canonical.py,
+ * tests/test_oracle.py), and against the public MurmurHash3_x64_128 vectors
+ * (the same ones spaolacci/murmur3's test-suite uses, which bloom/v3 documents
+ * strict equivalence with); what is NOT pinned against third-party code is the
+ * composition (location, % m, bit order, WriteTo, EstimateParameters).  Also
+ * pinned: CRC32C against its
  * standard check value, the (m,k) table of SURVEY.md §8(c), the semantic pins of
  * the reference's tests (tree semantics, sizing, FPR budget, round trip), and
  * an independent Python restatement (oracle/bloomref.py) that must agree with

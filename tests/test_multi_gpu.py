@@ -147,3 +147,61 @@ def test_or_reduce_and_mask_allgather_over_nccl():
         p.join(timeout=60)
     for rank, ok_or, ok_probe, err in res:
         assert ok_or and ok_probe, f"rank {rank}: or={ok_or} probe={ok_probe}\n{err}"
+
+
+def _timeout_worker(rank, world, uid_q, res_q, done_evt):
+    """Rank 0 enters a peer-memory collective its peer never joins: the kernel must trap after
+    BSG_COMM_TIMEOUT_S instead of spinning for ever, and the failure must surface as an exception."""
+    import os
+    import time
+    os.environ["BSG_COMM_TIMEOUT_S"] = "2"
+    import bloomsearch_b200 as bs
+    try:
+        torch.cuda.set_device(rank)
+        ctx = bs.Context(rank)
+        if rank == 0:
+            uid = bs.Context.comm_unique_id()
+            for _ in range(world - 1):
+                uid_q.put(uid)
+        else:
+            uid = uid_q.get(timeout=120)
+        ctx.comm_init(rank, world, uid)
+        peer_memory = ctx.comm_info()["peer_memory"]
+        d = ctx.comm_alloc(4096 * 8)
+        if rank == 0:
+            if not peer_memory:   # the NCCL path has its own watchdog; nothing to test here
+                res_q.put((0, "skip", 0.0))
+            else:
+                t0 = time.time()
+                try:
+                    ctx.or_reduce_device(d, 4096)
+                    ctx.synchronize()
+                    res_q.put((0, "no error raised", time.time() - t0))
+                except Exception as e:  # noqa: BLE001
+                    res_q.put((0, "raised: " + str(e)[:200], time.time() - t0))
+        done_evt.wait(timeout=120)
+    except Exception:  # noqa: BLE001
+        import traceback
+        res_q.put((rank, "setup failed: " + traceback.format_exc(), 0.0))
+    os._exit(0)   # rank 0's context is dead after the trap and clean-up is collective: leave without it
+
+
+def test_collective_traps_instead_of_hanging_on_a_missing_peer():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctxmp = mp.get_context("spawn")
+    uid_q, res_q, done_evt = ctxmp.Queue(), ctxmp.Queue(), ctxmp.Event()
+    procs = [ctxmp.Process(target=_timeout_worker, args=(r, world, uid_q, res_q, done_evt)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        rank, what, dt = res_q.get(timeout=180)
+    finally:
+        done_evt.set()
+        for p in procs:
+            p.join(timeout=60)
+    if what == "skip":
+        pytest.skip("communicator runs over NCCL (no peer memory)")
+    assert what.startswith("raised: "), what
+    assert 1.5 <= dt < 60, dt
