@@ -3,6 +3,10 @@
 corpus (one process; a fresh bsg context per setting since the knobs are read at bsg_create).
 
   python scripts/sweep_tiles.py 2b "BSG_PROBE_VARIANT=3" "BSG_TILES_SHAPE=0" "BSG_TILES_SHAPE=1 BSG_TILE_BYTES=16384" ...
+  python scripts/sweep_tiles.py 600x15000 "BSG_PROBE_VARIANT=7" "SWEEP_PATH=gather"     # 600 blocks of 15 000 rows (~105 KB units)
+
+A workload is a bench.py name (2a, 2b) or <blocks>x<rows per block>; SWEEP_PATH=gather in a setting times the gather
+kernel instead of the staged path.
 
 Prints per setting: us/launch on one stream (PDL as configured), on two streams, and whether the matrix
 equals the first setting's (the first setting should be a trusted kernel)."""
@@ -26,6 +30,9 @@ def main():
     steps = int(os.environ.get("SWEEP_STEPS", "200"))
     n_rep = int(os.environ.get("SWEEP_REPLICAS", "8"))
     scale = float(os.environ.get("SWEEP_SCALE", "1.0"))
+    if "x" in wl:
+        nb, rows = (int(x) for x in wl.split("x"))
+        bench.WORKLOADS[wl] = (nb, rows, min(100, nb))
     c = bench.gen_corpus(wl, 0, scale)
     ctx0 = bs.Context(0)
     desc, n_words = bench.size_filters(c, bs)
@@ -36,7 +43,6 @@ def main():
     L = N.lib()
     L.bsg_debug_run_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
     ref = None
-    RUN = N.PROBE_STAGED | N.RUN_MATRIX_ONLY
     touched = set()
     for setting in settings:
         for k in touched:
@@ -45,11 +51,13 @@ def main():
             k, v = kv.split("=")
             os.environ[k] = v
             touched.add(k)
+        path = N.PROBE_GATHER if os.environ.get("SWEEP_PATH") == "gather" else N.PROBE_STAGED
+        RUN = path | N.RUN_MATRIX_ONLY
         ctx = bs.Context(0)
         try:
             corpora = [bs.Corpus(ctx, desc, words) for _ in range(n_rep)]
             queries = [bs.Query(cp, keys, kinds, None) for cp in corpora]
-            queries[0].run(N.PROBE_STAGED)
+            queries[0].run(path)
             got, _ = queries[0].fetch()
             if ref is None:
                 ref = got
@@ -81,7 +89,13 @@ def main():
                 corpora[i % n_rep].probe_packed(blob, off, kinds, None, outm, None)
             e2e_us = (time.perf_counter() - t0) / 100 * 1e6
             same_e2e = bool(np.array_equal(outm, ref))
-            print(f"{wl} [{setting}] 1-stream {out[0]:.2f} us  2-stream {out[1]:.2f} us  bsg_probe {e2e_us:.1f} us/call  "
+            unit_kb = n_words * 8 / n_units / 1e3
+            L.bsg_debug_probe_kernel_name.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
+            name_buf = C.create_string_buffer(512)
+            N.check(L.bsg_debug_probe_kernel_name(ctx.handle, corpora[0].handle, name_buf, 512))
+            kname = "probe_gather_kernel" if path == N.PROBE_GATHER else name_buf.value.decode()
+            gbs = n_words * 8 / (out[0] * 1e-6) / 1e9
+            print(f"{wl} ({unit_kb:.0f} KB/unit; {kname}; {gbs:.0f} GB/s of bitsets on one stream) [{setting}] 1-stream {out[0]:.2f} us  2-stream {out[1]:.2f} us  bsg_probe {e2e_us:.1f} us/call  "
                   f"parity {'ok' if same and same_e2e else 'MISMATCH'}", flush=True)
             for q in queries:
                 q.close()
