@@ -1197,8 +1197,9 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
     auto tile_filter = [&](uint64_t u, int k, uint64_t rel_bytes) {
         const DevFilter& d = L.udesc[u * 3 + k];
         if (d.m == 0) return tile_filter_absent();
+        // offsets count from the start of the stage (the kernel adds one base, not header + data)
         return TileFilter{static_cast<uint32_t>(d.m), static_cast<uint32_t>(d.inv >> 32), static_cast<uint32_t>(d.inv),
-                          (static_cast<uint32_t>(rel_bytes) << 8) | static_cast<uint32_t>(d.k)};
+                          (static_cast<uint32_t>(rel_bytes + kTileBitmapOff) << 8) | static_cast<uint32_t>(d.k)};
     };
     auto small_k = [&](uint64_t u, int k) { const DevFilter& d = L.udesc[u * 3 + k]; return d.m && d.k < 4; };
     if (kind_mode) {
@@ -1209,6 +1210,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
             for (int part = 0; part < 2; ++part) {
                 TileRec r;
                 memset(&r, 0, sizeof(r));
+                r.ones = 0xffffffffu;
                 for (auto& fu : r.f) for (auto& fk : fu) fk = tile_filter_absent();
                 r.n_units = 1;
                 r.part_kinds = part == 0 ? 3u : 4u;
@@ -1260,6 +1262,7 @@ int build_tiles(bsg_ctx* ctx, bsg_corpus* c, const Layout& L, cudaStream_t s) {
                 close_tile();
             if (!open) {
                 memset(&r, 0, sizeof(r));
+                r.ones = 0xffffffffu;
                 for (auto& fu : r.f) for (auto& fk : fu) fk = tile_filter_absent();
                 r.part_kinds = 7u;
                 r.flags = kTileFirstPart | kTileLastPart;

@@ -179,7 +179,7 @@ __device__ __forceinline__ uint64_t mod_m(uint64_t x, uint64_t m, uint64_t inv) 
 //   x*I/2^64, each < 1, and x/m - x*I/2^64 is in [0,1)), so x - q_full*m is in [0, 3m), below 2^32 for m < 2^30.
 // A value below 2^32 is determined by its residue mod 2^32, and that residue needs only q_full mod 2^32:
 //   q = lo32(xh*Ih) + hi32((xh*Il + xl*Ih) mod 2^64),   r = lo32(xl - q*m)  — exact, then two conditional
-// subtractions (2m, m), each min(v, v - c): v - c wraps above v exactly when v < c.
+// subtractions of m (3m -> 2m -> m; no 2m has to be formed), each min(v, v - m): v - m wraps above v exactly when v < m.
 // No quotient ever has to fit 32 bits, so there is no separate reduction of xh (rounds 1-2 spent 12 instructions
 // on a two-step form).  (proof in DESIGN.md §5; m == 1 works through inv = 2^64-1; checked against 128-bit
 // arithmetic by tests/test_host_logic.py::test_mod_m32_formula.)
@@ -196,8 +196,8 @@ __device__ __forceinline__ uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih,
     const uint32_t nm = 0u - m;               // one negation per filter (hoisted), not one per location: written as
     uint32_t r;                               // C++, q * nm + xl is turned back into m * (-q) + xl
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(nm), "r"(xl));   // x - q_full*m, in [0, 3m)
-    r = min(r, r - 2u * m);
-    r = min(r, r - m);
+    r = min(r, r - m);   // [0, 3m) -> [0, 2m)
+    r = min(r, r - m);   //         -> [0, m)
     return r;
 }
 // Word index of a bit, opaque to the optimiser: `w32[bit >> 5]` is canonicalised to ((bit >> 3) & ~3) + base

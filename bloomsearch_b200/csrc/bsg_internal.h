@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the kernels and the C-ABI layer.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -108,12 +109,13 @@ constexpr uint32_t kTileMaxUnits = 8;
 struct __align__(16) TileFilter {  // staged filters: m < 2^30, k < 2^8, at most 16 MB into the tile data
     uint32_t m;        // bits
     uint32_t ih, il;   // hi / lo halves of floor(2^64/m), see mod_m32
-    uint32_t krel;     // (byte offset of the filter's words inside the tile data) << 8 | k
+    uint32_t krel;     // (byte offset of the filter's words from the START OF THE STAGE, header included) << 8 | k
 };
-// An ABSENT filter (Go nil: cannot disqualify, query_exec.go:137-151) is k = 0 and reads as a one-bit filter at
-// offset 0 (m = 1: every location reduces to bit 0 of the tile's first word), so the first tests of a key need
-// neither a predicate nor a zero-filled copy of the descriptor; the same record fills the kinds a KIND-mode tile
-// does not carry.
+// An ABSENT filter (Go nil: cannot disqualify, query_exec.go:137-151) is k = 0 and reads as a one-bit filter
+// (m = 1: every location reduces to bit 0) whose only word is TileRec::ones in the stage header, which is all
+// ones: the first tests of a key PASS on it with no predicate, no special case and no zero-filled copy of the
+// descriptor (round B1 then sets the key's bit because k <= NT); the same record fills the kinds a KIND-mode
+// tile does not carry.
 constexpr uint32_t kTileMaxK = 255;
 #if defined(__CUDACC__)
 #define BSG_HD __host__ __device__
@@ -122,7 +124,8 @@ constexpr uint32_t kTileMaxK = 255;
 #endif
 BSG_HD inline uint32_t tile_k(uint32_t krel) { return krel & 0xffu; }
 BSG_HD inline uint32_t tile_rel(uint32_t krel) { return krel >> 8; }
-inline TileFilter tile_filter_absent() { return TileFilter{1u, 0xffffffffu, 0xffffffffu, 0u}; }
+constexpr uint32_t kTileOnesOff = 12;   // offsetof(TileRec, ones)
+inline TileFilter tile_filter_absent() { return TileFilter{1u, 0xffffffffu, 0xffffffffu, kTileOnesOff << 8}; }
 struct __align__(16) TileFill {    // what the thread that (re)fills a stage needs
     uint64_t word_base;            // first word of the tile's data in the corpus words array (even)
     uint32_t data_bytes;           // all filters of the tile, 16-byte multiple
@@ -134,13 +137,14 @@ struct __align__(16) TileRec {
     uint32_t n_units;     // 1..kTileMaxUnits
     uint32_t part_kinds;  // kinds this tile covers (7 in UNIT mode; 3 or 4 in KIND mode)
     uint32_t flags;       // kTileFirstPart | kTileLastPart | kTileSmallK
-    uint32_t pad0;
+    uint32_t ones;        // 0xffffffff: the word an absent filter's record points at (tile_filter_absent)
     TileFill fill;
     uint32_t unit[kTileMaxUnits];         // global unit ids (matrix rows)
     TileFilter f[kTileMaxUnits][3];       // [unit in tile][kind]
     uint32_t pad1[4];
 };
 static_assert(sizeof(TileRec) == 512, "TileRec must be 512 bytes");
+static_assert(offsetof(TileRec, ones) == kTileOnesOff, "tile_filter_absent points at TileRec::ones");
 constexpr uint32_t kTileRecFixedBytes = 16 + 64 + 32;   // head + fill + unit ids; the descriptors follow
 constexpr uint32_t kTileDescOff = kTileRecFixedBytes;
 constexpr uint32_t kTileFirstPart = 1u, kTileLastPart = 2u, kTileSmallK = 4u;  // SmallK: some filter has k < 4

@@ -81,11 +81,11 @@ __device__ __forceinline__ void fill_tile(uint8_t* st, uint64_t* bar, const Tile
 }
 
 // NT membership tests of one key against one staged filter, no branch between them.
-// f = {m, ih, il, k << 16 | rel16}; SMALLK: some filter of the tile has k < 4, so location t exists
-// only when t < k.
+// f = {m, ih, il, rel << 8 | k}, rel counted from the stage start `st`; SMALLK: some filter of the tile has
+// k < 4, so location t exists only when t < k.
 template <int NT, bool SMALLK>
-__device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uint4 f, const uint8_t* data) {
-    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
+__device__ __forceinline__ bool first_tests(const uint64_t (&loc)[NT], const uint4 f, const uint8_t* st) {
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(st + tile_rel(f.w));
     uint32_t bit[NT], wv[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[t], f.x, f.y, f.z);
@@ -238,51 +238,53 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
         if (TRACE && tr && tid == 0 && 2 + 8 * n < a.trace_slots) tr[2 + 8 * n] = globaltimer_ns();
         const uint4 head = *reinterpret_cast<const uint4*>(st);  // n_units, part_kinds, flags
         const uint32_t my_unit = warp < head.x ? *reinterpret_cast<const uint32_t*>(st + 16 + 64 + 4 * warp) : 0u;
-        const uint8_t* data = st + a.hdr_bytes;
         // ---------------------------------------------------------------- round A ---
         if (warp_kinds & head.y) {
-            // every thread keeps, per key slot, the set of units whose first tests its key passed (bit u = unit u of
-            // the tile): one predicated OR per (key, unit), no ballot, no shared-memory traffic inside the loop, so
-            // consecutive units overlap; then ONE warp scan + ONE atomic per warp per tile reserve the warp's range
-            // of L1 and every thread appends its own few survivors (L1's order is free)
+            // every thread keeps, per key slot, the set of units whose first tests its key passed: one funnel shift
+            // per (key, unit) pushes the AND of the tested bits into the mask from the top (bit 0 of `p` is the
+            // verdict, the bits above it are junk and fall off), no predicate, no ballot, no shared-memory traffic
+            // inside the loop, so consecutive units overlap; the mask is shifted down once after the loop.  Then
+            // ONE warp scan + ONE atomic per warp per tile reserve the warp's range of L1 and every thread appends
+            // its own few survivors (L1's order is free)
             uint32_t umask[KPT];
 #pragma unroll
             for (int j = 0; j < KPT; ++j) umask[j] = 0;
             auto unit_loop = [&](auto small_k) {
                 constexpr bool SMALLK = decltype(small_k)::value;
                 const uint8_t* desc = st + kTileDescOff;
-                uint32_t ubit = 1u;
 #pragma unroll 2
-                for (uint32_t u = 0; u < head.x; ++u, desc += 48, ubit <<= 1) {
+                for (uint32_t u = 0; u < head.x; ++u, desc += 48) {
 #pragma unroll
                     for (int j = 0; j < KPT; ++j) {
                         // a key slot of a kind this tile does not carry reads an absent-filter record (see
                         // TileFilter) and is masked out after the loop
                         const uint4 f = *reinterpret_cast<const uint4*>(desc + koff[j]);
-                        // absent filter (k == 0, encoded as m = 1 at offset 0 so that the loads below need no
-                        // predicate): cannot disqualify (query_exec.go:137-151) -> round B1 sets the bit
-                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
+                        // absent filter (k == 0): a one-bit filter whose word is all ones (TileRec::ones), so the
+                        // tests pass by themselves — cannot disqualify (query_exec.go:137-151) — and round B1 sets the bit
+                        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(st + tile_rel(f.w));
                         uint32_t bit[NT], wv[NT];
 #pragma unroll
                         for (int t = 0; t < NT; ++t) bit[t] = mod_m32(loc[j][t], f.x, f.y, f.z);
 #pragma unroll
                         for (int t = 0; t < NT; ++t) wv[t] = w32[word_index(bit[t])];
-                        uint32_t p = 1u;
+                        uint32_t p = 0xffffffffu;
 #pragma unroll
                         for (int t = 0; t < NT; ++t) {
                             uint32_t b = wv[t] >> (bit[t] & 31u);
                             if (SMALLK) b |= static_cast<uint32_t>(tile_k(f.w) <= static_cast<uint32_t>(t));
                             p &= b;
                         }
-                        if (tile_k(f.w) == 0u || (p & 1u) != 0u) umask[j] |= ubit;
+                        umask[j] = __funnelshift_r(umask[j], p, 1);   // (umask >> 1) | (p << 31)
                     }
                 }
             };
             if (head.z & kTileSmallK) unit_loop(std::true_type{});
             else unit_loop(std::false_type{});
+            const uint32_t down = 32u - head.x;   // unit u entered u-th: it sits at bit 32 - n_units + u
             uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < KPT; ++j) {
+                umask[j] >>= down;
                 if ((kbit[j] & head.y) == 0) umask[j] = 0;   // not a key of this tile's kinds (or no key at all)
                 mine += __popc(umask[j]);
             }
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
                 bool fin = k <= static_cast<uint32_t>(NT);   // absent filter (k == 0), or every location already passed
                 if (!fin) {
                     const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
-                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(data + tile_rel(f.w));
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(st + tile_rel(f.w));
                     uint32_t ok = 1u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {   // locations NT..NT+3: i%4 == 0: h0+i*h2, 1: h1+i*h3, 2: h0+i*h3, 3: h1+i*h2
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR) probe_tiles_kernel(const Pr
             const uint4 f = *reinterpret_cast<const uint4*>(st + kTileDescOff + u * 48u + (si >> 14) * 16u);
             const ulonglong2 x = htab[2 * slot], y = htab[2 * slot + 1];
             if (test_from_s32<NT + 4>(x.x, x.y, y.x, y.y, f.x, f.y, f.z, tile_k(f.w),
-                                      reinterpret_cast<const uint32_t*>(data + tile_rel(f.w)))) {
+                                      reinterpret_cast<const uint32_t*>(st + tile_rel(f.w)))) {
                 const uint32_t pos = si & 0x3ffu;
                 atomicOr(&rows[u * 32u + (pos >> 5)], 1u << (pos & 31u));
             }

@@ -11,7 +11,7 @@ static uint32_t mod_m32(uint64_t x, uint32_t m, uint32_t ih, uint32_t il){
     uint64_t s=(uint64_t)xl*ih; s+= (uint64_t)xh*il; // wraps mod 2^64
     uint32_t q=(uint32_t)(s>>32)+xh*ih;
     uint32_t r=q*nm+xl;
-    r=umin(r,r-2u*m); r=umin(r,r-m); return r;
+    r=umin(r,r-m); r=umin(r,r-m); return r;
 }
 static uint64_t rnd_state=88172645463325252ull;
 static uint64_t rnd(){rnd_state^=rnd_state<<13;rnd_state^=rnd_state>>7;rnd_state^=rnd_state<<17;return rnd_state;}
