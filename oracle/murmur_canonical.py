@@ -1,4 +1,8 @@
-"""ctypes binding of oracle/_ref/libmurmur3_canonical.so — THIRD-PARTY PIN, TEST INFRASTRUCTURE ONLY.
+"""ctypes bindings of the third-party pins under oracle/_ref/ — TEST INFRASTRUCTURE ONLY.
+
+(1) libmurmur3_canonical.so, below; (2) libcrc32c_hw.so: CRC32C computed by the CPU's SSE4.2 `crc32`
+instruction (oracle/pins/crc32c_hw.c), against which the oracle's table-driven CRC32C is checked — the
+checksum of every filter section (/root/reference/file_format.go:44,379,399).
 
 The library is Austin Appleby's canonical MurmurHash3.cpp (public domain; the SMHasher source),
 compiled UNMODIFIED from where scikit-learn ships it in this image (sklearn/utils/src/, see
@@ -56,3 +60,37 @@ def murmur3_x64_128(data: bytes, seed: int = 0) -> tuple[int, int]:
 def base_hashes(data: bytes) -> tuple[int, int, int, int]:
     """What bloom/v3 documents baseHashes(data) to equal, computed ONLY with the canonical code."""
     return murmur3_x64_128(data) + murmur3_x64_128(data + b"\x01")
+
+
+# ---- second pin: CRC32C by the CPU's own SSE4.2 instruction (oracle/pins/crc32c_hw.c) ----
+_SO_CRC = os.path.join(_HERE, "_ref", "libcrc32c_hw.so")
+_lib_crc = None
+
+
+def build_crc32c_hw() -> str | None:
+    """Compiles the hardware CRC32C pin on x86-64 hosts with SSE4.2; returns the .so path or None."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    if "sse4_2" not in flags:
+        return None
+    if not os.path.exists(_SO_CRC):
+        subprocess.call(["make", "-s", "-C", _HERE, "ref-crc"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _SO_CRC if os.path.exists(_SO_CRC) else None
+
+
+def crc32c_hw_available() -> bool:
+    return build_crc32c_hw() is not None
+
+
+def crc32c_hw(data: bytes) -> int:
+    global _lib_crc
+    if _lib_crc is None:
+        so = build_crc32c_hw()
+        if so is None:
+            raise RuntimeError("no SSE4.2 crc32 instruction on this host")
+        _lib_crc = C.CDLL(so)
+        _lib_crc.crc32c_hw.argtypes = [C.c_char_p, C.c_size_t]
+        _lib_crc.crc32c_hw.restype = C.c_uint32
+    return int(_lib_crc.crc32c_hw(data, len(data)))

@@ -98,6 +98,18 @@ def test_estimate_parameters_table():
         assert py.estimate_parameters(n, p) == want
 
 
+@pytest.mark.skipif(not canon.crc32c_hw_available(), reason="no SSE4.2 crc32 instruction / gcc on this host")
+def test_crc32c_matches_the_cpu_instruction():
+    """THIRD-PARTY PIN: the oracle's table-driven CRC32C (the checksum of every filter section,
+    file_format.go:44,379,399: crc32.Checksum(payload, Castagnoli)) against the CPU's SSE4.2 crc32
+    instruction, for every length 0..300, long buffers and the standard check value."""
+    assert canon.crc32c_hw(b"123456789") == 0xE3069283
+    rng = random.Random(5)
+    for L in list(range(0, 301)) + [1000, 4096, 65537, 1 << 20]:
+        d = bytes(rng.getrandbits(8) for _ in range(L)) if L <= 65537 else rng.randbytes(L)
+        assert cref.crc32c(d) == canon.crc32c_hw(d), L
+
+
 def test_crc32c_check_value():
     assert cref.crc32c(b"123456789") == 0xE3069283 == py.crc32c(b"123456789")
     rng = random.Random(1)
