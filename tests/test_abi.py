@@ -103,3 +103,58 @@ def test_go_shim_and_cpp_host_bind_only_declared_entry_points():
         if fn.endswith((".cpp", ".hpp")):
             cpp_calls |= set(re.findall(r"\b(bsg_[a-z_0-9]+)\s*\(", open(os.path.join(host_dir, fn)).read()))
     assert cpp_calls and cpp_calls <= declared, sorted(cpp_calls - declared)
+
+
+def _declared_arity():
+    """name -> number of parameters, from include/bloomgpu.h."""
+    hdr = open(os.path.join(ROOT, "include", "bloomgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(bsg_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def _call_arities(src, prefix):
+    """(name, number of arguments) of every `<prefix>bsg_xxx(...)` call in src (top-level commas)."""
+    out = []
+    for m in re.finditer(prefix + r"(bsg_[a-z_0-9]+)\s*\(", src):
+        i, depth, commas, empty = m.end(), 1, 0, True
+        while depth and i < len(src):
+            c = src[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+            elif c == "," and depth == 1:
+                commas += 1
+            if depth and not c.isspace():
+                empty = False
+            i += 1
+        out.append((m.group(1), 0 if empty else commas + 1))
+    return out
+
+
+def test_bindings_pass_as_many_arguments_as_the_header_declares():
+    """Signature drift check for the bindings nothing here compiles or type-checks: every cgo call in
+    go/bloomgpu (no Go toolchain in the image) and every ctypes argtypes list in _native.py must have exactly
+    the number of parameters include/bloomgpu.h declares for that entry point."""
+    decl = _declared_arity()
+    assert len(decl) >= 60
+    bad = []
+    n_calls = 0
+    for fn in sorted(os.listdir(os.path.join(ROOT, "go", "bloomgpu"))):
+        if fn.endswith(".go"):
+            src = re.sub(r"//.*", "", open(os.path.join(ROOT, "go", "bloomgpu", fn)).read())
+            for name, n in _call_arities(src, r"\bC\."):
+                if name in decl:
+                    n_calls += 1
+                    if decl[name] != n:
+                        bad.append((fn, name, n, decl[name]))
+    assert n_calls >= 20 and not bad, bad
+    lib = N.lib()
+    for name, n in decl.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
