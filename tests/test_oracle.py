@@ -78,6 +78,22 @@ def test_fixture_base_hashes_match_canonical_murmurhash3():
         assert tuple(int(x, 16) for x in e["h"]) == canon.base_hashes(key), e["key"]
 
 
+def test_committed_third_party_vectors():
+    """tests/golden/canonical_vectors.json was written by third-party code only (make_canonical_vectors.py: the
+    canonical MurmurHash3.cpp and the CPU's crc32 instruction); it needs neither of them at test time, so this
+    pin holds on any box.  Both restatements must reproduce every vector."""
+    g = json.load(open(os.path.join(GOLDEN, "canonical_vectors.json")))
+    assert len(g["base_hashes"]) >= 80 and len(g["crc32c"]) >= 40
+    for e in g["base_hashes"]:
+        key = bytes.fromhex(e["key_hex"])
+        want = tuple(int(x, 16) for x in e["h"])
+        assert tuple(cref.base_hashes(key)) == want, e["key_hex"]
+        assert tuple(py.base_hashes(key)) == want, e["key_hex"]
+    for e in g["crc32c"]:
+        assert cref.crc32c(bytes.fromhex(e["data_hex"])) == int(e["crc"], 16)
+        assert py.crc32c(bytes.fromhex(e["data_hex"])) == int(e["crc"], 16)
+
+
 def test_location_pattern():
     # h0; h1+h3; h0+2h3; h1+3h2; h0+4h2; h1+5h3; h0+6h3; h1+7h2 (SURVEY §8c)
     h = (3, 5, 7, 11)
