@@ -250,6 +250,12 @@ uint32_t bref_crc32c(const uint8_t *data, size_t len) {
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("sse4.2")) return crc32c_hw(data, len);
 #endif
+    return bref_crc32c_sw(data, len);
+}
+
+/* The restated algorithm proper (table-driven); bref_crc32c falls back to it where the instruction is missing,
+ * and tests/test_oracle.py checks it against the instruction (oracle/pins/crc32c_hw.c) where it is present. */
+uint32_t bref_crc32c_sw(const uint8_t *data, size_t len) {
     pthread_once(&crc_once, crc32c_init);
     uint32_t c = 0xFFFFFFFFu;
     while (len >= 8) { /* slicing-by-8, comparable to Go's software path */

@@ -85,7 +85,8 @@ bref_filter *bref_build_sized_filter(const uint8_t *bytes, const uint64_t *key_o
                                      uint64_t n_keys, double fpr);
 
 /* ---- file_format.go:343-448 filter section codec ----------------------- */
-uint32_t bref_crc32c(const uint8_t *data, size_t len);
+uint32_t bref_crc32c(const uint8_t *data, size_t len);     /* SSE4.2 instruction where present (as Go does), else _sw */
+uint32_t bref_crc32c_sw(const uint8_t *data, size_t len);  /* table-driven, slicing-by-8 */
 /* filters[3] = field, token, fieldtoken; NULL entry = absent. returns bytes written
  * (call with out==NULL to size). */
 size_t bref_section_encode(const bref_filter *const filters[3], uint8_t *out);

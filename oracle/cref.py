@@ -85,6 +85,8 @@ def lib():
     L.bref_build_sized_filter.restype = vp
     L.bref_crc32c.argtypes = [C.c_char_p, C.c_size_t]
     L.bref_crc32c.restype = C.c_uint32
+    L.bref_crc32c_sw.argtypes = [C.c_char_p, C.c_size_t]
+    L.bref_crc32c_sw.restype = C.c_uint32
     L.bref_section_encode.argtypes = [C.POINTER(vp), vp]
     L.bref_section_encode.restype = C.c_size_t
     L.bref_section_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
@@ -149,6 +151,11 @@ def estimate_parameters(n: int, p: float):
 
 def crc32c(data: bytes) -> int:
     return lib().bref_crc32c(data, len(data))
+
+
+def crc32c_sw(data: bytes) -> int:
+    """The table-driven path alone (bref_crc32c takes the SSE4.2 instruction where the host has it)."""
+    return lib().bref_crc32c_sw(data, len(data))
 
 
 class Filter:

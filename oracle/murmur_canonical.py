@@ -1,7 +1,7 @@
 """ctypes bindings of the third-party pins under oracle/_ref/ — TEST INFRASTRUCTURE ONLY.
 
 (1) libmurmur3_canonical.so, below; (2) libcrc32c_hw.so: CRC32C computed by the CPU's SSE4.2 `crc32`
-instruction (oracle/pins/crc32c_hw.c), against which the oracle's table-driven CRC32C is checked — the
+instruction (oracle/pins/crc32c_hw.c), against which the oracle's table-driven CRC32C (bref_crc32c_sw) and the Python twin are checked — the
 checksum of every filter section (/root/reference/file_format.go:44,379,399).
 
 The library is Austin Appleby's canonical MurmurHash3.cpp (public domain; the SMHasher source),

@@ -2,7 +2,7 @@
  * crc32.MakeTable(crc32.Castagnoli), /root/reference/file_format.go:44,379,399) computed by the CPU's own
  * SSE4.2 `crc32` instruction — an implementation nobody here wrote.  crc32.Checksum starts from ^0 and
  * returns ^state, which is what this does.  tests/test_oracle.py compares oracle/bloomref.c's table-driven
- * bref_crc32c with it; the device CRC (csrc/kernels_sections.cu) is compared with the oracle by the GPU tests. */
+ * bref_crc32c_sw (and the Python twin) with it; the device CRC (csrc/kernels_sections.cu) is compared with the oracle by the GPU tests. */
 #include <nmmintrin.h>
 #include <stddef.h>
 #include <stdint.h>

@@ -90,6 +90,7 @@ def test_committed_third_party_vectors():
         assert tuple(cref.base_hashes(key)) == want, e["key_hex"]
         assert tuple(py.base_hashes(key)) == want, e["key_hex"]
     for e in g["crc32c"]:
+        assert cref.crc32c_sw(bytes.fromhex(e["data_hex"])) == int(e["crc"], 16)
         assert cref.crc32c(bytes.fromhex(e["data_hex"])) == int(e["crc"], 16)
         assert py.crc32c(bytes.fromhex(e["data_hex"])) == int(e["crc"], 16)
 
@@ -116,14 +117,20 @@ def test_estimate_parameters_table():
 
 @pytest.mark.skipif(not canon.crc32c_hw_available(), reason="no SSE4.2 crc32 instruction / gcc on this host")
 def test_crc32c_matches_the_cpu_instruction():
-    """THIRD-PARTY PIN: the oracle's table-driven CRC32C (the checksum of every filter section,
-    file_format.go:44,379,399: crc32.Checksum(payload, Castagnoli)) against the CPU's SSE4.2 crc32
-    instruction, for every length 0..300, long buffers and the standard check value."""
-    assert canon.crc32c_hw(b"123456789") == 0xE3069283
+    """THIRD-PARTY PIN: the oracle's table-driven CRC32C (bref_crc32c_sw: the restated algorithm; the checksum
+    of every filter section, file_format.go:44,379,399: crc32.Checksum(payload, Castagnoli)) and the Python
+    twin's against the CPU's SSE4.2 crc32 instruction, for every length 0..300, long buffers and the standard
+    check value.  (bref_crc32c itself takes the instruction where the host has it, as Go's hash/crc32 does — so
+    the comparison that means something is the software path's.)"""
+    assert canon.crc32c_hw(b"123456789") == 0xE3069283 == cref.crc32c_sw(b"123456789")
     rng = random.Random(5)
     for L in list(range(0, 301)) + [1000, 4096, 65537, 1 << 20]:
         d = bytes(rng.getrandbits(8) for _ in range(L)) if L <= 65537 else rng.randbytes(L)
-        assert cref.crc32c(d) == canon.crc32c_hw(d), L
+        want = canon.crc32c_hw(d)
+        assert cref.crc32c_sw(d) == want, L
+        assert cref.crc32c(d) == want, L
+        if L <= 4096:
+            assert py.crc32c(d) == want, L
 
 
 def test_crc32c_check_value():
